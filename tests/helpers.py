@@ -1,0 +1,38 @@
+"""Shared helpers for the parity tests."""
+import glob
+import os
+
+import numpy as np
+
+from raytracing_b200 import scene_io
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+_scene_cache = {}
+
+
+def scene(name):
+    if name not in _scene_cache:
+        _scene_cache[name] = scene_io.load_scene(name)
+    return _scene_cache[name]
+
+
+def golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN, "golden_*.npz.xz")))
+
+
+def load_golden(path):
+    g = scene_io.load_npz_xz(path)
+    base = os.path.basename(path)[len("golden_"):]
+    # file name: golden_<scene>_<w>x<h>_b<mb>[_wf].npz.xz
+    stem = base.replace(".npz.xz", "")
+    parts = stem.split("_")
+    if parts[-1] == "wf":
+        parts = parts[:-1]
+    g["scene_name"] = "_".join(parts[:-2])
+    return g
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype="<f4").view("<u4")

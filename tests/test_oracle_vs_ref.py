@@ -1,0 +1,61 @@
+"""
+CPU tests (-m "not gpu"), only where oracle/_ref/libref.so exists (built from /root/reference
+by oracle/build_ref.py): the oracle restatement against the reference's own kernels, LIVE,
+on configurations other than the committed golden ones (different resolution / bounce
+count / sample index / options).  Bar: bit-exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import refbind
+from oracle.orcbind import Oracle
+from raytracing_b200.camera import default_camera
+from tests.helpers import bits, scene
+
+pytestmark = pytest.mark.skipif(not refbind.available(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+@pytest.mark.parametrize("name,w,h,mb,wf", [
+    ("CornellBox", 97, 61, 3, False),
+    ("CornellBox", 64, 64, 5, True),
+    ("ShaderBalls", 160, 90, 8, False),
+    ("CornellBox_Dragon", 120, 68, 6, False),
+])
+def test_oracle_bit_exact_vs_reference_kernels(name, w, h, mb, wf):
+    sc = scene(name)
+    r = refbind.RefRenderer().open_arrays(sc)
+    r.begin(w, h)
+    cam = default_camera(w, h)
+    r.set_camera(cam)
+    r.set_max_bounces(mb)
+    r.enable_white_furnace(wf)
+    o = Oracle(sc)
+    acc = np.zeros((h, w, 4), dtype="<f4")
+    for sample in range(2):                     # progressive accumulation: sample_idx 0 then 1
+        r.integrate()
+        acc, hits, st = o.render(cam, w, h, mb, sample_idx=sample, white_furnace=wf, radiance=acc)
+        rs = r.stats()
+        for k in ("n_ext", "n_miss", "n_hit", "n_shadow", "n_cont", "n_unoccluded"):
+            assert np.array_equal(st[k][: mb + 1], rs[k][: mb + 1]), (k, sample)
+        assert np.array_equal(hits["primitive_id"], r.primary_hits()["primitive_id"])
+        assert np.array_equal(bits(acc[..., :3]), bits(r.radiance()[..., :3]))
+    r.close()
+
+
+def test_math_library_sensitivity_is_small():
+    """The OpenCL driver's libm is unpinned.  Swapping include/rt_math.h for glibc's libm inside the
+    reference kernels must leave all but a small fraction of pixels within 1e-4 relative."""
+    if not refbind.available(libm=True):
+        pytest.skip("libref_libm.so not built")
+    sc = scene("ShaderBalls")
+    w, h, mb = 160, 90, 8
+    cam = default_camera(w, h)
+    imgs = []
+    for libm in (False, True):
+        r = refbind.RefRenderer(libm=libm).open_arrays(sc)
+        r.begin(w, h); r.set_camera(cam); r.set_max_bounces(mb); r.integrate()
+        imgs.append(r.radiance()[..., :3].astype(np.float64)); r.close()
+    a, b = imgs
+    rel = np.abs(a - b) / np.maximum(np.abs(a), 1e-6)
+    frac_bad = (rel.max(axis=-1) > 1e-4).mean()
+    assert frac_bad < 0.02, frac_bad
