@@ -1,0 +1,329 @@
+#!/usr/bin/env python3
+"""
+bench.py — headline benchmark of the B200 wavefront path tracer.
+
+Metric (BASELINE.json): Mrays/s at 1920x1080, 8 bounces, 1 sample per pixel, where
+  rays = sum_b N_ext[b] + sum_b N_shadow[b]   (rays actually submitted to BVH traversal)
+A "step" is one frame: Reset + Integrate with sample_idx = 0, so every step traces identical rays.
+
+  python bench.py --gpus N --steps K --warmup W [--scene CornellBox] [--impl reference]
+
+One process per GPU (torchrun for N > 1): the image is partitioned by scanline (row y -> rank y % N,
+weak in nothing: total work fixed => "strong" scaling), each rank runs the whole wavefront on its rows,
+and ONE NCCL gather of the radiance slabs to rank 0 ends the frame (inside the timed region).
+
+The JSON line carries: value (HBM-resident, device-timed, max over ranks), e2e (through the public API with
+host buffers: camera upload + frame + resolve + device->host image), roofline (dominant kernel, algorithmic
+bytes / CUDA-event time vs MEASURED_PEAKS.json), cpu_baseline (the reference's own kernels compiled for the
+CPU, oracle/_ref, or the oracle port), clocks sampled during the timed region, gpu_launches.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (scene, width, height, max_bounces)
+    "CornellBox": ("CornellBox", 1920, 1080, 8),          # BASELINE configs[1] — the headline
+    "ShaderBalls": ("ShaderBalls", 1920, 1080, 8),        # configs[2]
+    "CornellBox_Dragon": ("CornellBox_Dragon", 3840, 2160, 16),   # configs[3]
+}
+
+
+def algorithmic_bytes(st, mb, n_pix):
+    """compulsory traffic of the reference layout, from per-bounce counters.
+    Returns (total bytes per frame, bytes attributable to the fused extend+shade kernel)."""
+    s = lambda k: st[k][: mb + 1].astype(np.float64)
+    n_ext, n_miss, n_shadow, n_cont = s("n_ext"), s("n_miss"), s("n_shadow"), s("n_cont")
+    n_hit = n_ext - n_miss
+    n_unocc, n_emis = s("n_unoccluded"), s("n_emissive_hits")
+    v_ext, t_ext, v_sh, t_sh = s("nodes_ext"), s("tris_ext"), s("nodes_shadow"), s("tris_shadow")
+    raygen = 52.0 * n_pix
+    extend = (48 * n_ext + 48 * (v_ext + t_ext) + 52 * n_miss + 264 * n_hit + 52 * n_shadow + 36 * n_cont + 32 * n_emis).sum()
+    shadow = (36 * n_shadow + 48 * (v_sh + t_sh) + 4 * n_shadow + 52 * n_unocc).sum()
+    return raygen + extend + shadow, extend, shadow
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def cpu_reference_frame(scene, cam, w, h, mb, budget_s, threads):
+    """Times the reference's CPU implementation of the path (oracle/_ref if built, else the oracle port) on a bounded
+    sample: rows y % step == 0 of the same frame.  Returns (Mrays/s, kind, cores, sample description, seconds)."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    from oracle import refbind
+    from oracle.orcbind import Oracle
+    use_ref = refbind.available()
+    o = Oracle(scene)
+    # probe on a sparse sample to size the bounded one (the port and _ref are bit-identical; the port is the cheaper probe)
+    t0 = time.perf_counter()
+    _, _, st = o.render(cam, w, h, mb, row_first=0, row_step=64, want_hits=False)
+    probe = time.perf_counter() - t0
+    est_full = probe * 64 * (4.0 if use_ref else 1.0)
+    step = max(1, int(np.ceil(est_full / budget_s)))
+    if use_ref:
+        r = refbind.RefRenderer().open_arrays(scene)
+        r.begin(w, h); r.set_camera(cam); r.set_max_bounces(mb)
+        r.set_row_sample(0, step)
+        t0 = time.perf_counter(); r.integrate(); dt = time.perf_counter() - t0
+        s = r.stats()
+        rays = float(s["n_ext"][: mb + 1].sum() + s["n_shadow"][: mb + 1].sum())
+        r.close()
+        kind = "reference"
+    else:
+        t0 = time.perf_counter()
+        _, _, st = o.render(cam, w, h, mb, row_first=0, row_step=step, want_hits=False)
+        dt = time.perf_counter() - t0
+        rays = float(st["n_ext"][: mb + 1].sum() + st["n_shadow"][: mb + 1].sum())
+        kind = "port"
+    rows = len(range(0, h, step))
+    sample = f"rows y%{step}==0 of the {w}x{h}x{mb}-bounce frame ({rows} rows, {rays / 1e6:.2f} Mrays), OpenMP over work-items"
+    return rays / dt / 1e6, kind, threads, sample, dt
+
+
+def run_reference_arm(args, workload):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from raytracing_b200 import scene_io
+    from raytracing_b200.camera import default_camera
+    name, w, h, mb = workload
+    scene = scene_io.load_scene(name)
+    cam = default_camera(w, h)
+    cores = os.cpu_count() or 1
+    total_budget = 150.0
+    per_step = max(2.0, total_budget / (args.steps + args.warmup))
+    vals, info = [], None
+    for i in range(args.warmup + args.steps):
+        v, kind, c, sample, dt = cpu_reference_frame(scene, cam, w, h, mb, per_step, cores)
+        if i >= args.warmup:
+            vals.append((v, dt))
+        info = (kind, c, sample)
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    line = {
+        "impl": "reference", "metric": "Mrays/sec @1920x1080x8-bounce", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name} {w}x{h} 1spp {mb}-bounce, default camera, sample_idx 0", "device": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": info[1], "kind": info[0], "sample": info[2]},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="CornellBox", choices=sorted(WORKLOADS))
+    ap.add_argument("--stepwise", action="store_true", help="time the one-kernel-per-reference-step schedule instead of the fused one")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    workload = WORKLOADS[args.scene]
+    if args.impl == "reference":
+        run_reference_arm(args, workload)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from raytracing_b200 import capi, scene_io
+    from raytracing_b200.camera import default_camera
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the render path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    name, w, h, mb = workload
+    scene = scene_io.load_scene(name)
+    cam = default_camera(w, h)
+    ctx = capi.Context(w, h, device=local_rank, rank=rank, world=world)
+    ctx.upload_scene(scene)
+    ctx.set_camera(cam)
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
+
+    # the local radiance slab as a torch tensor (zero copy) for the NCCL gather
+    ptr, nbytes = ctx.radiance_device_ptr()
+    n_local = ctx.local_pixel_count()
+
+    class _Slab:
+        __cuda_array_interface__ = {"shape": (n_local, 4), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+    slab = torch.as_tensor(_Slab(), device=torch.device("cuda", local_rank))
+    rows_max = (h + world - 1) // world
+    gathered = None
+    if world > 1:
+        send = torch.zeros((rows_max * w, 4), dtype=torch.float32, device=slab.device)
+        gathered = [torch.zeros_like(send) for _ in range(world)] if rank == 0 else None
+
+    def frame():
+        ctx.reset()
+        if args.stepwise:
+            ctx.integrate_stepwise(mb)
+        else:
+            ctx.integrate(mb)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                send[: n_local].copy_(slab)
+                dist.gather(send, gathered, dst=0)          # the ONE collective of the frame
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- one instrumented frame (untimed): per-bounce counters incl. traversal work -> rays/frame, algorithmic bytes
+    ctx.set_option(capi.OPT_COUNT_TRAVERSAL, 1)
+    ctx.reset(); ctx.integrate(mb); ctx.sync()
+    st = ctx.frame_stats()
+    ctx.set_option(capi.OPT_COUNT_TRAVERSAL, 0)
+    counters = torch.tensor([float(st[k][: mb + 1].sum()) for k in ("n_ext", "n_shadow")] +
+                            list(algorithmic_bytes(st, mb, n_local)), dtype=torch.float64, device=slab.device)
+    if world > 1:
+        dist.all_reduce(counters)
+    rays_per_frame = float(counters[0] + counters[1])
+    alg_total, alg_extend, alg_shadow = float(counters[2]), float(counters[3]), float(counters[4])
+
+    # ---- warm-up, then K timed steps: barrier + synchronize on both sides, CUDA events on the launching stream
+    for _ in range(args.warmup):
+        frame()
+    barrier()
+    launches0 = ctx.launch_count()
+    ctx.set_option(capi.OPT_KERNEL_TIMING, 1)
+    ctx.kernel_times()
+    sampler = ClockSampler(local_rank); sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        frame()
+    ev1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=slab.device)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms_total[0]) / args.steps
+    ktimes = ctx.kernel_times()
+    ctx.set_option(capi.OPT_KERNEL_TIMING, 0)
+    launches = ctx.launch_count() - launches0
+    sampler.join(timeout=2)
+    value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the public API with HOST buffers: camera H2D, frame, gather, resolve, image D2H
+    host_img = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory()
+    host_np = host_img.numpy()
+    cam_host = np.ascontiguousarray(cam)
+
+    def e2e_frame():
+        ctx.set_camera(cam_host)                       # per-frame input (render.cpp:188): 64 B host -> device (kernel parameter)
+        frame()
+        ctx.resolve(host_np)                           # resolve + device->host of this rank's rows; blocks
+    for _ in range(2):
+        e2e_frame()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        e2e_frame()
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64, device=slab.device)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = rays_per_frame / (float(e2e_ms[0]) * 1e-3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        dom = "shadow_accumulate" if ktimes["shadow_accumulate"][0] > ktimes["extend_shade"][0] else "extend_shade"
+        if args.stepwise:
+            dom = "intersect"
+        dom_ms, dom_n = ktimes[dom]
+        dom_bytes_frame = {"extend_shade": alg_extend, "shadow_accumulate": alg_shadow, "intersect": alg_extend}[dom] / world
+        achieved = (dom_bytes_frame * args.steps / (dom_ms * 1e-3) / 1e9) if dom_ms > 0 else None
+        line = {
+            "metric": "Mrays/sec @1920x1080x8-bounce", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{name} {w}x{h} 1spp {mb}-bounce, default camera, sample_idx 0, Reset+Integrate per step",
+                       "schedule": "stepwise" if args.stepwise else "fused", "partition": f"scanline y%{world}",
+                       "rays_per_step": rays_per_frame,
+                       "l2": "per-step working set (ray/shadow queues + radiance, ~365 MB at 1080p) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_ms[0]), "h2d_bytes_per_step": 64,
+                    "d2h_bytes_per_step": int(ctx.local_pixel_count()) * 16},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": alg_total, "kernel_algorithmic_bytes_per_step": dom_bytes_frame,
+                         "kernel_ms_per_step": dom_ms / args.steps, "kernel_launches_per_step": dom_n / args.steps,
+                         "whole_frame_algorithmic_GBs": alg_total / (ms_per_step * 1e-3) / 1e9},
+            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline:
+            v, kind, cores, sample, _ = cpu_reference_frame(scene, cam, w, h, mb, 15.0, os.cpu_count() or 1)
+            line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample}
+        print(json.dumps(line))
+    ctx.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

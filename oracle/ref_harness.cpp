@@ -142,7 +142,17 @@ protected:
     {
         refk_RayGeneration_std(N(), width_, height_, &cur_camera_, sample_counter_.p, rays_[0].p, ray_counter_[0].p,
             pixel_indices_[0].p, throughputs_.p, diffuse_albedo_.p, depth_.p, normal_.p, velocity_.p);
+        if (row_step_ > 1)
+        {   // bounded sample for CPU timing (bench.py): keep only the rays of rows y % step == first.  This is a
+            // host-side edit of the ray queue between two kernels; no kernel is modified.
+            Ray* r = (Ray*)rays_[0].p; std::uint32_t* pi = (std::uint32_t*)pixel_indices_[0].p;
+            std::uint32_t n = 0;
+            for (std::uint32_t y = row_first_; y < height_; y += row_step_)
+                for (std::uint32_t x = 0; x < width_; ++x) { r[n] = r[(size_t)y * width_ + x]; pi[n] = y * width_ + x; ++n; }
+            *(std::uint32_t*)ray_counter_[0].p = n;
+        }
     }
+    public: std::uint32_t row_first_ = 0, row_step_ = 1; protected:
     void IntersectRays(std::uint32_t bounce) override
     {
         int in = bounce & 1;
@@ -332,6 +342,7 @@ void ref_enable_white_furnace(void* handle, int e) { ((RefHandle*)handle)->integ
 void ref_set_sampler(void* handle, int blue_noise) { ((RefHandle*)handle)->integrator->SetSamplerType(blue_noise ? Integrator::SamplerType::kBlueNoise : Integrator::SamplerType::kRandom); }
 void ref_enable_denoiser(void* handle, int e) { ((RefHandle*)handle)->integrator->EnableDenoiser(e != 0); }
 void ref_set_aov(void* handle, int aov) { ((RefHandle*)handle)->integrator->SetAOV((Integrator::AOV)aov); }
+void ref_set_row_sample(void* handle, std::uint32_t first, std::uint32_t step) { auto& it = *((RefHandle*)handle)->integrator; it.row_first_ = first; it.row_step_ = step ? step : 1; }
 void ref_request_reset(void* handle) { ((RefHandle*)handle)->integrator->RequestReset(); }
 void ref_integrate(void* handle) { ((RefHandle*)handle)->integrator->Integrate(); }
 

@@ -47,6 +47,7 @@ class RefRenderer:
             getattr(L, name).argtypes = [C.c_void_p, C.c_int]
         for name in ("ref_request_reset", "ref_integrate", "ref_close"):
             getattr(L, name).argtypes = [C.c_void_p]
+        L.ref_set_row_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         L.ref_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         self.h = None
         self.width = self.height = 0
@@ -96,6 +97,7 @@ class RefRenderer:
     def set_blue_noise(self, e): self.lib.ref_set_sampler(self.h, int(e))
     def enable_denoiser(self, e): self.lib.ref_enable_denoiser(self.h, int(e))
     def set_aov(self, a): self.lib.ref_set_aov(self.h, int(a))
+    def set_row_sample(self, first, step): self.lib.ref_set_row_sample(self.h, first, step)
     def request_reset(self): self.lib.ref_request_reset(self.h)
     def integrate(self): self.lib.ref_integrate(self.h)
 

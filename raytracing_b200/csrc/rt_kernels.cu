@@ -1,0 +1,1166 @@
+/*
+ * rt_kernels.cu — the sm_100a kernels of the wavefront path tracer and the C ABI
+ * (include/rt_b200.h) that launches them.  One translation unit so that the shading
+ * code inlines into both the stepwise kernels (one per reference kernel) and the fused
+ * ones.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see
+ * __graft_entry__.build()).  There is no CPU fallback anywhere in this file.
+ *
+ * Data layout in HBM (all SoA streams of float4, indexed by compacted ray slot):
+ *   extension-ray queue q[b&1]:  A = (origin.xyz, pixel_idx bits)
+ *                                B = (dir.xyz, t_max)
+ *                                C = (path throughput.xyz, -)
+ *   shadow-ray queue:            A = (origin.xyz, pixel_idx bits)
+ *                                B = (dir.xyz, t_max = distance to light)
+ *                                C = (light sample.xyz, -)
+ *   hits (stepwise path only):   (bc.x, bc.y, primitive_id bits, t)
+ *   radiance:                    float4 per LOCAL pixel (scanline partition, see rt_set_partition)
+ * The reference keeps throughput in a per-pixel buffer that every bounce scatters to
+ * (hit_surface.cl:105,166); there is at most one live path per pixel, so carrying it in
+ * the ray stream is equivalent and turns the scatter into a coalesced stream.
+ * Ray counters are per bounce (q_count[b], shadow_count[b]): nothing has to be cleared
+ * between kernels (the reference launches two 1-thread clear kernels per bounce,
+ * integrator.cpp:45-46) and the per-bounce statistics fall out for free.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_b200.h"
+#include "rt_bvh_layout.h"
+#include "rt_device.cuh"
+
+using namespace rt;
+
+namespace
+{
+
+// ------------------------------------------------------------------------------------ device state
+struct DevCounters
+{
+    uint32_t q_count[RT_MAX_BOUNCES + 2];        // rays entering bounce b
+    uint32_t shadow_count[RT_MAX_BOUNCES + 1];
+    uint32_t n_miss[RT_MAX_BOUNCES + 1];
+    uint32_t n_emissive[RT_MAX_BOUNCES + 1];
+    uint32_t n_unoccluded[RT_MAX_BOUNCES + 1];
+    uint32_t work_ext[RT_MAX_BOUNCES + 1];       // persistent-kernel work cursors
+    uint32_t work_shadow[RT_MAX_BOUNCES + 1];
+    unsigned long long nodes_ext[RT_MAX_BOUNCES + 1], tris_ext[RT_MAX_BOUNCES + 1];
+    unsigned long long nodes_shadow[RT_MAX_BOUNCES + 1], tris_shadow[RT_MAX_BOUNCES + 1];
+};
+
+struct Queues
+{
+    float4* A[2]; float4* B[2]; float4* C[2];
+    float4* sA; float4* sB; float4* sC;
+    float4* hits;
+    uint32_t* shadow_flags;
+};
+
+struct FrameParams
+{
+    uint32_t width, height, rank, world, n_local, sample_idx;
+    int white_furnace;
+};
+
+__device__ __forceinline__ uint32_t local_index(const FrameParams& p, uint32_t px, uint32_t py)
+{
+    return (py / p.world) * p.width + px;
+}
+
+// warp-aggregated append: one atomic per warp, lanes get consecutive slots (coalesced stores).
+// Must be called by all 32 lanes of the warp.
+__device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred)
+{
+    unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return 0;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void warp_count(uint32_t* counter, bool pred)
+{
+    unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask != 0 && (threadIdx.x & 31) == __ffs(mask) - 1) atomicAdd(counter, (uint32_t)__popc(mask));
+}
+
+__device__ __forceinline__ void warp_sum64(unsigned long long* counter, uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(counter, (unsigned long long)v);
+}
+
+// ------------------------------------------------------------------------------------ traversal
+// Literal restatement of kernels/cl/trace_bvh.cl:99-211 on the reference node layout: per-ray
+// DFS, 64-entry private stack, far child pushed unconditionally and box-tested when popped,
+// near child chosen by ray_sign[axis], inclusive tests, later equal-t hit overwrites, back-face
+// culling (det < 1e-8 rejects).  ANY = the -D SHADOW_RAYS variant (returns 0 on first hit).
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ uint32_t trace_literal(const DevScene& sc, f3 o, f3 d, float t_min, float t_max,
+                                                  float& bu, float& bv, float& bt, uint32_t& nv, uint32_t& nt)
+{
+    f3 inv = splat(1.0f) / d;
+    int sx = inv.x < 0, sy = inv.y < 0, sz = inv.z < 0;
+    uint32_t prim = RT_INVALID_ID;
+    int to_visit = 0, cur = 0;
+    int stack[64];
+    for (;;)
+    {
+        float4 n0 = __ldg(sc.nodes_ref + (size_t)cur * 3), n1 = __ldg(sc.nodes_ref + (size_t)cur * 3 + 1), n2 = __ldg(sc.nodes_ref + (size_t)cur * 3 + 2);
+        if (COUNT) ++nv;
+        f3 t0 = (mk3(n0) - o) * inv, t1 = (mk3(n1) - o) * inv;
+        float lo = fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z));
+        float hi = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
+        bool box = fminf(hi, t_max) >= fmaxf(lo, t_min);
+        uint32_t offset = __float_as_uint(n2.x), npa = __float_as_uint(n2.y);
+        if (box)
+        {
+            int nprims = (int)(npa >> 16);
+            if (nprims > 0)
+            {
+                for (int i = 0; i < nprims; ++i)
+                {
+                    const float4* tp = sc.tris_ref + (size_t)(offset + i) * 3;
+                    f3 p1 = mk3(__ldg(tp)), p2 = mk3(__ldg(tp + 1)), p3 = mk3(__ldg(tp + 2));
+                    if (COUNT) ++nt;
+                    f3 e1 = p2 - p1, e2 = p3 - p1;
+                    f3 pvec = cross(d, e2);
+                    float det = dot(e1, pvec);
+                    if (det < 1e-8f || -det > 1e-8f) continue;
+                    float inv_det = 1.0f / det;
+                    f3 tvec = o - p1;
+                    float u = dot(tvec, pvec) * inv_det;
+                    if (u < 0.0f || u > 1.0f) continue;
+                    f3 qvec = cross(tvec, e1);
+                    float v = dot(d, qvec) * inv_det;
+                    if (v < 0.0f || u + v > 1.0f) continue;
+                    float t = dot(e2, qvec) * inv_det;
+                    if (t < t_min || t > t_max) continue;
+                    bu = u; bv = v; bt = t;
+                    prim = offset + i;
+                    t_max = t;
+                    if (ANY) return 0u;
+                }
+                if (to_visit == 0) break;
+                cur = stack[--to_visit];
+            }
+            else
+            {
+                uint32_t axis = npa & 0xFFFFu;
+                int s = axis == 0 ? sx : (axis == 1 ? sy : sz);
+                if (s) { stack[to_visit++] = cur + 1; cur = (int)offset; }
+                else   { stack[to_visit++] = (int)offset; cur = cur + 1; }
+            }
+        }
+        else
+        {
+            if (to_visit == 0) break;
+            cur = stack[--to_visit];
+        }
+    }
+    return prim;
+}
+
+// Optimised traversal on the child-box node layout (rt_bvh_layout.h).  Same visiting order and
+// the same arithmetic per box / triangle test as trace_literal, so results are bit-identical
+// for finite rays; non-finite rays (NaN/inf components; their traversal is garbage-in but must
+// still match) take the literal path.
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, f3 o, f3 d, float t_min, float t_max,
+                                               float& bu, float& bv, float& bt, uint32_t& nv, uint32_t& nt)
+{
+    float fin = ((o.x + o.y) + o.z) + ((d.x + d.y) + d.z);
+    if (!(fabsf(fin) <= 3.0e38f) || COUNT)
+        return trace_literal<ANY, COUNT>(sc, o, d, t_min, t_max, bu, bv, bt, nv, nt);
+
+    f3 inv = splat(1.0f) / d;
+    bool sx = inv.x < 0, sy = inv.y < 0, sz = inv.z < 0;
+    uint32_t prim = RT_INVALID_ID;
+    int sp = 0;
+    int cur = sc.root_ref;
+    int stack_ref[64];
+    float stack_t[64];
+    if (cur < 0)
+    {   // single-leaf tree: the root box is tested like any visited node
+        float4 r0 = __ldg(sc.nodes_ref), r1 = __ldg(sc.nodes_ref + 1);
+        f3 t0 = (mk3(r0) - o) * inv, t1 = (mk3(r1) - o) * inv;
+        float lo = fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z));
+        float hi = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
+        if (!(fminf(hi, t_max) >= fmaxf(lo, t_min))) return prim;
+    }
+    else
+    {   // root box test (the reference tests every node it visits, including the root)
+        float4 r0 = __ldg(sc.nodes_ref), r1 = __ldg(sc.nodes_ref + 1);
+        f3 t0 = (mk3(r0) - o) * inv, t1 = (mk3(r1) - o) * inv;
+        float lo = fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z));
+        float hi = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
+        if (!(fminf(hi, t_max) >= fmaxf(lo, t_min))) return prim;
+    }
+    for (;;)
+    {
+        while (cur >= 0)
+        {
+            const float4* np = sc.wnodes + (size_t)cur * 4;
+            float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2), m = __ldg(np + 3);
+            // child 0 box: min (a.x,a.y,a.z) max (a.w,b.x,b.y); child 1 box: min (b.z,b.w,c.x) max (c.y,c.z,c.w)
+            f3 t00 = (mk3(a.x, a.y, a.z) - o) * inv, t01 = (mk3(a.w, b.x, b.y) - o) * inv;
+            f3 t10 = (mk3(b.z, b.w, c.x) - o) * inv, t11 = (mk3(c.y, c.z, c.w) - o) * inv;
+            float lo0 = fmaxf(fmaxf(fmaxf(fminf(t00.x, t01.x), fminf(t00.y, t01.y)), fminf(t00.z, t01.z)), t_min);
+            float hi0 = fminf(fminf(fmaxf(t00.x, t01.x), fmaxf(t00.y, t01.y)), fmaxf(t00.z, t01.z));
+            float lo1 = fmaxf(fmaxf(fmaxf(fminf(t10.x, t11.x), fminf(t10.y, t11.y)), fminf(t10.z, t11.z)), t_min);
+            float hi1 = fminf(fminf(fmaxf(t10.x, t11.x), fmaxf(t10.y, t11.y)), fmaxf(t10.z, t11.z));
+            bool h0 = fminf(hi0, t_max) >= lo0, h1 = fminf(hi1, t_max) >= lo1;
+            int r0 = __float_as_int(m.x), r1 = __float_as_int(m.y);
+            uint32_t axis = __float_as_uint(m.z);
+            bool swap = axis == 0 ? sx : (axis == 1 ? sy : sz);       // near child = second iff inv_dir[axis] < 0
+            int near_ref = swap ? r1 : r0, far_ref = swap ? r0 : r1;
+            bool near_hit = swap ? h1 : h0, far_hit = swap ? h0 : h1;
+            float far_lo = swap ? lo0 : lo1;
+            if (near_hit)
+            {
+                if (far_hit) { stack_ref[sp] = far_ref; stack_t[sp] = far_lo; ++sp; }
+                cur = near_ref;
+            }
+            else if (far_hit) cur = far_ref;
+            else
+            {   // pop: a pushed far child is re-tested against the (possibly shrunk) t_max, as the
+                // reference does when it pops it; its slab interval was already valid at push time
+                bool found = false;
+                while (sp > 0) { --sp; if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; } }
+                if (!found) return prim;
+            }
+        }
+        // leaf: triangles [~cur ...] until the end-of-leaf flag
+        uint32_t ti = (uint32_t)(~cur);
+        for (;;)
+        {
+            const float4* tp = sc.wtris + (size_t)ti * 3;
+            float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+            f3 p1 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
+            bool last = __float_as_uint(q2.y) != 0u;
+            f3 pvec = cross(d, e2);
+            float det = dot(e1, pvec);
+            if (!(det < 1e-8f || -det > 1e-8f))
+            {
+                float inv_det = 1.0f / det;
+                f3 tvec = o - p1;
+                float u = dot(tvec, pvec) * inv_det;
+                if (!(u < 0.0f || u > 1.0f))
+                {
+                    f3 qvec = cross(tvec, e1);
+                    float v = dot(d, qvec) * inv_det;
+                    if (!(v < 0.0f || u + v > 1.0f))
+                    {
+                        float t = dot(e2, qvec) * inv_det;
+                        if (!(t < t_min || t > t_max))
+                        {
+                            bu = u; bv = v; bt = t; prim = ti; t_max = t;
+                            if (ANY) return 0u;
+                        }
+                    }
+                }
+            }
+            if (last) break;
+            ++ti;
+        }
+        bool found = false;
+        while (sp > 0) { --sp; if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; } }
+        if (!found) return prim;
+    }
+}
+
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ uint32_t trace(const DevScene& sc, int mode, f3 o, f3 d, float t_min, float t_max,
+                                          float& bu, float& bv, float& bt, uint32_t& nv, uint32_t& nt)
+{
+    if (mode == 0) return trace_literal<ANY, COUNT>(sc, o, d, t_min, t_max, bu, bv, bt, nv, nt);
+    return trace_fast<ANY, COUNT>(sc, o, d, t_min, t_max, bu, bv, bt, nv, nt);
+}
+
+// ------------------------------------------------------------------------------------ shading
+struct ShadeOut
+{
+    bool spawn_shadow, spawn_next, emissive;
+    f3 emission_add;
+    f3 s_origin, s_dir, s_sample; float s_tmax;
+    f3 n_origin, n_dir, n_throughput;
+};
+
+// kernels/cl/miss.cl:41-77: radiance += sky * throughput
+__device__ __forceinline__ void shade_miss(const DevScene& sc, const FrameParams& p, float4* radiance, uint32_t pixel, f3 dir, f3 throughput)
+{
+    f3 sky = p.white_furnace ? splat(0.5f) : sample_sky(sc, dir);
+    f3 add = sky * throughput;
+    uint32_t li = local_index(p, pixel % p.width, pixel / p.width);
+    float4 r = radiance[li];
+    r.x += add.x; r.y += add.y; r.z += add.z;
+    radiance[li] = r;
+}
+
+// kernels/cl/hit_surface.cl:30-186
+__device__ __forceinline__ void shade_hit(const DevScene& sc, const FrameParams& p, uint32_t bounce, uint32_t pixel,
+                                          f3 ray_dir, f3 hit_throughput, uint32_t prim, float u, float v, ShadeOut& out)
+{
+    f3 incoming = -ray_dir;
+    uint32_t px = pixel % p.width, py = pixel / p.width;
+    const float4* tp = sc.triangles + (size_t)prim * 10;
+    f3 p1 = mk3(__ldg(tp)), uv1 = mk3(__ldg(tp + 1)), n1 = mk3(__ldg(tp + 2));
+    f3 p2 = mk3(__ldg(tp + 3)), uv2 = mk3(__ldg(tp + 4)), n2 = mk3(__ldg(tp + 5));
+    f3 p3 = mk3(__ldg(tp + 6)), uv3 = mk3(__ldg(tp + 7)), n3 = mk3(__ldg(tp + 8));
+    uint32_t mtl = __float_as_uint(__ldg(tp + 9).x);
+    float w0 = 1.0f - u - v;
+    f3 position = p1 * w0 + p2 * u + p3 * v;
+    f3 geometry_normal = normalize(cross(p2 - p1, p3 - p1));
+    f2 texcoord; texcoord.x = uv1.x * w0 + uv2.x * u + uv3.x * v; texcoord.y = uv1.y * w0 + uv2.y * u + uv3.y * v;
+    f3 normal = normalize(n1 * w0 + n2 * u + n3 * v);
+    Material material = unpack_material(sc, mtl, texcoord);
+
+    out.emissive = false;
+    if (!p.white_furnace && dot(material.emission, splat(1.0f)) > 0.0f)
+    {
+        out.emissive = true;
+        out.emission_add = hit_throughput * material.emission;
+    }
+    uint32_t pixel_seed = sample_seed_pixel(px, py, p.sample_idx);
+    {   // direct lighting (next-event estimation on analytic lights)
+        float s_light = sample_random(pixel_seed, bounce, SAMPLE_LIGHT);
+        f3 outgoing; float pdf;
+        f3 light_radiance = light_sample(sc, position, s_light, outgoing, pdf);
+        float distance_to_light = length(outgoing);
+        outgoing = normalize(outgoing);
+        f3 brdf = evaluate_material(material, normal, incoming, outgoing);
+        f3 ls = light_radiance * hit_throughput * brdf / pdf * fmaxf(dot(outgoing, normal), 0.0f);
+        out.spawn_shadow = (pdf > 0.0f) && (dot(ls, ls) > 0.0f);
+        out.s_origin = position + normal * RT_EPS;
+        out.s_dir = outgoing; out.s_tmax = distance_to_light; out.s_sample = ls;
+    }
+    {   // BSDF sampling
+        f2 s; s.x = sample_random(pixel_seed, bounce, SAMPLE_U); s.y = sample_random(pixel_seed, bounce, SAMPLE_V);
+        float s1 = sample_random(pixel_seed, bounce, SAMPLE_LAYER);
+        float pdf = 0.0f, offset = 1.0f;
+        f3 outgoing = mk3(0.0f, 0.0f, 0.0f);
+        f3 bxdf = sample_bxdf(s1, s, material, normal, incoming, p.white_furnace != 0, outgoing, pdf, offset);
+        f3 throughput = splat(0.0f);
+        if (pdf > 0.0f) throughput = bxdf / pdf;
+        out.n_throughput = hit_throughput * throughput;
+        out.spawn_next = pdf > 0.0f;
+        out.n_origin = position + geometry_normal * RT_EPS * offset;
+        out.n_dir = outgoing;
+    }
+}
+
+// ------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(256) k_reset(float4* radiance, uint32_t n)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) radiance[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// raygeneration.cl:65-139.  One thread per LOCAL pixel; slot i of queue 0 = local pixel i.
+__global__ void __launch_bounds__(256) k_raygen(FrameParams p, RayGenConsts c, Queues q, DevCounters* ctr)
+{
+    uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li == 0) ctr->q_count[0] = p.n_local;
+    if (li >= p.n_local) return;
+    uint32_t px = li % p.width, py = (li / p.width) * p.world + p.rank;
+    uint32_t pixel = py * p.width + px;
+    f3 o, d;
+    generate_primary_ray(c, pixel, px, py, p.sample_idx, o, d);
+    q.A[0][li] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
+    q.B[0][li] = make_float4(d.x, d.y, d.z, RT_MAX_RENDER_DIST);
+    q.C[0][li] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+}
+
+// IntersectRays (stepwise): closest hit of every live ray of bounce b -> hits[]
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_intersect(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, uint32_t bounce)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = ctr->q_count[bounce];
+    int in = bounce & 1;
+    uint32_t nv = 0, nt = 0;
+    if (i < n)
+    {
+        float4 a = q.A[in][i], b = q.B[in][i];
+        float bu = 0.0f, bv = 0.0f, bt = 0.0f;
+        uint32_t prim = trace<false, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
+        q.hits[i] = make_float4(bu, bv, __uint_as_float(prim), bt);
+    }
+    if (COUNT) { warp_sum64(&ctr->nodes_ext[bounce], nv); warp_sum64(&ctr->tris_ext[bounce], nt); }
+}
+
+// ShadeMissedRays (stepwise)
+__global__ void __launch_bounds__(256) k_shade_miss(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = ctr->q_count[bounce];
+    int in = bounce & 1;
+    bool miss = false;
+    if (i < n)
+    {
+        float4 h = q.hits[i];
+        miss = __float_as_uint(h.z) == RT_INVALID_ID;
+        if (miss)
+        {
+            float4 a = q.A[in][i], b = q.B[in][i], c = q.C[in][i];
+            shade_miss(sc, p, radiance, __float_as_uint(a.w), mk3(b), mk3(c));
+        }
+    }
+    warp_count(&ctr->n_miss[bounce], miss);
+}
+
+__device__ __forceinline__ void emit_rays(const FrameParams& p, Queues& q, DevCounters* ctr, float4* radiance, uint32_t bounce,
+                                          uint32_t pixel, bool hit, const ShadeOut& so)
+{
+    int out = (bounce + 1) & 1;
+    if (hit && so.emissive)
+    {
+        uint32_t li = local_index(p, pixel % p.width, pixel / p.width);
+        float4 r = radiance[li];
+        r.x += so.emission_add.x; r.y += so.emission_add.y; r.z += so.emission_add.z;
+        radiance[li] = r;
+    }
+    warp_count(&ctr->n_emissive[bounce], hit && so.emissive);
+    bool ss = hit && so.spawn_shadow;
+    uint32_t si = warp_append(&ctr->shadow_count[bounce], ss);
+    if (ss)
+    {
+        q.sA[si] = make_float4(so.s_origin.x, so.s_origin.y, so.s_origin.z, __uint_as_float(pixel));
+        q.sB[si] = make_float4(so.s_dir.x, so.s_dir.y, so.s_dir.z, so.s_tmax);
+        q.sC[si] = make_float4(so.s_sample.x, so.s_sample.y, so.s_sample.z, 0.0f);
+    }
+    bool sn = hit && so.spawn_next;
+    uint32_t ni = warp_append(&ctr->q_count[bounce + 1], sn);
+    if (sn)
+    {
+        q.A[out][ni] = make_float4(so.n_origin.x, so.n_origin.y, so.n_origin.z, __uint_as_float(pixel));
+        q.B[out][ni] = make_float4(so.n_dir.x, so.n_dir.y, so.n_dir.z, RT_MAX_RENDER_DIST);
+        q.C[out][ni] = make_float4(so.n_throughput.x, so.n_throughput.y, so.n_throughput.z, 0.0f);
+    }
+}
+
+// ShadeSurfaceHits (stepwise)
+__global__ void __launch_bounds__(256) k_shade_hits(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = ctr->q_count[bounce];
+    int in = bounce & 1;
+    bool hit = false;
+    uint32_t pixel = 0;
+    ShadeOut so;
+    so.emissive = so.spawn_next = so.spawn_shadow = false;
+    if (i < n)
+    {
+        float4 h = q.hits[i];
+        uint32_t prim = __float_as_uint(h.z);
+        hit = prim != RT_INVALID_ID;
+        if (hit)
+        {
+            float4 a = q.A[in][i], b = q.B[in][i], c = q.C[in][i];
+            pixel = __float_as_uint(a.w);
+            shade_hit(sc, p, bounce, pixel, mk3(b), mk3(c), prim, h.x, h.y, so);
+        }
+    }
+    emit_rays(p, q, ctr, radiance, bounce, pixel, hit, so);
+}
+
+// IntersectShadowRays (stepwise): any-hit -> flags (0 = occluded, INVALID_ID = unoccluded)
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_intersect_shadow(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, uint32_t bounce)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = ctr->shadow_count[bounce];
+    uint32_t nv = 0, nt = 0;
+    if (i < n)
+    {
+        float4 a = q.sA[i], b = q.sB[i];
+        float bu, bv, bt;
+        q.shadow_flags[i] = trace<true, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
+    }
+    if (COUNT) { warp_sum64(&ctr->nodes_shadow[bounce], nv); warp_sum64(&ctr->tris_shadow[bounce], nt); }
+}
+
+// AccumulateDirectSamples (stepwise): accumulate_direct_samples.cl:27-53
+__global__ void __launch_bounds__(256) k_accumulate(FrameParams p, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = ctr->shadow_count[bounce];
+    bool un = false;
+    if (i < n)
+    {
+        un = q.shadow_flags[i] == RT_INVALID_ID;
+        if (un)
+        {
+            float4 a = q.sA[i], c = q.sC[i];
+            uint32_t pixel = __float_as_uint(a.w);
+            uint32_t li = local_index(p, pixel % p.width, pixel / p.width);
+            float4 r = radiance[li];
+            r.x += c.x; r.y += c.y; r.z += c.z;
+            radiance[li] = r;
+        }
+    }
+    warp_count(&ctr->n_unoccluded[bounce], un);
+}
+
+// Fused IntersectRays + ShadeMissedRays + ShadeSurfaceHits: the ray is read once, the hit never
+// goes to memory.  Persistent warps drain the bounce's ray queue through a global atomic cursor
+// (work_ext[bounce]), 32 consecutive rays per grab, so the launch is sized by the machine
+// (SMs x resident CTAs), not by the image.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_extend_shade(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
+{
+    const uint32_t n = ctr->q_count[bounce];
+    const int in = bounce & 1;
+    const int lane = threadIdx.x & 31;
+    uint32_t nv = 0, nt = 0;
+    for (;;)
+    {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->work_ext[bounce], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        bool live = i < n, hit = false, miss = false;
+        uint32_t pixel = 0;
+        ShadeOut so;
+        so.emissive = so.spawn_next = so.spawn_shadow = false;
+        if (live)
+        {
+            float4 a = q.A[in][i], b = q.B[in][i], c = q.C[in][i];
+            pixel = __float_as_uint(a.w);
+            float bu = 0.0f, bv = 0.0f, bt = 0.0f;
+            uint32_t prim = trace<false, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
+            hit = prim != RT_INVALID_ID;
+            miss = !hit;
+            if (miss) shade_miss(sc, p, radiance, pixel, mk3(b), mk3(c));
+            else shade_hit(sc, p, bounce, pixel, mk3(b), mk3(c), prim, bu, bv, so);
+        }
+        warp_count(&ctr->n_miss[bounce], miss);
+        emit_rays(p, q, ctr, radiance, bounce, pixel, hit, so);
+    }
+    if (COUNT) { warp_sum64(&ctr->nodes_ext[bounce], nv); warp_sum64(&ctr->tris_ext[bounce], nt); }
+}
+
+// Fused IntersectShadowRays + AccumulateDirectSamples, persistent like k_extend_shade.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_shadow_accumulate(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
+{
+    const uint32_t n = ctr->shadow_count[bounce];
+    const int lane = threadIdx.x & 31;
+    uint32_t nv = 0, nt = 0;
+    for (;;)
+    {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->work_shadow[bounce], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        bool un = false;
+        if (i < n)
+        {
+            float4 a = q.sA[i], b = q.sB[i];
+            float bu, bv, bt;
+            un = trace<true, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
+            if (un)
+            {
+                float4 c = q.sC[i];
+                uint32_t pixel = __float_as_uint(a.w);
+                uint32_t li = local_index(p, pixel % p.width, pixel / p.width);
+                float4 r = radiance[li];
+                r.x += c.x; r.y += c.y; r.z += c.z;
+                radiance[li] = r;
+            }
+        }
+        warp_count(&ctr->n_unoccluded[bounce], un);
+    }
+    if (COUNT) { warp_sum64(&ctr->nodes_shadow[bounce], nv); warp_sum64(&ctr->tris_shadow[bounce], nt); }
+}
+
+// resolve_radiance.cl:31-86 (shaded colour): hdr = radiance / sample_count; ldr = hdr / (hdr + 1)
+__global__ void __launch_bounds__(256) k_resolve(const float4* radiance, float4* out, uint32_t n, uint32_t sample_count, int denoiser)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 r = radiance[i];
+    f3 hdr = mk3(r);
+    if (!denoiser) hdr = hdr / (float)sample_count;
+    f3 ldr = hdr / (mk3(hdr.x + 1.0f, hdr.y + 1.0f, hdr.z + 1.0f));
+    out[i] = make_float4(ldr.x, ldr.y, ldr.z, 1.0f);
+}
+
+__global__ void k_unpack_rays(const float4* A, const float4* B, const uint32_t* count, RtRay* rays, uint32_t* pixels)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count) return;
+    float4 a = A[i], b = B[i];
+    rays[i].origin = RtFloat3{ a.x, a.y, a.z, 0.0f };
+    rays[i].direction = RtFloat3{ b.x, b.y, b.z, b.w };
+    pixels[i] = __float_as_uint(a.w);
+}
+
+} // namespace
+
+// ====================================================================================== host side
+struct rt_ctx
+{
+    int device = 0;
+    uint32_t width = 0, height = 0, rank = 0, world = 1, n_local = 0, local_rows = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    std::string error;
+
+    // options
+    int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 1;
+
+    // per-pixel buffers
+    Queues q = {};
+    float4* radiance = nullptr;
+    float4* resolved = nullptr;
+    DevCounters* counters = nullptr;
+    void* scratch = nullptr; size_t scratch_bytes = 0;
+
+    // scene
+    bool scene_ready = false, camera_ready = false;
+    DevScene scene = {};
+    std::vector<void*> scene_allocs;
+    RtCamera camera = {};
+    RayGenConsts raygen = {};
+
+    uint32_t sample_count = 0;
+    uint32_t cur_bounce = 0;
+    bool frame_started = false;
+    uint64_t launches = 0;
+
+    // kernel timing
+    struct Timed { cudaEvent_t a, b; int cls; };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> event_pool;
+    float ms[RT_K_CLASS_COUNT] = {};
+    uint32_t nlaunch[RT_K_CLASS_COUNT] = {};
+};
+
+static std::string g_create_error;
+
+#define RT_FAIL(ctx, code, ...)                                   \
+    do {                                                          \
+        char rt_buf_[512];                                        \
+        snprintf(rt_buf_, sizeof(rt_buf_), __VA_ARGS__);          \
+        (ctx)->error = rt_buf_;                                   \
+        return (code);                                            \
+    } while (0)
+
+#define RT_CUDA(ctx, expr)                                                                         \
+    do {                                                                                           \
+        cudaError_t rt_e_ = (expr);                                                                \
+        if (rt_e_ != cudaSuccess)                                                                  \
+            RT_FAIL(ctx, RT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(rt_e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define RT_CHECK_CTX(ctx) do { if (!(ctx)) return RT_ERR_INVALID_ARGUMENT; } while (0)
+
+namespace
+{
+
+struct TimedLaunch
+{
+    rt_ctx* c; int cls; cudaEvent_t a = nullptr, b = nullptr;
+    TimedLaunch(rt_ctx* ctx, int k) : c(ctx), cls(k)
+    {
+        ++c->launches;
+        if (!c->kernel_timing) return;
+        auto get = [&]() { cudaEvent_t e; if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+        a = get(); b = get();
+        cudaEventRecord(a, c->stream);
+    }
+    ~TimedLaunch()
+    {
+        if (!a) return;
+        cudaEventRecord(b, c->stream);
+        c->timed.push_back({ a, b, cls });
+    }
+};
+
+inline dim3 grid_for(uint32_t n, uint32_t block = 256) { return dim3((n + block - 1) / block); }
+
+int post_launch(rt_ctx* c, const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) RT_FAIL(c, RT_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return RT_OK;
+}
+
+FrameParams frame_params(const rt_ctx* c)
+{
+    FrameParams p;
+    p.width = c->width; p.height = c->height; p.rank = c->rank; p.world = c->world; p.n_local = c->n_local;
+    p.sample_idx = c->sample_count; p.white_furnace = c->white_furnace;
+    return p;
+}
+
+int require_ready(rt_ctx* c)
+{
+    if (!c->scene_ready) RT_FAIL(c, RT_ERR_NOT_READY, "rt_upload_scene has not been called");
+    if (!c->camera_ready) RT_FAIL(c, RT_ERR_NOT_READY, "rt_set_camera has not been called");
+    return RT_OK;
+}
+
+int alloc_frame_buffers(rt_ctx* c)
+{
+    auto freep = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+    for (int i = 0; i < 2; ++i) { freep(c->q.A[i]); freep(c->q.B[i]); freep(c->q.C[i]); }
+    freep(c->q.sA); freep(c->q.sB); freep(c->q.sC); freep(c->q.hits); freep(c->q.shadow_flags);
+    freep(c->radiance); freep(c->resolved);
+    c->local_rows = (c->height > c->rank) ? (c->height - c->rank + c->world - 1) / c->world : 0;
+    c->n_local = c->local_rows * c->width;
+    size_t n = c->n_local ? c->n_local : 1;
+    for (int i = 0; i < 2; ++i)
+    {
+        RT_CUDA(c, cudaMalloc(&c->q.A[i], n * 16)); RT_CUDA(c, cudaMalloc(&c->q.B[i], n * 16)); RT_CUDA(c, cudaMalloc(&c->q.C[i], n * 16));
+    }
+    RT_CUDA(c, cudaMalloc(&c->q.sA, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.sB, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.sC, n * 16));
+    RT_CUDA(c, cudaMalloc(&c->q.hits, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.shadow_flags, n * 4));
+    RT_CUDA(c, cudaMalloc(&c->radiance, n * 16)); RT_CUDA(c, cudaMalloc(&c->resolved, n * 16));
+    RT_CUDA(c, cudaMemsetAsync(c->radiance, 0, n * 16, c->stream));
+    return RT_OK;
+}
+
+int persistent_grid(rt_ctx* c) { return c->num_sms * 8; }   // 8 CTAs x 256 threads = full occupancy target per SM
+
+} // namespace
+
+extern "C" {
+
+const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int rt_create(uint32_t width, uint32_t height, int device, rt_ctx** out_ctx)
+{
+    if (!out_ctx || width == 0 || height == 0) { g_create_error = "rt_create: bad arguments"; return RT_ERR_INVALID_ARGUMENT; }
+    *out_ctx = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+    {
+        g_create_error = std::string("rt_create: no CUDA device (") + cudaGetErrorString(e) + "); this backend has no CPU fallback";
+        return RT_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "rt_create: device index out of range"; return RT_ERR_INVALID_ARGUMENT; }
+    rt_ctx* c = new rt_ctx;
+    c->device = device; c->width = width; c->height = height;
+    auto fail = [&](const char* what, cudaError_t err) { g_create_error = std::string("rt_create: ") + what + ": " + cudaGetErrorString(err); delete c; return RT_ERR_CUDA; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+    c->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaMalloc(&c->counters, sizeof(DevCounters))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
+    cudaMemsetAsync(c->counters, 0, sizeof(DevCounters), c->stream);
+    int rc = alloc_frame_buffers(c);
+    if (rc != RT_OK) { g_create_error = c->error; rt_destroy(c); return rc; }
+    *out_ctx = c;
+    return RT_OK;
+}
+
+int rt_destroy(rt_ctx* c)
+{
+    if (!c) return RT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 2; ++i) { cudaFree(c->q.A[i]); cudaFree(c->q.B[i]); cudaFree(c->q.C[i]); }
+    cudaFree(c->q.sA); cudaFree(c->q.sB); cudaFree(c->q.sC); cudaFree(c->q.hits); cudaFree(c->q.shadow_flags);
+    cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->counters); cudaFree(c->scratch);
+    for (void* p : c->scene_allocs) cudaFree(p);
+    for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RT_OK;
+}
+
+int rt_set_partition(rt_ctx* c, uint32_t rank, uint32_t world)
+{
+    RT_CHECK_CTX(c);
+    if (world == 0 || rank >= world) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_set_partition: need rank < world, world >= 1");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    c->rank = rank; c->world = world;
+    return alloc_frame_buffers(c);
+}
+
+int rt_upload_scene(rt_ctx* c, const RtSceneDesc* s)
+{
+    RT_CHECK_CTX(c);
+    if (!s) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: null scene");
+    // cl_pt_integrator.cpp:385,404 assert non-empty triangles/materials; light.h:46 divides by the light count
+    if (!s->triangles || s->n_triangles == 0) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: scene has no triangles");
+    if (!s->materials || s->n_materials == 0) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: scene has no materials");
+    if (!s->nodes || s->n_nodes == 0) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: scene has no BVH nodes");
+    if (!s->lights || s->n_lights == 0 || s->scene_info.analytic_light_count == 0)
+        RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: at least one analytic light is required (light.h:46 divides by the count)");
+    if (s->scene_info.analytic_light_count > s->n_lights) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: analytic_light_count exceeds n_lights");
+    if (!s->env_image || s->env_width == 0 || s->env_height == 0) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: environment image required");
+    if (s->n_triangles >= 0x7FFFFFFFull || s->n_nodes >= 0x7FFFFFFFull) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: scene too large");
+    for (uint64_t i = 0; i < s->n_triangles; ++i)
+        if (s->triangles[i].mtlIndex >= s->n_materials) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: triangle %llu has material index out of range", (unsigned long long)i);
+
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (void* p : c->scene_allocs) cudaFree(p);
+    c->scene_allocs.clear();
+    c->scene_ready = false;
+
+    auto upload = [&](const void* src, size_t bytes, const void** dst) -> int {
+        void* d = nullptr;
+        size_t alloc = bytes ? bytes : 16;
+        RT_CUDA(c, cudaMalloc(&d, alloc));
+        c->scene_allocs.push_back(d);
+        if (bytes) RT_CUDA(c, cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+        *dst = d;
+        return RT_OK;
+    };
+    int rc;
+    DevScene& ds = c->scene;
+    if ((rc = upload(s->nodes, s->n_nodes * sizeof(RtLinearBVHNode), (const void**)&ds.nodes_ref))) return rc;
+    if ((rc = upload(s->triangles, s->n_triangles * sizeof(RtTriangle), (const void**)&ds.triangles))) return rc;
+    {   // RTTriangle[] derived at upload, cl_pt_integrator.cpp:392-402
+        std::vector<RtRTTriangle> rt(s->n_triangles);
+        for (uint64_t i = 0; i < s->n_triangles; ++i)
+        {
+            rt[i].position1 = s->triangles[i].v1.position; rt[i].position2 = s->triangles[i].v2.position; rt[i].position3 = s->triangles[i].v3.position;
+        }
+        if ((rc = upload(rt.data(), rt.size() * sizeof(RtRTTriangle), (const void**)&ds.tris_ref))) return rc;
+    }
+    if ((rc = upload(s->materials, s->n_materials * sizeof(RtPackedMaterial), (const void**)&ds.materials))) return rc;
+    if ((rc = upload(s->lights, s->n_lights * sizeof(RtLight), (const void**)&ds.lights))) return rc;
+    if ((rc = upload(s->textures, s->n_textures * sizeof(RtTexture), (const void**)&ds.textures))) return rc;
+    if ((rc = upload(s->texture_data, s->n_texture_data * 4, (const void**)&ds.texels))) return rc;
+    if ((rc = upload(s->env_image, (size_t)s->env_width * s->env_height * 16, (const void**)&ds.env))) return rc;
+    ds.env_w = (int)s->env_width; ds.env_h = (int)s->env_height;
+    ds.light_count = s->scene_info.analytic_light_count;
+    {   // optimised traversal layout
+        rtbvh::WideLayout wl;
+        std::string err;
+        if (!rtbvh::build_layout(s->nodes, s->n_nodes, s->triangles, s->n_triangles, wl, err))
+            RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: malformed BVH: %s", err.c_str());
+        if ((rc = upload(wl.nodes.data(), wl.nodes.size() * 16, (const void**)&ds.wnodes))) return rc;
+        if ((rc = upload(wl.tris.data(), wl.tris.size() * 16, (const void**)&ds.wtris))) return rc;
+        ds.root_ref = wl.root_ref;
+    }
+    c->scene_ready = true;
+    return RT_OK;
+}
+
+int rt_set_camera(rt_ctx* c, const RtCamera* cam)
+{
+    RT_CHECK_CTX(c);
+    if (!cam) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_set_camera: null camera");
+    c->camera = *cam;
+    RayGenConsts& r = c->raygen;
+    r.position = f3{ cam->position.x, cam->position.y, cam->position.z };
+    r.front = f3{ cam->front.x, cam->front.y, cam->front.z };
+    r.up = f3{ cam->up.x, cam->up.y, cam->up.z };
+    // cross(front, up), raygeneration.cl:112 — plain float ops on the host (no contraction: -fmad=false
+    // applies to host code too, and x86-64 has no implicit FMA)
+    r.right = f3{ r.front.y * r.up.z - r.front.z * r.up.y, r.front.z * r.up.x - r.front.x * r.up.z, r.front.x * r.up.y - r.front.y * r.up.x };
+    r.tan_half_fov = rt_tanf(0.5f * cam->fov);        // raygeneration.cl:108, uniform over the frame
+    r.aspect_ratio = cam->aspect_ratio;
+    r.aperture = cam->aperture; r.focus_distance = cam->focus_distance;
+    r.inv_width = 1.0f / (float)c->width; r.inv_height = 1.0f / (float)c->height;
+    c->camera_ready = true;
+    return RT_OK;
+}
+
+int rt_set_option(rt_ctx* c, int key, uint32_t value)
+{
+    RT_CHECK_CTX(c);
+    switch (key)
+    {
+    case RT_OPT_WHITE_FURNACE: c->white_furnace = value != 0; return RT_OK;
+    case RT_OPT_SAMPLER:
+        if (value != 0) RT_FAIL(c, RT_ERR_UNSUPPORTED, "blue-noise sampler is not implemented yet (SURVEY 8f rank 3)");
+        c->sampler = 0; return RT_OK;
+    case RT_OPT_AOV:
+        if (value > 4) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "AOV index out of range");
+        if (value != 0) RT_FAIL(c, RT_ERR_UNSUPPORTED, "AOV views are not implemented yet (SURVEY 8f rank 2)");
+        c->aov = (int)value; return RT_OK;
+    case RT_OPT_DENOISER:
+        if (value != 0) RT_FAIL(c, RT_ERR_UNSUPPORTED, "temporal denoiser is not implemented yet (SURVEY 8f rank 4)");
+        c->denoiser = 0; return RT_OK;
+    case RT_OPT_COUNT_TRAVERSAL: c->count_traversal = value != 0; return RT_OK;
+    case RT_OPT_KERNEL_TIMING: c->kernel_timing = value != 0; return RT_OK;
+    case RT_OPT_TRAVERSAL:
+        if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "traversal mode must be 0 or 1");
+        c->traversal = (int)value; return RT_OK;
+    }
+    RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "unknown option key %d", key);
+}
+
+int rt_reset(rt_ctx* c)
+{
+    RT_CHECK_CTX(c);
+    RT_CUDA(c, cudaSetDevice(c->device));
+    if (!c->denoiser) c->sample_count = 0;                                   // cl_pt_integrator.cpp:499-504
+    TimedLaunch t(c, RT_K_MISC);
+    k_reset<<<grid_for(c->n_local), 256, 0, c->stream>>>(c->radiance, c->n_local);
+    return post_launch(c, "k_reset");
+}
+
+int rt_advance_sample_count(rt_ctx* c) { RT_CHECK_CTX(c); ++c->sample_count; return RT_OK; }
+
+int rt_generate_rays(rt_ctx* c)
+{
+    RT_CHECK_CTX(c);
+    int rc = require_ready(c); if (rc) return rc;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(DevCounters), c->stream));
+    TimedLaunch t(c, RT_K_RAYGEN);
+    k_raygen<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->raygen, c->q, c->counters);
+    c->frame_started = true;
+    return post_launch(c, "k_raygen");
+}
+
+#define RT_BOUNCE_CHECK(c, b)                                                                                   \
+    do {                                                                                                        \
+        int rt_rc_ = require_ready(c); if (rt_rc_) return rt_rc_;                                               \
+        if ((b) > RT_MAX_BOUNCES) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "bounce %u exceeds RT_MAX_BOUNCES", (b)); \
+        if (!(c)->frame_started) RT_FAIL(c, RT_ERR_NOT_READY, "rt_generate_rays has not been called");          \
+        RT_CUDA(c, cudaSetDevice((c)->device));                                                                 \
+    } while (0)
+
+int rt_intersect(rt_ctx* c, uint32_t bounce)
+{
+    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
+    TimedLaunch t(c, RT_K_INTERSECT);
+    if (c->count_traversal) k_intersect<true><<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
+    else k_intersect<false><<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
+    return post_launch(c, "k_intersect");
+}
+
+int rt_compute_aovs(rt_ctx* c) { RT_CHECK_CTX(c); return RT_OK; }   /* AOVs not produced yet: empty step, like gl_pt_integrator.cpp:230-243 */
+
+int rt_shade_miss(rt_ctx* c, uint32_t bounce)
+{
+    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
+    TimedLaunch t(c, RT_K_MISS);
+    k_shade_miss<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce);
+    return post_launch(c, "k_shade_miss");
+}
+
+int rt_clear_outgoing_counter(rt_ctx* c, uint32_t) { RT_CHECK_CTX(c); return RT_OK; }
+int rt_clear_shadow_counter(rt_ctx* c) { RT_CHECK_CTX(c); return RT_OK; }
+
+int rt_shade_hits(rt_ctx* c, uint32_t bounce)
+{
+    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
+    c->cur_bounce = bounce;
+    TimedLaunch t(c, RT_K_HIT);
+    k_shade_hits<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce);
+    return post_launch(c, "k_shade_hits");
+}
+
+int rt_intersect_shadow(rt_ctx* c)
+{
+    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, c->cur_bounce);
+    TimedLaunch t(c, RT_K_INTERSECT_SHADOW);
+    if (c->count_traversal) k_intersect_shadow<true><<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->cur_bounce);
+    else k_intersect_shadow<false><<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->cur_bounce);
+    return post_launch(c, "k_intersect_shadow");
+}
+
+int rt_accumulate_direct(rt_ctx* c)
+{
+    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, c->cur_bounce);
+    TimedLaunch t(c, RT_K_ACCUMULATE);
+    k_accumulate<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->q, c->counters, c->radiance, c->cur_bounce);
+    return post_launch(c, "k_accumulate");
+}
+
+int rt_denoise(rt_ctx* c) { RT_CHECK_CTX(c); return RT_OK; }
+int rt_copy_history(rt_ctx* c) { RT_CHECK_CTX(c); return RT_OK; }
+
+int rt_extend_shade(rt_ctx* c, uint32_t bounce)
+{
+    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
+    c->cur_bounce = bounce;
+    TimedLaunch t(c, RT_K_EXTEND_SHADE);
+    int grid = persistent_grid(c);
+    if (c->count_traversal) k_extend_shade<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    else k_extend_shade<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    return post_launch(c, "k_extend_shade");
+}
+
+int rt_shadow_accumulate(rt_ctx* c, uint32_t bounce)
+{
+    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
+    TimedLaunch t(c, RT_K_SHADOW_ACCUMULATE);
+    int grid = persistent_grid(c);
+    if (c->count_traversal) k_shadow_accumulate<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    else k_shadow_accumulate<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    return post_launch(c, "k_shadow_accumulate");
+}
+
+int rt_integrate(rt_ctx* c, uint32_t max_bounces)
+{
+    RT_CHECK_CTX(c);
+    if (max_bounces > RT_MAX_BOUNCES) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "max_bounces %u exceeds RT_MAX_BOUNCES", max_bounces);
+    int rc = rt_generate_rays(c); if (rc) return rc;
+    for (uint32_t b = 0; b <= max_bounces; ++b)          // inclusive, integrator.cpp:37
+    {
+        if ((rc = rt_extend_shade(c, b))) return rc;
+        if ((rc = rt_shadow_accumulate(c, b))) return rc;
+    }
+    return rt_advance_sample_count(c);
+}
+
+int rt_resolve(rt_ctx* c, float* dst)
+{
+    RT_CHECK_CTX(c);
+    RT_CUDA(c, cudaSetDevice(c->device));
+    {
+        TimedLaunch t(c, RT_K_RESOLVE);
+        k_resolve<<<grid_for(c->n_local), 256, 0, c->stream>>>(c->radiance, c->resolved, c->n_local, c->sample_count, c->denoiser);
+        int rc = post_launch(c, "k_resolve"); if (rc) return rc;
+    }
+    if (dst && c->local_rows)
+        RT_CUDA(c, cudaMemcpy2DAsync(dst + (size_t)c->rank * c->width * 4, (size_t)c->world * c->width * 16, c->resolved,
+                                     (size_t)c->width * 16, (size_t)c->width * 16, c->local_rows, cudaMemcpyDeviceToHost, c->stream));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+int rt_sync(rt_ctx* c)
+{
+    RT_CHECK_CTX(c);
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+static int ensure_scratch(rt_ctx* c, size_t bytes)
+{
+    if (c->scratch_bytes >= bytes) return RT_OK;
+    cudaFree(c->scratch); c->scratch = nullptr; c->scratch_bytes = 0;
+    RT_CUDA(c, cudaMalloc(&c->scratch, bytes));
+    c->scratch_bytes = bytes;
+    return RT_OK;
+}
+
+int rt_read_hits(rt_ctx* c, uint32_t bounce, RtHit* hits, uint32_t* pixels, uint32_t* n_out)
+{
+    RT_CHECK_CTX(c);
+    if (bounce > RT_MAX_BOUNCES || !n_out) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_hits: bad arguments");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint32_t n = 0;
+    RT_CUDA(c, cudaMemcpy(&n, &c->counters->q_count[bounce], 4, cudaMemcpyDeviceToHost));
+    *n_out = n;
+    if (hits && n) RT_CUDA(c, cudaMemcpy(hits, c->q.hits, (size_t)n * 16, cudaMemcpyDeviceToHost));   // same 16-byte layout as RtHit
+    if (pixels && n)
+    {
+        std::vector<float4> a(n);
+        RT_CUDA(c, cudaMemcpy(a.data(), c->q.A[bounce & 1], (size_t)n * 16, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < n; ++i) memcpy(&pixels[i], &a[i].w, 4);
+    }
+    return RT_OK;
+}
+
+int rt_read_rays(rt_ctx* c, uint32_t bounce, RtRay* rays, uint32_t* pixels, uint32_t* n_out)
+{
+    RT_CHECK_CTX(c);
+    if (bounce > RT_MAX_BOUNCES || !n_out || !rays || !pixels) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_rays: bad arguments");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_scratch(c, (size_t)c->n_local * (sizeof(RtRay) + 4) + 64); if (rc) return rc;
+    RtRay* drays = (RtRay*)c->scratch;
+    uint32_t* dpix = (uint32_t*)((char*)c->scratch + (size_t)c->n_local * sizeof(RtRay));
+    k_unpack_rays<<<grid_for(c->n_local), 256, 0, c->stream>>>(c->q.A[bounce & 1], c->q.B[bounce & 1], &c->counters->q_count[bounce], drays, dpix);
+    ++c->launches;
+    if ((rc = post_launch(c, "k_unpack_rays"))) return rc;
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    uint32_t n = 0;
+    RT_CUDA(c, cudaMemcpy(&n, &c->counters->q_count[bounce], 4, cudaMemcpyDeviceToHost));
+    *n_out = n;
+    if (n)
+    {
+        RT_CUDA(c, cudaMemcpy(rays, drays, (size_t)n * sizeof(RtRay), cudaMemcpyDeviceToHost));
+        RT_CUDA(c, cudaMemcpy(pixels, dpix, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    }
+    return RT_OK;
+}
+
+int rt_read_radiance(rt_ctx* c, float* dst)
+{
+    RT_CHECK_CTX(c);
+    if (!dst) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_radiance: null destination");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    if (c->local_rows)
+        RT_CUDA(c, cudaMemcpy2DAsync(dst + (size_t)c->rank * c->width * 4, (size_t)c->world * c->width * 16, c->radiance,
+                                     (size_t)c->width * 16, (size_t)c->width * 16, c->local_rows, cudaMemcpyDeviceToHost, c->stream));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+int rt_read_frame_stats(rt_ctx* c, RtFrameStats* out)
+{
+    RT_CHECK_CTX(c);
+    if (!out) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_frame_stats: null destination");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    static thread_local DevCounters h;
+    RT_CUDA(c, cudaMemcpy(&h, c->counters, sizeof(DevCounters), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    for (uint32_t b = 0; b <= RT_MAX_BOUNCES; ++b)
+    {
+        out->n_ext[b] = h.q_count[b]; out->n_miss[b] = h.n_miss[b]; out->n_emissive_hits[b] = h.n_emissive[b];
+        out->n_shadow[b] = h.shadow_count[b]; out->n_cont[b] = h.q_count[b + 1]; out->n_unoccluded[b] = h.n_unoccluded[b];
+        out->nodes_ext[b] = h.nodes_ext[b]; out->tris_ext[b] = h.tris_ext[b];
+        out->nodes_shadow[b] = h.nodes_shadow[b]; out->tris_shadow[b] = h.tris_shadow[b];
+    }
+    return RT_OK;
+}
+
+int rt_read_sample_count(rt_ctx* c, uint32_t* out) { RT_CHECK_CTX(c); if (!out) return RT_ERR_INVALID_ARGUMENT; *out = c->sample_count; return RT_OK; }
+
+int rt_read_aovs(rt_ctx* c, float*, float*, float*, float*) { RT_CHECK_CTX(c); RT_FAIL(c, RT_ERR_UNSUPPORTED, "AOV buffers are not implemented yet (SURVEY 8f rank 2)"); }
+
+int rt_kernel_times(rt_ctx* c, float* ms, uint32_t* launches)
+{
+    RT_CHECK_CTX(c);
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (auto& t : c->timed)
+    {
+        float m = 0.0f;
+        RT_CUDA(c, cudaEventElapsedTime(&m, t.a, t.b));
+        c->ms[t.cls] += m; c->nlaunch[t.cls] += 1;
+        c->event_pool.push_back(t.a); c->event_pool.push_back(t.b);
+    }
+    c->timed.clear();
+    for (int k = 0; k < RT_K_CLASS_COUNT; ++k)
+    {
+        if (ms) ms[k] = c->ms[k];
+        if (launches) launches[k] = c->nlaunch[k];
+        c->ms[k] = 0.0f; c->nlaunch[k] = 0;
+    }
+    return RT_OK;
+}
+
+int rt_launch_count(rt_ctx* c, uint64_t* out) { RT_CHECK_CTX(c); if (!out) return RT_ERR_INVALID_ARGUMENT; *out = c->launches; return RT_OK; }
+int rt_local_pixel_count(rt_ctx* c, uint32_t* out) { RT_CHECK_CTX(c); if (!out) return RT_ERR_INVALID_ARGUMENT; *out = c->n_local; return RT_OK; }
+
+int rt_radiance_device_ptr(rt_ctx* c, void** out_ptr, uint64_t* out_bytes)
+{
+    RT_CHECK_CTX(c);
+    if (!out_ptr || !out_bytes) return RT_ERR_INVALID_ARGUMENT;
+    *out_ptr = c->radiance; *out_bytes = (uint64_t)c->n_local * 16;
+    return RT_OK;
+}
+
+int rt_stream_handle(rt_ctx* c, void** out) { RT_CHECK_CTX(c); if (!out) return RT_ERR_INVALID_ARGUMENT; *out = (void*)c->stream; return RT_OK; }
+
+} // extern "C"
