@@ -53,33 +53,40 @@ def algorithmic_bytes(st, mb, n_pix):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock, power and throttle reasons sampled through NVML every ~2 ms DURING the timed region
+    (same quantities as the nvidia-smi line of B200_PROFILING.md; nvidia-smi itself is too slow for a ~40 ms region)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.power, self.reason_bits, self.stop_flag, self.err = index, [], [], 0, False, None
+        self.sm_max = None
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                time.sleep(0.002)
+        except Exception as e:           # noqa: BLE001
+            self.err = repr(e)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["nvml unavailable: %s" % self.err]}
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": [n for b, n in names.items() if self.reason_bits & b],
+                "samples": len(sm), "power_w_max": max(self.power) if self.power else None}
 
 
 def measured_peak_hbm():
@@ -207,11 +214,8 @@ def main():
     class _Slab:
         __cuda_array_interface__ = {"shape": (n_local, 4), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
     slab = torch.as_tensor(_Slab(), device=torch.device("cuda", local_rank))
-    rows_max = (h + world - 1) // world
-    gathered = None
-    if world > 1:
-        send = torch.zeros((rows_max * w, 4), dtype=torch.float32, device=slab.device)
-        gathered = [torch.zeros_like(send) for _ in range(world)] if rank == 0 else None
+    from raytracing_b200.distributed import RadianceGather
+    gather = RadianceGather(w, h, rank, world, slab.device)
 
     def frame():
         ctx.reset()
@@ -221,8 +225,7 @@ def main():
             ctx.integrate(mb)
         if world > 1:
             with torch.cuda.stream(stream):
-                send[: n_local].copy_(slab)
-                dist.gather(send, gathered, dst=0)          # the ONE collective of the frame
+                gather.gather(slab)                         # the ONE collective of the frame (NCCL, NVLink/NVSwitch)
 
     def barrier():
         if world > 1:

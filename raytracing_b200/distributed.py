@@ -1,0 +1,48 @@
+"""
+Multi-GPU plumbing (one process per GPU, torch.distributed): the image is partitioned by scanline — row y
+belongs to rank y % world — every rank renders its rows with the scene replicated, and ONE gather of the
+radiance slabs to rank 0 ends the frame (BASELINE.json north_star).  No other collective exists
+on the data path.  Backend "nccl" on the GPUs (NVLink 5 / NVSwitch), "gloo" in the CPU tests.
+
+A rank's slab is local_rows x width float4, local row r = image row rank + r * world.  Ranks can own one row
+less than rank 0 when world does not divide the height, so slabs are padded to rows_max for the gather.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def local_rows(height: int, rank: int, world: int) -> int:
+    return (height - rank + world - 1) // world if height > rank else 0
+
+
+def rows_max(height: int, world: int) -> int:
+    return (height + world - 1) // world
+
+
+class RadianceGather:
+    """Pre-allocated buffers for the per-frame gather; `slab` is the rank's radiance as a (n_local, 4) float32 tensor
+    (zero-copy view of the device buffer on GPU)."""
+
+    def __init__(self, width: int, height: int, rank: int, world: int, device):
+        self.width, self.height, self.rank, self.world = width, height, rank, world
+        self.n_local = local_rows(height, rank, world) * width
+        self.n_pad = rows_max(height, world) * width
+        self.send = torch.zeros((self.n_pad, 4), dtype=torch.float32, device=device)
+        self.recv = [torch.zeros_like(self.send) for _ in range(world)] if rank == 0 else None
+
+    def gather(self, slab: torch.Tensor):
+        """The one collective of the frame.  Returns the list of padded slabs on rank 0, None elsewhere."""
+        if self.world == 1:
+            return [slab]
+        self.send[: self.n_local].copy_(slab[: self.n_local])
+        dist.gather(self.send, self.recv, dst=0)
+        return self.recv
+
+    def reassemble(self, slabs) -> np.ndarray:
+        """Rank 0: padded slabs -> full height x width x 4 image (host)."""
+        img = np.zeros((self.height, self.width, 4), dtype=np.float32)
+        for r, s in enumerate(slabs):
+            n = local_rows(self.height, r, self.world)
+            img[r::self.world] = s[: n * self.width].reshape(n, self.width, 4).cpu().numpy()
+        return img

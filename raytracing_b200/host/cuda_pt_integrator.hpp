@@ -1,0 +1,76 @@
+/*
+ * CUDAPathTraceIntegrator — the B200 backend behind the reference's Integrator interface, the
+ * counterpart of CLPathTraceIntegrator (/root/reference/src/integrator/cl_pt_integrator.hpp:31-125).
+ * It owns an opaque rt_ctx and forwards every virtual step to the C ABI (include/rt_b200.h), which
+ * takes the place of CLContext/CLKernel.  Errors come back as status codes and are re-thrown as
+ * std::runtime_error, the behaviour callers of the OpenCL backend see (CLException).
+ *
+ * Schedules:
+ *   kFused (default)  the seven per-bounce virtuals map onto TWO kernels: ShadeSurfaceHits(b) launches
+ *                     the fused intersect+miss+shade kernel, AccumulateDirectSamples() the fused
+ *                     shadow-trace+accumulate kernel; IntersectRays, ShadeMissedRays, the two counter
+ *                     clears and IntersectShadowRays are empty (the OpenGL backend of the reference
+ *                     also leaves steps empty: gl_pt_integrator.cpp:230-243,354-357,466-474).  At the
+ *                     end of each loop iteration of Integrate() the device state is the same as with
+ *                     the stepwise schedule, bit for bit.
+ *   kStepwise         one kernel per virtual, like the OpenCL backend.
+ * The last constructor argument of the OpenCL backend is a GL texture to resolve into
+ * (cl_pt_integrator.hpp:33-34); here ResolveRadiance() writes to a host RGBA32F image instead
+ * (SetResolveTarget), or only resolves on the device if none is set.
+ */
+#pragma once
+
+#include <string>
+
+#include "integrator.hpp"
+#include "rt_b200.h"
+
+namespace rt_host
+{
+
+class CUDAPathTraceIntegrator : public Integrator
+{
+public:
+    enum class Schedule { kFused, kStepwise };
+
+    CUDAPathTraceIntegrator(std::uint32_t width, std::uint32_t height, AccelerationStructure& acc_structure,
+                            int device = 0, Schedule schedule = Schedule::kFused);
+    ~CUDAPathTraceIntegrator() override;
+
+    void UploadGPUData(Scene const& scene, AccelerationStructure const& acc_structure) override;
+    void SetCameraData(Camera const& camera) override;
+    void SetSamplerType(SamplerType sampler_type) override;
+    void SetAOV(AOV aov) override;
+    void EnableDenoiser(bool enable) override;
+
+    void SetResolveTarget(float* host_rgba) { resolve_target_ = host_rgba; }
+    void SetSchedule(Schedule s) { schedule_ = s; }
+    rt_ctx* Context() const { return ctx_; }
+
+protected:
+    void CreateKernels() override;
+    void Reset() override;
+    void AdvanceSampleCount() override;
+    void GenerateRays() override;
+    void IntersectRays(std::uint32_t bounce) override;
+    void ComputeAOVs() override;
+    void ShadeMissedRays(std::uint32_t bounce) override;
+    void ShadeSurfaceHits(std::uint32_t bounce) override;
+    void IntersectShadowRays() override;
+    void AccumulateDirectSamples() override;
+    void ClearOutgoingRayCounter(std::uint32_t bounce) override;
+    void ClearShadowRayCounter() override;
+    void Denoise() override;
+    void CopyHistoryBuffers() override;
+    void ResolveRadiance() override;
+
+private:
+    void Check(int status, const char* what) const;
+
+    rt_ctx* ctx_ = nullptr;
+    Schedule schedule_;
+    std::uint32_t current_bounce_ = 0;
+    float* resolve_target_ = nullptr;
+};
+
+} // namespace rt_host

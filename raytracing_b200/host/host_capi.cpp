@@ -1,0 +1,136 @@
+/*
+ * host_capi.cpp — small C façade over the C++ host classes so that the Python tests and bench.py can drive
+ * them (ctypes): scene loading, BVH build, and the headless Render with RenderBackend::kCUDA.  Not part of
+ * the reference-facing boundary (that is include/rt_b200.h + the C++ classes); test/bench plumbing only.
+ */
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "bvh.hpp"
+#include "render.hpp"
+#include "scene.hpp"
+
+using namespace rt_host;
+
+namespace
+{
+thread_local std::string g_error;
+struct SceneHandle { std::unique_ptr<Scene> scene; Bvh bvh; bool built = false; };
+struct RenderHandle { std::unique_ptr<Render> render; };
+}
+
+extern "C" {
+
+const char* rth_last_error() { return g_error.c_str(); }
+
+void* rth_scene_load(const char* obj_path, float scale, int flip_yz)
+{
+    try { auto* h = new SceneHandle; h->scene.reset(new Scene(obj_path, scale, flip_yz != 0)); return h; }
+    catch (std::exception& e) { g_error = e.what(); return nullptr; }
+}
+void rth_scene_free(void* h) { delete (SceneHandle*)h; }
+
+int rth_scene_add_directional_light(void* h, float dx, float dy, float dz, float r, float g, float b)
+{
+    ((SceneHandle*)h)->scene->AddDirectionalLight(make_float3(dx, dy, dz), make_float3(r, g, b)); return 0;
+}
+int rth_scene_add_point_light(void* h, float x, float y, float z, float r, float g, float b)
+{
+    ((SceneHandle*)h)->scene->AddPointLight(make_float3(x, y, z), make_float3(r, g, b)); return 0;
+}
+int rth_scene_build_bvh(void* h)
+{
+    try { auto* s = (SceneHandle*)h; s->bvh.BuildCPU(s->scene->GetTriangles()); s->built = true; return 0; }
+    catch (std::exception& e) { g_error = e.what(); return -1; }
+}
+int rth_scene_finalize_hdr(void* h, const char* env_path)
+{
+    try { ((SceneHandle*)h)->scene->Finalize(env_path); return 0; }
+    catch (std::exception& e) { g_error = e.what(); return -1; }
+}
+int rth_scene_finalize_image(void* h, const float* env, std::uint32_t w, std::uint32_t hgt)
+{
+    ((SceneHandle*)h)->scene->Finalize(env, w, hgt); return 0;
+}
+// which: 0 triangles 1 nodes 2 materials 3 lights 4 textures 5 texels 6 emissive 7 env 8 scene_info
+int rth_scene_query(void* h, int which, const void** ptr, size_t* count, std::uint32_t* e0, std::uint32_t* e1)
+{
+    auto* s = (SceneHandle*)h;
+    const Scene& sc = *s->scene;
+    *e0 = *e1 = 0;
+    switch (which)
+    {
+    case 0: *ptr = sc.GetTriangles().data(); *count = sc.GetTriangles().size(); return 0;
+    case 1: *ptr = s->bvh.GetNodes().data(); *count = s->bvh.GetNodes().size(); return 0;
+    case 2: *ptr = sc.GetMaterials().data(); *count = sc.GetMaterials().size(); return 0;
+    case 3: *ptr = sc.GetLights().data(); *count = sc.GetLights().size(); return 0;
+    case 4: *ptr = sc.GetTextures().data(); *count = sc.GetTextures().size(); return 0;
+    case 5: *ptr = sc.GetTextureData().data(); *count = sc.GetTextureData().size(); return 0;
+    case 6: *ptr = sc.GetEmissiveIndices().data(); *count = sc.GetEmissiveIndices().size(); return 0;
+    case 7: *ptr = sc.GetEnvImage().data.data(); *count = sc.GetEnvImage().data.size(); *e0 = sc.GetEnvImage().width; *e1 = sc.GetEnvImage().height; return 0;
+    case 8: *ptr = &sc.GetSceneInfo(); *count = 1; return 0;
+    }
+    return -1;
+}
+
+// Stand-alone BVH build over a caller-provided triangle array (reordered in place); nodes_out must hold 2*n entries.
+int rth_bvh_build(RtTriangle* triangles, size_t n, RtLinearBVHNode* nodes_out, size_t* n_nodes, std::uint32_t* max_depth)
+{
+    try
+    {
+        std::vector<Triangle> t(triangles, triangles + n);
+        Bvh bvh;
+        bvh.BuildCPU(t);
+        memcpy(triangles, t.data(), n * sizeof(Triangle));
+        memcpy(nodes_out, bvh.GetNodes().data(), bvh.GetNodes().size() * sizeof(LinearBVHNode));
+        *n_nodes = bvh.GetNodes().size();
+        if (max_depth) *max_depth = bvh.MaxDepth();
+        return 0;
+    }
+    catch (std::exception& e) { g_error = e.what(); return -1; }
+}
+
+int rth_default_camera(std::uint32_t width, std::uint32_t height, RtCamera* out)
+{
+    CameraController c(width, height);
+    *out = c.GetData();
+    return 0;
+}
+
+// Headless Render with the CUDA backend; the scene handle must not have had its BVH built yet (Render builds it).
+void* rth_render_create(void* scene_handle, std::uint32_t width, std::uint32_t height, const char* env_path, int device, int stepwise)
+{
+    try
+    {
+        auto* s = (SceneHandle*)scene_handle;
+        auto* h = new RenderHandle;
+        h->render.reset(new Render(width, height, Render::RenderBackend::kCUDA, *s->scene, env_path, device));
+        if (stepwise) static_cast<CUDAPathTraceIntegrator&>(h->render->GetIntegrator()).SetSchedule(CUDAPathTraceIntegrator::Schedule::kStepwise);
+        return h;
+    }
+    catch (std::exception& e) { g_error = e.what(); return nullptr; }
+}
+void rth_render_free(void* h) { delete (RenderHandle*)h; }
+int rth_render_set_max_bounces(void* h, std::uint32_t b)
+{
+    try { ((RenderHandle*)h)->render->SetMaxBounces(b); return 0; } catch (std::exception& e) { g_error = e.what(); return -1; }
+}
+int rth_render_enable_white_furnace(void* h, int e)
+{
+    try { ((RenderHandle*)h)->render->GetIntegrator().EnableWhiteFurnace(e != 0); return 0; } catch (std::exception& ex) { g_error = ex.what(); return -1; }
+}
+int rth_render_set_sampler(void* h, int blue_noise)
+{
+    try { ((RenderHandle*)h)->render->GetIntegrator().SetSamplerType(blue_noise ? Integrator::SamplerType::kBlueNoise : Integrator::SamplerType::kRandom); return 0; }
+    catch (std::exception& ex) { g_error = ex.what(); return -1; }
+}
+int rth_render_frame(void* h)
+{
+    try { ((RenderHandle*)h)->render->RenderFrame(); return 0; } catch (std::exception& e) { g_error = e.what(); return -1; }
+}
+int rth_render_request_reset(void* h) { ((RenderHandle*)h)->render->NotifyCameraChanged(); return 0; }
+const float* rth_render_image(void* h) { return ((RenderHandle*)h)->render->GetImage().data(); }
+void* rth_render_context(void* h) { return static_cast<CUDAPathTraceIntegrator&>(((RenderHandle*)h)->render->GetIntegrator()).Context(); }
+
+} // extern "C"

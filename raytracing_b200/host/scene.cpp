@@ -1,0 +1,343 @@
+#include "scene.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+
+namespace rt_host
+{
+
+namespace
+{
+
+float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// scene.cpp:53-61
+std::uint32_t PackAlbedo(float r, float g, float b, std::uint32_t tex)
+{
+    r = clampf(r, 0.0f, 1.0f); g = clampf(g, 0.0f, 1.0f); b = clampf(b, 0.0f, 1.0f);
+    return ((std::uint32_t)(r * 255.0f)) | ((std::uint32_t)(g * 255.0f) << 8) | ((std::uint32_t)(b * 255.0f) << 16) | (tex << 24);
+}
+
+// scene.cpp:63-85
+std::uint32_t PackRGBE(float r, float g, float b)
+{
+    r = std::fmax(r, 0.0f); g = std::fmax(g, 0.0f); b = std::fmax(b, 0.0f);
+    float v = r;
+    if (g > v) v = g;
+    if (b > v) v = b;
+    if (v < 1e-32f) return 0;
+    int e;
+    v = (float)(std::frexp(v, &e) * 256.0f / v);
+    return ((std::uint32_t)(r * v)) | ((std::uint32_t)(g * v) << 8) | ((std::uint32_t)(b * v) << 16) | ((std::uint32_t)(e + 128) << 24);
+}
+
+// scene.cpp:87-103 (host-side unpack used only to find emissive triangles)
+float EmissionSum(std::uint32_t rgbe)
+{
+    int e = (int)(rgbe >> 24);
+    if (!e) return 0.0f;
+    float f = std::ldexp(1.0f, e - (128 + 8));
+    float r = (float)((rgbe >> 0) & 0xFF) * f, g = (float)((rgbe >> 8) & 0xFF) * f, b = (float)((rgbe >> 16) & 0xFF) * f;
+    return r + g + b;
+}
+
+// scene.cpp:105-124
+std::uint32_t PackRoughnessMetalness(float roughness, std::uint32_t ri, float metalness, std::uint32_t mi)
+{
+    roughness = clampf(roughness, 0.0f, 1.0f); metalness = clampf(metalness, 0.0f, 1.0f);
+    return ((std::uint32_t)(roughness * 255.0f)) | (ri << 8) | ((std::uint32_t)(metalness * 255.0f) << 16) | (mi << 24);
+}
+std::uint32_t PackIorEmissionIdxTransparency(float ior, std::uint32_t ei, float transparency, std::uint32_t ti)
+{
+    ior = clampf(ior, 0.0f, 10.0f); transparency = clampf(transparency, 0.0f, 1.0f);
+    return ((std::uint32_t)(ior * 25.5f)) | (ei << 8) | ((std::uint32_t)(transparency * 255.0f) << 16) | (ti << 24);
+}
+
+struct MtlRecord
+{   // tinyobjloader defaults, tiny_obj_loader.h:1331-1340
+    float diffuse[3] = { 0, 0, 0 }, specular[3] = { 0, 0, 0 }, transmittance[3] = { 0, 0, 0 }, emission[3] = { 0, 0, 0 };
+    float ior = 1.0f, roughness = 0.0f, metallic = 0.0f;
+    bool has_texture = false;
+};
+
+std::string dirname_of(const std::string& p)
+{
+    size_t s = p.find_last_of("/\\");
+    return s == std::string::npos ? std::string() : p.substr(0, s);
+}
+
+float parse_real(const char*& p)
+{
+    char* end = nullptr;
+    double v = std::strtod(p, &end);
+    p = end;
+    return (float)v;
+}
+
+void parse_mtl(const std::string& path, std::vector<MtlRecord>& mats, std::map<std::string, int>& index)
+{
+    std::ifstream f(path);
+    if (!f) return;      // tinyobjloader only warns when the .mtl is missing
+    std::string line;
+    MtlRecord* cur = nullptr;
+    while (std::getline(f, line))
+    {
+        const char* p = line.c_str();
+        while (*p == ' ' || *p == '\t') ++p;
+        if (*p == '#' || *p == 0) continue;
+        auto key = [&](const char* k) { size_t n = strlen(k); return strncmp(p, k, n) == 0 && (p[n] == ' ' || p[n] == '\t'); };
+        if (key("newmtl"))
+        {
+            std::string name(p + 7);
+            while (!name.empty() && (name.back() == '\r' || name.back() == ' ' || name.back() == '\t')) name.pop_back();
+            size_t b = name.find_first_not_of(" \t");
+            name = b == std::string::npos ? std::string() : name.substr(b);
+            index[name] = (int)mats.size();
+            mats.push_back(MtlRecord());
+            cur = &mats.back();
+            continue;
+        }
+        if (!cur) continue;
+        auto read3 = [&](const char* q, float* out) { out[0] = parse_real(q); out[1] = parse_real(q); out[2] = parse_real(q); };
+        if (key("Kd")) read3(p + 2, cur->diffuse);
+        else if (key("Ks")) read3(p + 2, cur->specular);
+        else if (key("Ke")) read3(p + 2, cur->emission);
+        else if (key("Kt") || key("Tf")) read3(p + 2, cur->transmittance);
+        else if (key("Ni")) { const char* q = p + 2; cur->ior = parse_real(q); }
+        else if (key("Pr")) { const char* q = p + 2; cur->roughness = parse_real(q); }
+        else if (key("Pm")) { const char* q = p + 2; cur->metallic = parse_real(q); }
+        else if (strncmp(p, "map_", 4) == 0) cur->has_texture = true;
+    }
+}
+
+} // namespace
+
+Scene::Scene(const char* filename, float scale, bool flip_yz) { Load(filename, scale, flip_yz); }
+
+// scene.cpp:127-274
+void Scene::Load(const char* filename, float scale, bool flip_yz)
+{
+    std::ifstream f(filename);
+    if (!f) throw std::runtime_error("Failed to load the scene!");
+    std::string folder = dirname_of(filename);
+
+    std::vector<float> positions, normals, texcoords;
+    std::vector<MtlRecord> mtls;
+    std::map<std::string, int> mtl_index;
+    struct Corner { int v, vt, vn; };
+    struct Face { Corner c[3]; int material; };
+    std::vector<Face> faces;
+    int current_material = -1;
+
+    std::string line;
+    while (std::getline(f, line))
+    {
+        const char* p = line.c_str();
+        while (*p == ' ' || *p == '\t') ++p;
+        if (p[0] == 'v' && (p[1] == ' ' || p[1] == '\t')) { const char* q = p + 1; for (int i = 0; i < 3; ++i) positions.push_back(parse_real(q)); }
+        else if (p[0] == 'v' && p[1] == 'n' && (p[2] == ' ' || p[2] == '\t')) { const char* q = p + 2; for (int i = 0; i < 3; ++i) normals.push_back(parse_real(q)); }
+        else if (p[0] == 'v' && p[1] == 't' && (p[2] == ' ' || p[2] == '\t')) { const char* q = p + 2; for (int i = 0; i < 2; ++i) texcoords.push_back(parse_real(q)); }
+        else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t'))
+        {
+            const char* q = p + 1;
+            std::vector<Corner> corners;
+            for (;;)
+            {
+                while (*q == ' ' || *q == '\t') ++q;
+                if (*q == 0 || *q == '\r' || *q == '\n') break;
+                Corner c = { 0, 0, 0 };
+                char* end;
+                c.v = (int)strtol(q, &end, 10); q = end;
+                if (*q == '/') { ++q; if (*q != '/') { c.vt = (int)strtol(q, &end, 10); q = end; } if (*q == '/') { ++q; c.vn = (int)strtol(q, &end, 10); q = end; } }
+                // OBJ indices are 1-based; negative = relative to the end
+                auto fix = [](int idx, size_t n) { return idx > 0 ? idx - 1 : (idx < 0 ? (int)n + idx : -1); };
+                c.v = fix(c.v, positions.size() / 3); c.vt = fix(c.vt, texcoords.size() / 2); c.vn = fix(c.vn, normals.size() / 3);
+                corners.push_back(c);
+            }
+            // fan triangulation of polygons (the shipped assets are already triangulated)
+            for (size_t k = 2; k < corners.size(); ++k)
+                faces.push_back(Face{ { corners[0], corners[k - 1], corners[k] }, current_material });
+        }
+        else if (strncmp(p, "usemtl", 6) == 0 && (p[6] == ' ' || p[6] == '\t'))
+        {
+            std::string name(p + 7);
+            while (!name.empty() && (name.back() == '\r' || name.back() == ' ' || name.back() == '\t')) name.pop_back();
+            size_t b = name.find_first_not_of(" \t");
+            name = b == std::string::npos ? std::string() : name.substr(b);
+            auto it = mtl_index.find(name);
+            current_material = it == mtl_index.end() ? -1 : it->second;
+        }
+        else if (strncmp(p, "mtllib", 6) == 0 && (p[6] == ' ' || p[6] == '\t'))
+        {
+            std::string name(p + 7);
+            while (!name.empty() && (name.back() == '\r' || name.back() == ' ' || name.back() == '\t')) name.pop_back();
+            size_t b = name.find_first_not_of(" \t");
+            name = b == std::string::npos ? std::string() : name.substr(b);
+            parse_mtl(folder.empty() ? name : folder + "/" + name, mtls, mtl_index);
+        }
+    }
+
+    const float kGamma = 2.2f;
+    const std::uint32_t kInvalidTextureIndex = 0xFF;
+    materials_.resize(mtls.size());
+    for (size_t i = 0; i < mtls.size(); ++i)
+    {
+        const MtlRecord& m = mtls[i];
+        if (m.has_texture) throw std::runtime_error("material uses image textures (map_*): not supported by this loader");
+        PackedMaterial& o = materials_[i];
+        o.diffuse_albedo = PackAlbedo(std::pow(m.diffuse[0], kGamma), std::pow(m.diffuse[1], kGamma), std::pow(m.diffuse[2], kGamma), kInvalidTextureIndex);
+        o.specular_albedo = PackAlbedo(std::pow(m.specular[0], kGamma), std::pow(m.specular[1], kGamma), std::pow(m.specular[2], kGamma), kInvalidTextureIndex);
+        o.emission = PackRGBE(m.emission[0], m.emission[1], m.emission[2]);
+        o.roughness_metalness = PackRoughnessMetalness(m.roughness, kInvalidTextureIndex, m.metallic, kInvalidTextureIndex);
+        o.ior_emission_idx_transparency = PackIorEmissionIdxTransparency(m.ior, kInvalidTextureIndex, m.transmittance[0], kInvalidTextureIndex);
+    }
+
+    auto flip = [flip_yz](float3& v) { if (flip_yz) { float t = v.y; v.y = v.z; v.z = t; v.y = -v.y; } };
+    triangles_.reserve(faces.size());
+    for (const Face& face : faces)
+    {
+        Triangle t;
+        memset(&t, 0, sizeof(t));
+        Vertex* vs[3] = { &t.v1, &t.v2, &t.v3 };
+        for (int k = 0; k < 3; ++k)
+        {
+            const Corner& c = face.c[k];
+            if (c.v < 0 || (size_t)c.v * 3 + 2 >= positions.size()) throw std::runtime_error("OBJ face references a missing vertex");
+            if (c.vn < 0 || (size_t)c.vn * 3 + 2 >= normals.size()) throw std::runtime_error("OBJ face has no normal (normals are required, scene.cpp:222-224)");
+            Vertex& v = *vs[k];
+            v.position = make_float3(positions[c.v * 3 + 0] * scale, positions[c.v * 3 + 1] * scale, positions[c.v * 3 + 2] * scale);
+            v.normal = make_float3(normals[c.vn * 3 + 0], normals[c.vn * 3 + 1], normals[c.vn * 3 + 2]);
+            v.texcoord = make_float3(c.vt < 0 ? 0.0f : texcoords[c.vt * 2 + 0], c.vt < 0 ? 0.0f : texcoords[c.vt * 2 + 1], 0.0f);
+            flip(v.position); flip(v.normal);
+        }
+        t.mtlIndex = (face.material >= 0 && (size_t)face.material < materials_.size()) ? (std::uint32_t)face.material : 0u;
+        triangles_.push_back(t);
+    }
+}
+
+void Scene::CollectEmissiveTriangles()
+{
+    emissive_indices_.clear();
+    for (std::uint32_t i = 0; i < triangles_.size(); ++i)
+        if (EmissionSum(materials_[triangles_[i].mtlIndex].emission) > 0.0f) emissive_indices_.push_back(i);
+    scene_info_.emissive_count = (std::uint32_t)emissive_indices_.size();
+}
+
+void Scene::AddPointLight(float3 origin, float3 radiance)
+{
+    Light l; memset(&l, 0, sizeof(l));
+    l.origin = origin; l.radiance = radiance; l.type = RT_LIGHT_TYPE_POINT;
+    lights_.push_back(l);
+}
+
+void Scene::AddDirectionalLight(float3 d, float3 radiance)
+{
+    // float3::Normalize (mathlib.hpp:47-48): each component divided by the length
+    float len = std::sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+    Light l; memset(&l, 0, sizeof(l));
+    l.origin = make_float3(d.x / len, d.y / len, d.z / len); l.radiance = radiance; l.type = RT_LIGHT_TYPE_DIRECTIONAL;
+    lights_.push_back(l);
+}
+
+void Scene::Finalize(const char* env_map_path)
+{
+    CollectEmissiveTriangles();
+    scene_info_.analytic_light_count = (std::uint32_t)lights_.size();
+    if (!LoadHDR(env_map_path, env_image_)) throw std::runtime_error(std::string("Failed to load environment map ") + env_map_path);
+}
+
+void Scene::Finalize(const float* env_rgba, std::uint32_t env_width, std::uint32_t env_height)
+{
+    CollectEmissiveTriangles();
+    scene_info_.analytic_light_count = (std::uint32_t)lights_.size();
+    env_image_.width = env_width; env_image_.height = env_height;
+    env_image_.data.assign(env_rgba, env_rgba + (size_t)env_width * env_height * 4);
+}
+
+// ------------------------------------------------------------------------------------------------ Radiance HDR
+namespace
+{
+struct Rgbe { unsigned char c[4]; };
+
+bool read_flat(std::vector<Rgbe>& line, size_t from, FILE* f)
+{   // old-style scanline with run markers (1,1,1,count)
+    int rshift = 0;
+    size_t i = from;
+    while (i < line.size())
+    {
+        int r = fgetc(f), g = fgetc(f), b = fgetc(f), e = fgetc(f);
+        if (e == EOF) return false;
+        if (r == 1 && g == 1 && b == 1)
+        {
+            for (int n = e << rshift; n > 0 && i < line.size(); --n) { line[i] = line[i - 1]; ++i; }
+            rshift += 8;
+        }
+        else { line[i].c[0] = (unsigned char)r; line[i].c[1] = (unsigned char)g; line[i].c[2] = (unsigned char)b; line[i].c[3] = (unsigned char)e; ++i; rshift = 0; }
+    }
+    return true;
+}
+
+bool read_scanline(std::vector<Rgbe>& line, FILE* f)
+{
+    size_t len = line.size();
+    if (len < 8 || len > 32767) return read_flat(line, 0, f);
+    int c0 = fgetc(f);
+    if (c0 != 2) { ungetc(c0, f); return read_flat(line, 0, f); }
+    int g = fgetc(f), b = fgetc(f), e = fgetc(f);
+    if (g != 2 || (b & 128))
+    {
+        line[0].c[0] = 2; line[0].c[1] = (unsigned char)g; line[0].c[2] = (unsigned char)b; line[0].c[3] = (unsigned char)e;
+        return read_flat(line, 1, f);
+    }
+    for (int comp = 0; comp < 4; ++comp)
+        for (size_t j = 0; j < len;)
+        {
+            int code = fgetc(f);
+            if (code == EOF) return false;
+            if (code > 128) { int n = code & 127, val = fgetc(f); while (n-- && j < len) line[j++].c[comp] = (unsigned char)val; }
+            else { int n = code; while (n-- && j < len) line[j++].c[comp] = (unsigned char)fgetc(f); }
+        }
+    return !feof(f);
+}
+} // namespace
+
+bool LoadHDR(const char* filename, Image& res)
+{
+    FILE* f = fopen(filename, "rb");
+    if (!f) return false;
+    char magic[10];
+    if (fread(magic, 10, 1, f) != 1 || memcmp(magic, "#?RADIANCE", 10) != 0) { fclose(f); return false; }
+    // header lines up to the empty line, then the resolution line "-Y h +X w"
+    int prev = 0, c = 0;
+    fgetc(f);
+    for (;;) { prev = c; c = fgetc(f); if (c == EOF) { fclose(f); return false; } if (c == '\n' && prev == '\n') break; }
+    char reso[200]; int n = 0;
+    for (;;) { c = fgetc(f); if (c == EOF || n >= 199) { fclose(f); return false; } reso[n++] = (char)c; if (c == '\n') break; }
+    reso[n] = 0;
+    long w = 0, h = 0;
+    if (sscanf(reso, "-Y %ld +X %ld", &h, &w) != 2 || w <= 0 || h <= 0) { fclose(f); return false; }
+    res.width = (std::uint32_t)w; res.height = (std::uint32_t)h;
+    res.data.assign((size_t)w * h * 4, 0.0f);
+    std::vector<Rgbe> line((size_t)w);
+    float* out = res.data.data();
+    for (long y = 0; y < h; ++y)
+    {
+        if (!read_scanline(line, f)) break;
+        for (long x = 0; x < w; ++x)
+        {   // hdr_loader.cpp:102-120: v = val / 256, d = 2^(E - 128)
+            float d = std::pow(2.0f, (float)((int)line[x].c[3] - 128));
+            out[0] = (line[x].c[0] / 256.0f) * d; out[1] = (line[x].c[1] / 256.0f) * d; out[2] = (line[x].c[2] / 256.0f) * d;
+            out += 4;
+        }
+    }
+    fclose(f);
+    return true;
+}
+
+} // namespace rt_host

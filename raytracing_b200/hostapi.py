@@ -1,0 +1,158 @@
+"""
+ctypes binding of raytracing_b200/librt_host.so: the C++ host side (Scene loader, SAH BVH builder,
+Integrator / CUDAPathTraceIntegrator, headless Render with RenderBackend::kCUDA) through the small C
+façade in host/host_capi.cpp.  Used by tests and bench.py; the C++ classes are the real interface.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .layouts import CAMERA_DT, NODE_DT, SCENE_ARRAYS, TRIANGLE_DT
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librt_host.so")
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(LIB_PATH)
+    L.rth_last_error.restype = C.c_char_p
+    L.rth_scene_load.restype = C.c_void_p
+    L.rth_scene_load.argtypes = [C.c_char_p, C.c_float, C.c_int]
+    L.rth_scene_free.argtypes = [C.c_void_p]
+    L.rth_scene_add_directional_light.argtypes = [C.c_void_p] + [C.c_float] * 6
+    L.rth_scene_add_point_light.argtypes = [C.c_void_p] + [C.c_float] * 6
+    L.rth_scene_build_bvh.argtypes = [C.c_void_p]
+    L.rth_scene_finalize_hdr.argtypes = [C.c_void_p, C.c_char_p]
+    L.rth_scene_finalize_image.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.rth_scene_query.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.rth_bvh_build.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
+    L.rth_default_camera.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+    L.rth_render_create.restype = C.c_void_p
+    L.rth_render_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_int, C.c_int]
+    L.rth_render_free.argtypes = [C.c_void_p]
+    L.rth_render_set_max_bounces.argtypes = [C.c_void_p, C.c_uint32]
+    L.rth_render_enable_white_furnace.argtypes = [C.c_void_p, C.c_int]
+    L.rth_render_set_sampler.argtypes = [C.c_void_p, C.c_int]
+    L.rth_render_frame.argtypes = [C.c_void_p]
+    L.rth_render_request_reset.argtypes = [C.c_void_p]
+    L.rth_render_image.restype = C.POINTER(C.c_float)
+    L.rth_render_image.argtypes = [C.c_void_p]
+    L.rth_render_context.restype = C.c_void_p
+    L.rth_render_context.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _err(L):
+    return HostError(L.rth_last_error().decode())
+
+
+def default_camera(width, height):
+    cam = np.zeros((), dtype=CAMERA_DT)
+    load_library().rth_default_camera(width, height, cam.ctypes.data)
+    return cam
+
+
+def build_bvh(triangles):
+    """Host SAH build over a triangle array -> (triangles in leaf order, LinearBVHNode[], max depth)."""
+    L = load_library()
+    t = np.ascontiguousarray(triangles, dtype=TRIANGLE_DT).copy()
+    nodes = np.zeros(2 * t.shape[0], dtype=NODE_DT)
+    n, depth = C.c_size_t(), C.c_uint32()
+    if L.rth_bvh_build(t.ctypes.data, t.shape[0], nodes.ctypes.data, C.byref(n), C.byref(depth)) != 0:
+        raise _err(L)
+    return t, nodes[: n.value].copy(), depth.value
+
+
+class HostScene:
+    """rt_host::Scene (+ an rt_host::Bvh) behind a handle."""
+
+    def __init__(self, obj_path, scale=1.0, flip_yz=False):
+        self.L = load_library()
+        self.h = self.L.rth_scene_load(obj_path.encode(), scale, int(flip_yz))
+        if not self.h:
+            raise _err(self.L)
+
+    def add_directional_light(self, d, rgb): self.L.rth_scene_add_directional_light(self.h, *map(float, d), *map(float, rgb))
+    def add_point_light(self, p, rgb): self.L.rth_scene_add_point_light(self.h, *map(float, p), *map(float, rgb))
+
+    def build_bvh(self):
+        if self.L.rth_scene_build_bvh(self.h) != 0:
+            raise _err(self.L)
+
+    def finalize(self, env_path=None, env=None, env_width=0, env_height=0):
+        if env_path is not None:
+            if self.L.rth_scene_finalize_hdr(self.h, env_path.encode()) != 0:
+                raise _err(self.L)
+        else:
+            e = np.ascontiguousarray(env, dtype="<f4")
+            self.L.rth_scene_finalize_image(self.h, e.ctypes.data, env_width, env_height)
+
+    def arrays(self) -> dict:
+        out = {}
+        for i, (name, dt) in enumerate(SCENE_ARRAYS):
+            p, n, e0, e1 = C.c_void_p(), C.c_size_t(), C.c_uint32(), C.c_uint32()
+            self.L.rth_scene_query(self.h, i, C.byref(p), C.byref(n), C.byref(e0), C.byref(e1))
+            nbytes = n.value * dt.itemsize
+            buf = (C.c_char * nbytes).from_address(p.value) if nbytes else b""
+            out[name] = np.frombuffer(bytes(buf), dtype=dt).copy()
+            if name == "env":
+                out["env_width"], out["env_height"] = e0.value, e1.value
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.rth_scene_free(self.h)
+            self.h = None
+
+
+class HostRender:
+    """rt_host::Render(width, height, RenderBackend::kCUDA, scene): builds the BVH, finalizes the scene, creates the
+    CUDAPathTraceIntegrator and uploads, like Render::Render in the reference (render.cpp:38-83)."""
+
+    def __init__(self, scene: HostScene, width, height, env_path, device=0, stepwise=False):
+        self.L = scene.L
+        self.width, self.height = width, height
+        self.h = self.L.rth_render_create(scene.h, width, height, env_path.encode(), device, int(stepwise))
+        if not self.h:
+            raise _err(self.L)
+
+    def set_max_bounces(self, b):
+        if self.L.rth_render_set_max_bounces(self.h, b) != 0:
+            raise _err(self.L)
+
+    def enable_white_furnace(self, e):
+        if self.L.rth_render_enable_white_furnace(self.h, int(e)) != 0:
+            raise _err(self.L)
+
+    def set_blue_noise(self, e):
+        if self.L.rth_render_set_sampler(self.h, int(e)) != 0:
+            raise _err(self.L)
+
+    def render_frame(self):
+        if self.L.rth_render_frame(self.h) != 0:
+            raise _err(self.L)
+
+    def request_reset(self): self.L.rth_render_request_reset(self.h)
+
+    def image(self):
+        p = self.L.rth_render_image(self.h)
+        return np.ctypeslib.as_array(p, shape=(self.height, self.width, 4)).copy()
+
+    def context_handle(self): return self.L.rth_render_context(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.rth_render_free(self.h)
+            self.h = None
