@@ -47,9 +47,10 @@ def algorithmic_bytes(st, mb, n_pix):
     n_unocc, n_emis = s("n_unoccluded"), s("n_emissive_hits")
     v_ext, t_ext, v_sh, t_sh = s("nodes_ext"), s("tris_ext"), s("nodes_shadow"), s("tris_shadow")
     raygen = 52.0 * n_pix
-    extend = (48 * n_ext + 48 * (v_ext + t_ext) + 52 * n_miss + 264 * n_hit + 52 * n_shadow + 36 * n_cont + 32 * n_emis).sum()
-    shadow = (36 * n_shadow + 48 * (v_sh + t_sh) + 4 * n_shadow + 52 * n_unocc).sum()
-    return raygen + extend + shadow, extend, shadow
+    trace = (48 * n_ext + 48 * (v_ext + t_ext)).sum()                                     # Ray in, Hit out, node + triangle fetches
+    shade = (52 * n_miss + 264 * n_hit + 52 * n_shadow + 36 * n_cont + 32 * n_emis).sum() # miss + hit-surface streams
+    shadow = (36 * n_shadow + 48 * (v_sh + t_sh) + 4 * n_shadow + 52 * n_unocc).sum()     # any-hit trace + accumulate
+    return raygen + trace + shade + shadow, trace, shade, shadow
 
 
 class ClockSampler(threading.Thread):
@@ -174,6 +175,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="CornellBox", choices=sorted(WORKLOADS))
     ap.add_argument("--stepwise", action="store_true", help="time the one-kernel-per-reference-step schedule instead of the fused one")
+    ap.add_argument("--monolithic", action="store_true", help="fused schedule with ONE extend+shade kernel instead of trace -> queues -> shade")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     workload = WORKLOADS[args.scene]
@@ -205,6 +207,8 @@ def main():
     ctx = capi.Context(w, h, device=local_rank, rank=rank, world=world)
     ctx.upload_scene(scene)
     ctx.set_camera(cam)
+    if args.monolithic:
+        ctx.set_option(capi.OPT_FUSION, 1)
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
 
     # the local radiance slab as a torch tensor (zero copy) for the NCCL gather
@@ -242,7 +246,9 @@ def main():
     if world > 1:
         dist.all_reduce(counters)
     rays_per_frame = float(counters[0] + counters[1])
-    alg_total, alg_extend, alg_shadow = float(counters[2]), float(counters[3]), float(counters[4])
+    alg_total, alg_trace, alg_shade, alg_shadow = (float(counters[i]) for i in (2, 3, 4, 5))
+    alg_of = {"trace_closest": alg_trace, "shade_queues": alg_shade, "shadow_accumulate": alg_shadow, "extend_shade": alg_trace + alg_shade,
+              "intersect": alg_trace, "hit": alg_shade, "intersect_shadow": alg_shadow}
 
     # ---- warm-up, then K timed steps: barrier + synchronize on both sides, CUDA events on the launching stream
     for _ in range(args.warmup):
@@ -294,18 +300,16 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        dom = "shadow_accumulate" if ktimes["shadow_accumulate"][0] > ktimes["extend_shade"][0] else "extend_shade"
-        if args.stepwise:
-            dom = "intersect"
+        dom = max(alg_of, key=lambda k: ktimes[k][0])          # the kernel class with the largest share of the step
         dom_ms, dom_n = ktimes[dom]
-        dom_bytes_frame = {"extend_shade": alg_extend, "shadow_accumulate": alg_shadow, "intersect": alg_extend}[dom] / world
+        dom_bytes_frame = alg_of[dom] / world
         achieved = (dom_bytes_frame * args.steps / (dom_ms * 1e-3) / 1e9) if dom_ms > 0 else None
         line = {
             "metric": "Mrays/sec @1920x1080x8-bounce", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{name} {w}x{h} 1spp {mb}-bounce, default camera, sample_idx 0, Reset+Integrate per step",
-                       "schedule": "stepwise" if args.stepwise else "fused", "partition": f"scanline y%{world}",
+                       "schedule": "stepwise" if args.stepwise else ("fused-monolithic" if args.monolithic else "fused: trace -> hit/miss queues -> shade, shadow+accumulate"), "partition": f"scanline y%{world}",
                        "rays_per_step": rays_per_frame,
                        "l2": "per-step working set (ray/shadow queues + radiance, ~365 MB at 1080p) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_ms[0]), "h2d_bytes_per_step": 64,

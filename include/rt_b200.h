@@ -66,8 +66,10 @@ typedef enum RtOption {
     RT_OPT_COUNT_TRAVERSAL = 16,/* 1: kernels also count BVH nodes visited / triangles tested (slower; for
                                    the algorithmic-bytes figure of the roofline)     */
     RT_OPT_KERNEL_TIMING = 17,  /* 1: bracket every launch with CUDA events on the context's stream */
-    RT_OPT_TRAVERSAL = 18       /* 0: literal reference-order traversal on the reference node layout,
+    RT_OPT_TRAVERSAL = 18,      /* 0: literal reference-order traversal on the reference node layout,
                                    1: optimised traversal (default); results are bit-identical */
+    RT_OPT_FUSION = 19          /* rt_extend_shade: 0 = traversal kernel + hit/miss queue compaction + shading kernel
+                                   (default), 1 = one monolithic kernel; results are bit-identical */
 } RtOption;
 
 #define RT_MAX_BOUNCES 255u     /* bounce index range supported per frame (reference GUI: 0..5) */
@@ -90,7 +92,7 @@ typedef struct RtFrameStats {
 typedef enum RtKernelClass {
     RT_K_RAYGEN = 0, RT_K_INTERSECT = 1, RT_K_MISS = 2, RT_K_HIT = 3, RT_K_INTERSECT_SHADOW = 4,
     RT_K_ACCUMULATE = 5, RT_K_EXTEND_SHADE = 6, RT_K_SHADOW_ACCUMULATE = 7, RT_K_RESOLVE = 8,
-    RT_K_AOV = 9, RT_K_MISC = 10, RT_K_CLASS_COUNT = 11
+    RT_K_AOV = 9, RT_K_MISC = 10, RT_K_TRACE_CLOSEST = 11, RT_K_SHADE_QUEUES = 12, RT_K_CLASS_COUNT = 13
 } RtKernelClass;
 
 /* ---- lifetime ------------------------------------------------------------------ */

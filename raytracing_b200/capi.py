@@ -16,9 +16,9 @@ LIB_PATH = os.path.join(HERE, "librt_b200.so")
 MAX_BOUNCES = 255
 
 OPT_WHITE_FURNACE, OPT_SAMPLER, OPT_AOV, OPT_DENOISER = 0, 1, 2, 3
-OPT_COUNT_TRAVERSAL, OPT_KERNEL_TIMING, OPT_TRAVERSAL = 16, 17, 18
+OPT_COUNT_TRAVERSAL, OPT_KERNEL_TIMING, OPT_TRAVERSAL, OPT_FUSION = 16, 17, 18, 19
 KERNEL_CLASSES = ["raygen", "intersect", "miss", "hit", "intersect_shadow", "accumulate", "extend_shade",
-                  "shadow_accumulate", "resolve", "aov", "misc"]
+                  "shadow_accumulate", "resolve", "aov", "misc", "trace_closest", "shade_queues"]
 
 # every symbol include/rt_b200.h declares
 SYMBOLS = ["rt_create", "rt_destroy", "rt_last_error", "rt_set_partition", "rt_upload_scene", "rt_set_camera", "rt_set_option",

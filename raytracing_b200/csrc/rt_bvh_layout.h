@@ -24,6 +24,7 @@
  */
 #pragma once
 
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -126,6 +127,93 @@ inline bool build_layout(const RtLinearBVHNode* nodes, uint64_t n_nodes, const R
         out.tris[i * 3 + 2] = F4{ e2z, fl, 0.0f, 0.0f };
     }
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Shading records.  Everything below is a pure function of the uploaded scene evaluated ONCE on the host
+// with the same IEEE binary32 operations, in the same order, that the reference performs per hit on the
+// device (x86-64 baseline ISA has no FMA; the file is compiled with -ffp-contract=off), so the kernels
+// load a few float4 instead of recomputing them per path vertex.  Results are bit-identical.
+//
+//   tri_shade: 7 x float4 per triangle (112 B instead of the reference's 160-byte Triangle):
+//      [0] p1.xyz, mtlIndex bits   [1] p2.xyz, gn.x   [2] p3.xyz, gn.y   [3] n1.xyz, gn.z
+//      [4] n2.xyz, uv1.x           [5] n3.xyz, uv1.y  [6] uv2.xy, uv3.xy
+//      gn = normalize(cross(p2 - p1, p3 - p1)), hit_surface.cl:91
+//   mat_rec: 4 x float4 per material: [0] diffuse.rgb, roughness  [1] specular.rgb, metalness
+//      [2] emission.rgb, ior  [3] transparency, has_texture flag   (utils.h:133-190, material.h:251-264)
+//   light_rec: 2 x float4 per light: [0] point: origin.xyz | directional: normalize(origin*MAX_RENDER_DIST),
+//      w = |origin*MAX_RENDER_DIST|   [1] radiance.xyz, type bits   (light.h:30-65, hit_surface.cl:122-123)
+
+inline float bits_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+inline void normalize3(float x, float y, float z, float* out)
+{
+    float inv = 1.0f / sqrtf(x * x + y * y + z * z);        // same association as rt::dot / rt::normalize
+    out[0] = x * inv; out[1] = y * inv; out[2] = z * inv;
+}
+
+inline void build_tri_shade(const RtTriangle* tris, uint64_t n, std::vector<F4>& out)
+{
+    out.resize((size_t)n * 7);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const RtTriangle& t = tris[i];
+        const RtFloat3 &p1 = t.v1.position, &p2 = t.v2.position, &p3 = t.v3.position;
+        float e1x = p2.x - p1.x, e1y = p2.y - p1.y, e1z = p2.z - p1.z;
+        float e2x = p3.x - p1.x, e2y = p3.y - p1.y, e2z = p3.z - p1.z;
+        float cx = e1y * e2z - e1z * e2y, cy = e1z * e2x - e1x * e2z, cz = e1x * e2y - e1y * e2x;
+        float gn[3];
+        normalize3(cx, cy, cz, gn);
+        F4* r = &out[(size_t)i * 7];
+        r[0] = F4{ p1.x, p1.y, p1.z, bits_float(t.mtlIndex) };
+        r[1] = F4{ p2.x, p2.y, p2.z, gn[0] };
+        r[2] = F4{ p3.x, p3.y, p3.z, gn[1] };
+        r[3] = F4{ t.v1.normal.x, t.v1.normal.y, t.v1.normal.z, gn[2] };
+        r[4] = F4{ t.v2.normal.x, t.v2.normal.y, t.v2.normal.z, t.v1.texcoord.x };
+        r[5] = F4{ t.v3.normal.x, t.v3.normal.y, t.v3.normal.z, t.v1.texcoord.y };
+        r[6] = F4{ t.v2.texcoord.x, t.v2.texcoord.y, t.v3.texcoord.x, t.v3.texcoord.y };
+    }
+}
+
+inline void build_mat_rec(const RtPackedMaterial* mats, uint64_t n, std::vector<F4>& out)
+{
+    out.resize((size_t)n * 4);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const RtPackedMaterial& m = mats[i];
+        auto rgb = [](uint32_t d, float* o) { o[0] = (float)(d & 0xFF) / 255.0f; o[1] = (float)((d >> 8) & 0xFF) / 255.0f; o[2] = (float)((d >> 16) & 0xFF) / 255.0f; };
+        float dif[3], spec[3];
+        rgb(m.diffuse_albedo, dif); rgb(m.specular_albedo, spec);
+        float f = ldexpf(1.0f, (int)(m.emission >> 24) - (128 + 8));
+        float em[3] = { (float)(int)(m.emission & 0xFF) * f, (float)(int)((m.emission >> 8) & 0xFF) * f, (float)(int)((m.emission >> 16) & 0xFF) * f };
+        uint32_t rm = m.roughness_metalness, it = m.ior_emission_idx_transparency;
+        bool textured = (m.diffuse_albedo >> 24) != 0xFF || (m.specular_albedo >> 24) != 0xFF || ((rm >> 8) & 0xFF) != 0xFF ||
+                        (rm >> 24) != 0xFF || ((it >> 8) & 0xFF) != 0xFF || (it >> 24) != 0xFF;
+        F4* r = &out[(size_t)i * 4];
+        r[0] = F4{ dif[0], dif[1], dif[2], (float)(rm & 0xFF) / 255.0f };
+        r[1] = F4{ spec[0], spec[1], spec[2], (float)((rm >> 16) & 0xFF) / 255.0f };
+        r[2] = F4{ em[0], em[1], em[2], (float)(it & 0xFF) / 25.5f };
+        r[3] = F4{ (float)((it >> 16) & 0xFF) / 255.0f, bits_float(textured ? 1u : 0u), 0.0f, 0.0f };
+    }
+}
+
+inline void build_light_rec(const RtLight* lights, uint64_t n, std::vector<F4>& out)
+{
+    out.resize((size_t)n * 2);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const RtLight& l = lights[i];
+        F4* r = &out[(size_t)i * 2];
+        if (l.type == RT_LIGHT_TYPE_POINT) r[0] = F4{ l.origin.x, l.origin.y, l.origin.z, 0.0f };
+        else
+        {
+            float vx = l.origin.x * RT_MAX_RENDER_DIST, vy = l.origin.y * RT_MAX_RENDER_DIST, vz = l.origin.z * RT_MAX_RENDER_DIST;
+            float d2 = vx * vx + vy * vy + vz * vz;
+            float len = sqrtf(d2), inv = 1.0f / sqrtf(d2);
+            r[0] = F4{ vx * inv, vy * inv, vz * inv, len };
+        }
+        r[1] = F4{ l.radiance.x, l.radiance.y, l.radiance.z, bits_float(l.type) };
+    }
 }
 
 } // namespace rtbvh

@@ -115,9 +115,10 @@ struct DevScene
 {
     const float4* nodes_ref;       // reference LinearBVHNode[]: 3 x float4 per node
     const float4* tris_ref;        // RTTriangle[]: 3 x float4 (positions), cl_pt_integrator.cpp:392-402
-    const float4* triangles;       // reference Triangle[]: 10 x float4 per triangle
-    const uint32_t* materials;     // PackedMaterial[]: 5 x uint32
-    const float4* lights;          // Light[]: 3 x float4
+    const float4* tri_shade;       // 7 x float4 per triangle: positions, normals, uvs, material, geometric normal (rt_bvh_layout.h)
+    const uint32_t* materials;     // PackedMaterial[]: 5 x uint32 (only read for textured materials)
+    const float4* mat_rec;         // 4 x float4 per material: unpacked constants (rt_bvh_layout.h)
+    const float4* light_rec;       // 2 x float4 per light
     const int4* textures;          // Texture[]
     const uint32_t* texels;
     const float4* env;             // RGBA32F
@@ -208,6 +209,23 @@ __device__ __forceinline__ Material unpack_material(const DevScene& sc, uint32_t
     m.transparency = (float)((w4 >> 16) & 0xFF) / 255.0f;
     if (((w4 >> 8) & 0xFF) != RT_INVALID_TEXTURE_IDX) m.emission = m.emission * pow3(sample_texture(sc, (w4 >> 8) & 0xFF, uv), 2.2f);
     if ((w4 >> 24) != RT_INVALID_TEXTURE_IDX) m.transparency *= sample_texture(sc, w4 >> 24, uv).x;
+    return m;
+}
+
+// Untextured materials (every material of the shipped scenes): the unpack of material.h:251-264 /
+// utils.h:123-190 is a pure function of the 20 packed bytes, so rt_upload_scene evaluates it once per
+// material on the host with the same IEEE operations (rt_bvh_layout.h) and the kernel loads the result.
+__device__ __forceinline__ Material load_material(const DevScene& sc, uint32_t mtl_index, f2 uv)
+{
+    const float4* r = sc.mat_rec + (size_t)mtl_index * 4;
+    float4 r3 = __ldg(r + 3);
+    if (__float_as_uint(r3.y) != 0u) return unpack_material(sc, mtl_index, uv);     // has a texture: per-hit path
+    float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+    Material m;
+    m.diffuse_albedo = mk3(r0); m.roughness = r0.w;
+    m.specular_albedo = mk3(r1); m.metalness = r1.w;
+    m.emission = mk3(r2); m.ior = r2.w;
+    m.transparency = r3.x;
     return m;
 }
 
@@ -331,24 +349,28 @@ __device__ __forceinline__ f3 sample_bxdf(float s1, f2 s, Material m, f3 normal,
     return bxdf;
 }
 
-// kernels/common/light.h:30-65
-__device__ __forceinline__ f3 light_sample(const DevScene& sc, f3 position, float s, f3& outgoing, float& pdf)
+// kernels/common/light.h:30-65 followed by hit_surface.cl:122-123 (length + normalize of the direction).
+// For directional lights `outgoing = origin * MAX_RENDER_DIST`, its length and its normalisation are constants
+// of the light: computed once at upload with the same operations (rt_bvh_layout.h).
+__device__ __forceinline__ f3 light_sample(const DevScene& sc, f3 position, float s, f3& outgoing_n, float& distance, float& pdf)
 {
     int n = (int)sc.light_count;
     int idx = (int)(s * (float)sc.light_count);
     idx = idx < 0 ? 0 : (idx > n - 1 ? n - 1 : idx);
-    float4 lo = __ldg(sc.lights + (size_t)idx * 3), lr = __ldg(sc.lights + (size_t)idx * 3 + 1), lt = __ldg(sc.lights + (size_t)idx * 3 + 2);
+    float4 l0 = __ldg(sc.light_rec + (size_t)idx * 2), l1 = __ldg(sc.light_rec + (size_t)idx * 2 + 1);
     pdf = 1.0f / (float)sc.light_count;
-    f3 radiance = mk3(lr);
-    if (__float_as_uint(lt.x) == RT_LIGHT_TYPE_POINT)
+    f3 radiance = mk3(l1);
+    if (__float_as_uint(l1.w) == RT_LIGHT_TYPE_POINT)
     {
-        f3 to_light = mk3(lo) - position;
+        f3 to_light = mk3(l0) - position;
         radiance = radiance / dot(to_light, to_light);
-        outgoing = to_light;
+        distance = length(to_light);
+        outgoing_n = normalize(to_light);
     }
     else
     {
-        outgoing = mk3(lo) * RT_MAX_RENDER_DIST;
+        outgoing_n = mk3(l0);
+        distance = l0.w;
     }
     return radiance;
 }

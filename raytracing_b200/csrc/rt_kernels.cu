@@ -12,8 +12,12 @@
  *   shadow-ray queue:            A = (origin.xyz, pixel_idx bits)
  *                                B = (dir.xyz, t_max = distance to light)
  *                                C = (light sample.xyz, -)
+ *   hit queue:                   (bc.x, bc.y, primitive_id bits, ray slot bits)   — rays that hit, compacted
+ *   miss queue:                  ray slot (uint32)                                — rays that missed, compacted
  *   hits (stepwise path only):   (bc.x, bc.y, primitive_id bits, t)
  *   radiance:                    float4 per LOCAL pixel (scanline partition, see rt_set_partition)
+ * "pixel_idx bits" is the pixel packed as x | y << 16 (the RNG and the radiance index need x and y, never the
+ * linear index, and this saves two integer divisions per path vertex); the API converts back.
  * The reference keeps throughput in a per-pixel buffer that every bounce scatters to
  * (hit_surface.cl:105,166); there is at most one live path per pixel, so carrying it in
  * the ray stream is equivalent and turns the scatter into a coalesced stream.
@@ -46,7 +50,9 @@ struct DevCounters
     uint32_t n_miss[RT_MAX_BOUNCES + 1];
     uint32_t n_emissive[RT_MAX_BOUNCES + 1];
     uint32_t n_unoccluded[RT_MAX_BOUNCES + 1];
+    uint32_t hit_count[RT_MAX_BOUNCES + 1];      // entries of the hit queue (queue-split schedule)
     uint32_t work_ext[RT_MAX_BOUNCES + 1];       // persistent-kernel work cursors
+    uint32_t work_shade[RT_MAX_BOUNCES + 1];
     uint32_t work_shadow[RT_MAX_BOUNCES + 1];
     unsigned long long nodes_ext[RT_MAX_BOUNCES + 1], tris_ext[RT_MAX_BOUNCES + 1];
     unsigned long long nodes_shadow[RT_MAX_BOUNCES + 1], tris_shadow[RT_MAX_BOUNCES + 1];
@@ -58,6 +64,8 @@ struct Queues
     float4* sA; float4* sB; float4* sC;
     float4* hits;
     uint32_t* shadow_flags;
+    float4* hitq;
+    uint32_t* missq;
 };
 
 struct FrameParams
@@ -66,9 +74,11 @@ struct FrameParams
     int white_furnace;
 };
 
-__device__ __forceinline__ uint32_t local_index(const FrameParams& p, uint32_t px, uint32_t py)
+__device__ __forceinline__ uint32_t pack_pixel(uint32_t px, uint32_t py) { return px | (py << 16); }
+__device__ __forceinline__ uint32_t local_index(const FrameParams& p, uint32_t pxy)
 {
-    return (py / p.world) * p.width + px;
+    uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
+    return (p.world == 1 ? py : py / p.world) * p.width + px;
 }
 
 // warp-aggregated append: one atomic per warp, lanes get consecutive slots (coalesced stores).
@@ -295,33 +305,37 @@ struct ShadeOut
 };
 
 // kernels/cl/miss.cl:41-77: radiance += sky * throughput
-__device__ __forceinline__ void shade_miss(const DevScene& sc, const FrameParams& p, float4* radiance, uint32_t pixel, f3 dir, f3 throughput)
+__device__ __forceinline__ void shade_miss(const DevScene& sc, const FrameParams& p, float4* radiance, uint32_t pxy, f3 dir, f3 throughput)
 {
     f3 sky = p.white_furnace ? splat(0.5f) : sample_sky(sc, dir);
     f3 add = sky * throughput;
-    uint32_t li = local_index(p, pixel % p.width, pixel / p.width);
+    uint32_t li = local_index(p, pxy);
     float4 r = radiance[li];
     r.x += add.x; r.y += add.y; r.z += add.z;
     radiance[li] = r;
 }
 
 // kernels/cl/hit_surface.cl:30-186
-__device__ __forceinline__ void shade_hit(const DevScene& sc, const FrameParams& p, uint32_t bounce, uint32_t pixel,
+__device__ __forceinline__ void shade_hit(const DevScene& sc, const FrameParams& p, uint32_t bounce, uint32_t pxy,
                                           f3 ray_dir, f3 hit_throughput, uint32_t prim, float u, float v, ShadeOut& out)
 {
     f3 incoming = -ray_dir;
-    uint32_t px = pixel % p.width, py = pixel / p.width;
-    const float4* tp = sc.triangles + (size_t)prim * 10;
-    f3 p1 = mk3(__ldg(tp)), uv1 = mk3(__ldg(tp + 1)), n1 = mk3(__ldg(tp + 2));
-    f3 p2 = mk3(__ldg(tp + 3)), uv2 = mk3(__ldg(tp + 4)), n2 = mk3(__ldg(tp + 5));
-    f3 p3 = mk3(__ldg(tp + 6)), uv3 = mk3(__ldg(tp + 7)), n3 = mk3(__ldg(tp + 8));
-    uint32_t mtl = __float_as_uint(__ldg(tp + 9).x);
+    uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
+    const float4* tp = sc.tri_shade + (size_t)prim * 7;
+    float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2), r3 = __ldg(tp + 3), r4 = __ldg(tp + 4), r5 = __ldg(tp + 5);
+    f3 p1 = mk3(r0), p2 = mk3(r1), p3 = mk3(r2), n1 = mk3(r3), n2 = mk3(r4), n3 = mk3(r5);
+    uint32_t mtl = __float_as_uint(r0.w);
+    f3 geometry_normal = mk3(r1.w, r2.w, r3.w);       // normalize(cross(p2-p1, p3-p1)), precomputed at upload
     float w0 = 1.0f - u - v;
     f3 position = p1 * w0 + p2 * u + p3 * v;
-    f3 geometry_normal = normalize(cross(p2 - p1, p3 - p1));
-    f2 texcoord; texcoord.x = uv1.x * w0 + uv2.x * u + uv3.x * v; texcoord.y = uv1.y * w0 + uv2.y * u + uv3.y * v;
     f3 normal = normalize(n1 * w0 + n2 * u + n3 * v);
-    Material material = unpack_material(sc, mtl, texcoord);
+    f2 texcoord; texcoord.x = 0.0f; texcoord.y = 0.0f;
+    if (__float_as_uint(__ldg(sc.mat_rec + (size_t)mtl * 4 + 3).y) != 0u)
+    {   // texture coordinates are only needed by textured materials (hit_surface.cl:96-97)
+        float4 r6 = __ldg(tp + 6);
+        texcoord.x = r4.w * w0 + r6.x * u + r6.z * v; texcoord.y = r5.w * w0 + r6.y * u + r6.w * v;
+    }
+    Material material = load_material(sc, mtl, texcoord);
 
     out.emissive = false;
     if (!p.white_furnace && dot(material.emission, splat(1.0f)) > 0.0f)
@@ -332,10 +346,8 @@ __device__ __forceinline__ void shade_hit(const DevScene& sc, const FrameParams&
     uint32_t pixel_seed = sample_seed_pixel(px, py, p.sample_idx);
     {   // direct lighting (next-event estimation on analytic lights)
         float s_light = sample_random(pixel_seed, bounce, SAMPLE_LIGHT);
-        f3 outgoing; float pdf;
-        f3 light_radiance = light_sample(sc, position, s_light, outgoing, pdf);
-        float distance_to_light = length(outgoing);
-        outgoing = normalize(outgoing);
+        f3 outgoing; float pdf, distance_to_light;
+        f3 light_radiance = light_sample(sc, position, s_light, outgoing, distance_to_light, pdf);
         f3 brdf = evaluate_material(material, normal, incoming, outgoing);
         f3 ls = light_radiance * hit_throughput * brdf / pdf * fmaxf(dot(outgoing, normal), 0.0f);
         out.spawn_shadow = (pdf > 0.0f) && (dot(ls, ls) > 0.0f);
@@ -374,7 +386,7 @@ __global__ void __launch_bounds__(256) k_raygen(FrameParams p, RayGenConsts c, Q
     uint32_t pixel = py * p.width + px;
     f3 o, d;
     generate_primary_ray(c, pixel, px, py, p.sample_idx, o, d);
-    q.A[0][li] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
+    q.A[0][li] = make_float4(o.x, o.y, o.z, __uint_as_float(pack_pixel(px, py)));
     q.B[0][li] = make_float4(d.x, d.y, d.z, RT_MAX_RENDER_DIST);
     q.C[0][li] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
 }
@@ -423,7 +435,7 @@ __device__ __forceinline__ void emit_rays(const FrameParams& p, Queues& q, DevCo
     int out = (bounce + 1) & 1;
     if (hit && so.emissive)
     {
-        uint32_t li = local_index(p, pixel % p.width, pixel / p.width);
+        uint32_t li = local_index(p, pixel);
         float4 r = radiance[li];
         r.x += so.emission_add.x; r.y += so.emission_add.y; r.z += so.emission_add.z;
         radiance[li] = r;
@@ -501,7 +513,7 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams p, Queues q, Dev
         {
             float4 a = q.sA[i], c = q.sC[i];
             uint32_t pixel = __float_as_uint(a.w);
-            uint32_t li = local_index(p, pixel % p.width, pixel / p.width);
+            uint32_t li = local_index(p, pixel);
             float4 r = radiance[li];
             r.x += c.x; r.y += c.y; r.z += c.z;
             radiance[li] = r;
@@ -573,7 +585,7 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(FrameParams p, DevSce
             {
                 float4 c = q.sC[i];
                 uint32_t pixel = __float_as_uint(a.w);
-                uint32_t li = local_index(p, pixel % p.width, pixel / p.width);
+                uint32_t li = local_index(p, pixel);
                 float4 r = radiance[li];
                 r.x += c.x; r.y += c.y; r.z += c.z;
                 radiance[li] = r;
@@ -582,6 +594,89 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(FrameParams p, DevSce
         warp_count(&ctr->n_unoccluded[bounce], un);
     }
     if (COUNT) { warp_sum64(&ctr->nodes_shadow[bounce], nv); warp_sum64(&ctr->tris_shadow[bounce], nt); }
+}
+
+// ---- queue-split schedule (default): hit/miss stream compaction between traversal and shading --------------
+// Traversal and shading are separate persistent kernels: the traversal kernel stays small in registers
+// (more resident warps to hide the dependent node fetches), and it compacts its results into a HIT queue and a
+// MISS queue with one warp-aggregated atomic each (__ballot + __popc), so that the shading kernel runs full
+// warps of hits (Lambert/GGX + NEE) and full warps of misses (environment lookup) instead of warps that
+// mix the two and idle through each other's code.  Both kernels drain their queues through a global atomic
+// cursor, 32 entries per grab.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) k_trace_closest(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, uint32_t bounce)
+{
+    const uint32_t n = ctr->q_count[bounce];
+    const int in = bounce & 1;
+    const int lane = threadIdx.x & 31;
+    uint32_t nv = 0, nt = 0;
+    for (;;)
+    {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->work_ext[bounce], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + lane;
+        bool live = i < n, hit = false;
+        float bu = 0.0f, bv = 0.0f, bt = 0.0f;
+        uint32_t prim = RT_INVALID_ID;
+        if (live)
+        {
+            float4 a = q.A[in][i], b = q.B[in][i];
+            prim = trace<false, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
+            hit = prim != RT_INVALID_ID;
+        }
+        uint32_t hi = warp_append(&ctr->hit_count[bounce], hit);
+        if (hit) q.hitq[hi] = make_float4(bu, bv, __uint_as_float(prim), __uint_as_float(i));
+        bool miss = live && !hit;
+        uint32_t mi = warp_append(&ctr->n_miss[bounce], miss);
+        if (miss) q.missq[mi] = i;
+    }
+    if (COUNT) { warp_sum64(&ctr->nodes_ext[bounce], nv); warp_sum64(&ctr->tris_ext[bounce], nt); }
+}
+
+// ShadeSurfaceHits over the hit queue, then ShadeMissedRays over the miss queue (independent pixels).
+__global__ void __launch_bounds__(256) k_shade_queues(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
+{
+    const uint32_t n_hit = ctr->hit_count[bounce], n_miss = ctr->n_miss[bounce];
+    const uint32_t hit_span = (n_hit + 31u) & ~31u;            // warps never mix hits and misses
+    const uint32_t total = hit_span + n_miss;
+    const int in = bounce & 1;
+    const int lane = threadIdx.x & 31;
+    for (;;)
+    {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->work_shade[bounce], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        if (base < hit_span)
+        {
+            uint32_t k = base + lane;
+            bool hit = k < n_hit;
+            uint32_t pixel = 0;
+            ShadeOut so;
+            so.emissive = so.spawn_next = so.spawn_shadow = false;
+            if (hit)
+            {
+                float4 h = q.hitq[k];
+                uint32_t i = __float_as_uint(h.w);
+                float4 a = q.A[in][i], b = q.B[in][i], c = q.C[in][i];
+                pixel = __float_as_uint(a.w);
+                shade_hit(sc, p, bounce, pixel, mk3(b), mk3(c), __float_as_uint(h.z), h.x, h.y, so);
+            }
+            emit_rays(p, q, ctr, radiance, bounce, pixel, hit, so);
+        }
+        else
+        {
+            uint32_t k = base - hit_span + lane;
+            if (k < n_miss)
+            {
+                uint32_t i = q.missq[k];
+                float4 a = q.A[in][i], b = q.B[in][i], c = q.C[in][i];
+                shade_miss(sc, p, radiance, __float_as_uint(a.w), mk3(b), mk3(c));
+            }
+        }
+    }
 }
 
 // resolve_radiance.cl:31-86 (shaded colour): hdr = radiance / sample_count; ldr = hdr / (hdr + 1)
@@ -596,14 +691,15 @@ __global__ void __launch_bounds__(256) k_resolve(const float4* radiance, float4*
     out[i] = make_float4(ldr.x, ldr.y, ldr.z, 1.0f);
 }
 
-__global__ void k_unpack_rays(const float4* A, const float4* B, const uint32_t* count, RtRay* rays, uint32_t* pixels)
+__global__ void k_unpack_rays(const float4* A, const float4* B, const uint32_t* count, uint32_t width, RtRay* rays, uint32_t* pixels)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *count) return;
     float4 a = A[i], b = B[i];
     rays[i].origin = RtFloat3{ a.x, a.y, a.z, 0.0f };
     rays[i].direction = RtFloat3{ b.x, b.y, b.z, b.w };
-    pixels[i] = __float_as_uint(a.w);
+    uint32_t pxy = __float_as_uint(a.w);
+    pixels[i] = (pxy >> 16) * width + (pxy & 0xFFFFu);
 }
 
 } // namespace
@@ -618,7 +714,7 @@ struct rt_ctx
     std::string error;
 
     // options
-    int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 1;
+    int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 1, fusion = 0;
 
     // per-pixel buffers
     Queues q = {};
@@ -717,6 +813,7 @@ int alloc_frame_buffers(rt_ctx* c)
     auto freep = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     for (int i = 0; i < 2; ++i) { freep(c->q.A[i]); freep(c->q.B[i]); freep(c->q.C[i]); }
     freep(c->q.sA); freep(c->q.sB); freep(c->q.sC); freep(c->q.hits); freep(c->q.shadow_flags);
+    freep(c->q.hitq); freep(c->q.missq);
     freep(c->radiance); freep(c->resolved);
     c->local_rows = (c->height > c->rank) ? (c->height - c->rank + c->world - 1) / c->world : 0;
     c->n_local = c->local_rows * c->width;
@@ -727,6 +824,7 @@ int alloc_frame_buffers(rt_ctx* c)
     }
     RT_CUDA(c, cudaMalloc(&c->q.sA, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.sB, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.sC, n * 16));
     RT_CUDA(c, cudaMalloc(&c->q.hits, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.shadow_flags, n * 4));
+    RT_CUDA(c, cudaMalloc(&c->q.hitq, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.missq, n * 4));
     RT_CUDA(c, cudaMalloc(&c->radiance, n * 16)); RT_CUDA(c, cudaMalloc(&c->resolved, n * 16));
     RT_CUDA(c, cudaMemsetAsync(c->radiance, 0, n * 16, c->stream));
     return RT_OK;
@@ -742,7 +840,10 @@ const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->error.c_str() :
 
 int rt_create(uint32_t width, uint32_t height, int device, rt_ctx** out_ctx)
 {
-    if (!out_ctx || width == 0 || height == 0) { g_create_error = "rt_create: bad arguments"; return RT_ERR_INVALID_ARGUMENT; }
+    if (!out_ctx || width == 0 || height == 0 || width > 65535u || height > 65535u)
+    {
+        g_create_error = "rt_create: bad arguments (need 1 <= width, height <= 65535)"; return RT_ERR_INVALID_ARGUMENT;
+    }
     *out_ctx = nullptr;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -775,6 +876,7 @@ int rt_destroy(rt_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 2; ++i) { cudaFree(c->q.A[i]); cudaFree(c->q.B[i]); cudaFree(c->q.C[i]); }
     cudaFree(c->q.sA); cudaFree(c->q.sB); cudaFree(c->q.sC); cudaFree(c->q.hits); cudaFree(c->q.shadow_flags);
+    cudaFree(c->q.hitq); cudaFree(c->q.missq);
     cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->counters); cudaFree(c->scratch);
     for (void* p : c->scene_allocs) cudaFree(p);
     for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -809,6 +911,21 @@ int rt_upload_scene(rt_ctx* c, const RtSceneDesc* s)
     for (uint64_t i = 0; i < s->n_triangles; ++i)
         if (s->triangles[i].mtlIndex >= s->n_materials) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: triangle %llu has material index out of range", (unsigned long long)i);
 
+    for (uint64_t i = 0; i < s->n_materials; ++i)
+    {   // texture indices of the packed materials must exist (0xFF = none)
+        const RtPackedMaterial& m = s->materials[i];
+        uint32_t idx[6] = { m.diffuse_albedo >> 24, m.specular_albedo >> 24, (m.roughness_metalness >> 8) & 0xFF, m.roughness_metalness >> 24,
+                            (m.ior_emission_idx_transparency >> 8) & 0xFF, m.ior_emission_idx_transparency >> 24 };
+        for (uint32_t t : idx)
+            if (t != RT_INVALID_TEXTURE_IDX && t >= s->n_textures) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: material %llu references texture %u of %llu", (unsigned long long)i, t, (unsigned long long)s->n_textures);
+    }
+    for (uint64_t i = 0; i < s->n_textures; ++i)
+    {
+        const RtTexture& t = s->textures[i];
+        if (t.width <= 0 || t.height <= 0 || t.data_start < 0 || (uint64_t)t.data_start + (uint64_t)t.width * t.height > s->n_texture_data)
+            RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: texture %llu lies outside the texel array", (unsigned long long)i);
+    }
+
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     for (void* p : c->scene_allocs) cudaFree(p);
@@ -827,7 +944,15 @@ int rt_upload_scene(rt_ctx* c, const RtSceneDesc* s)
     int rc;
     DevScene& ds = c->scene;
     if ((rc = upload(s->nodes, s->n_nodes * sizeof(RtLinearBVHNode), (const void**)&ds.nodes_ref))) return rc;
-    if ((rc = upload(s->triangles, s->n_triangles * sizeof(RtTriangle), (const void**)&ds.triangles))) return rc;
+    {
+        std::vector<rtbvh::F4> rec;
+        rtbvh::build_tri_shade(s->triangles, s->n_triangles, rec);
+        if ((rc = upload(rec.data(), rec.size() * 16, (const void**)&ds.tri_shade))) return rc;
+        rtbvh::build_mat_rec(s->materials, s->n_materials, rec);
+        if ((rc = upload(rec.data(), rec.size() * 16, (const void**)&ds.mat_rec))) return rc;
+        rtbvh::build_light_rec(s->lights, s->n_lights, rec);
+        if ((rc = upload(rec.data(), rec.size() * 16, (const void**)&ds.light_rec))) return rc;
+    }
     {   // RTTriangle[] derived at upload, cl_pt_integrator.cpp:392-402
         std::vector<RtRTTriangle> rt(s->n_triangles);
         for (uint64_t i = 0; i < s->n_triangles; ++i)
@@ -837,7 +962,6 @@ int rt_upload_scene(rt_ctx* c, const RtSceneDesc* s)
         if ((rc = upload(rt.data(), rt.size() * sizeof(RtRTTriangle), (const void**)&ds.tris_ref))) return rc;
     }
     if ((rc = upload(s->materials, s->n_materials * sizeof(RtPackedMaterial), (const void**)&ds.materials))) return rc;
-    if ((rc = upload(s->lights, s->n_lights * sizeof(RtLight), (const void**)&ds.lights))) return rc;
     if ((rc = upload(s->textures, s->n_textures * sizeof(RtTexture), (const void**)&ds.textures))) return rc;
     if ((rc = upload(s->texture_data, s->n_texture_data * 4, (const void**)&ds.texels))) return rc;
     if ((rc = upload(s->env_image, (size_t)s->env_width * s->env_height * 16, (const void**)&ds.env))) return rc;
@@ -894,6 +1018,9 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
         c->denoiser = 0; return RT_OK;
     case RT_OPT_COUNT_TRAVERSAL: c->count_traversal = value != 0; return RT_OK;
     case RT_OPT_KERNEL_TIMING: c->kernel_timing = value != 0; return RT_OK;
+    case RT_OPT_FUSION:
+        if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "fusion mode must be 0 or 1");
+        c->fusion = (int)value; return RT_OK;
     case RT_OPT_TRAVERSAL:
         if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "traversal mode must be 0 or 1");
         c->traversal = (int)value; return RT_OK;
@@ -988,11 +1115,23 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
 {
     RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
     c->cur_bounce = bounce;
-    TimedLaunch t(c, RT_K_EXTEND_SHADE);
     int grid = persistent_grid(c);
-    if (c->count_traversal) k_extend_shade<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-    else k_extend_shade<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-    return post_launch(c, "k_extend_shade");
+    if (c->fusion == 1)
+    {   // monolithic variant: trace + miss + shade in one kernel
+        TimedLaunch t(c, RT_K_EXTEND_SHADE);
+        if (c->count_traversal) k_extend_shade<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+        else k_extend_shade<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+        return post_launch(c, "k_extend_shade");
+    }
+    {
+        TimedLaunch t(c, RT_K_TRACE_CLOSEST);
+        if (c->count_traversal) k_trace_closest<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
+        else k_trace_closest<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
+        int rc = post_launch(c, "k_trace_closest"); if (rc) return rc;
+    }
+    TimedLaunch t(c, RT_K_SHADE_QUEUES);
+    k_shade_queues<<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce);
+    return post_launch(c, "k_shade_queues");
 }
 
 int rt_shadow_accumulate(rt_ctx* c, uint32_t bounce)
@@ -1065,7 +1204,7 @@ int rt_read_hits(rt_ctx* c, uint32_t bounce, RtHit* hits, uint32_t* pixels, uint
     {
         std::vector<float4> a(n);
         RT_CUDA(c, cudaMemcpy(a.data(), c->q.A[bounce & 1], (size_t)n * 16, cudaMemcpyDeviceToHost));
-        for (uint32_t i = 0; i < n; ++i) memcpy(&pixels[i], &a[i].w, 4);
+        for (uint32_t i = 0; i < n; ++i) { uint32_t pxy; memcpy(&pxy, &a[i].w, 4); pixels[i] = (pxy >> 16) * c->width + (pxy & 0xFFFFu); }
     }
     return RT_OK;
 }
@@ -1078,7 +1217,7 @@ int rt_read_rays(rt_ctx* c, uint32_t bounce, RtRay* rays, uint32_t* pixels, uint
     int rc = ensure_scratch(c, (size_t)c->n_local * (sizeof(RtRay) + 4) + 64); if (rc) return rc;
     RtRay* drays = (RtRay*)c->scratch;
     uint32_t* dpix = (uint32_t*)((char*)c->scratch + (size_t)c->n_local * sizeof(RtRay));
-    k_unpack_rays<<<grid_for(c->n_local), 256, 0, c->stream>>>(c->q.A[bounce & 1], c->q.B[bounce & 1], &c->counters->q_count[bounce], drays, dpix);
+    k_unpack_rays<<<grid_for(c->n_local), 256, 0, c->stream>>>(c->q.A[bounce & 1], c->q.B[bounce & 1], &c->counters->q_count[bounce], c->width, drays, dpix);
     ++c->launches;
     if ((rc = post_launch(c, "k_unpack_rays"))) return rc;
     RT_CUDA(c, cudaStreamSynchronize(c->stream));

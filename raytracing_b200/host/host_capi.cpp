@@ -130,6 +130,12 @@ int rth_render_frame(void* h)
     try { ((RenderHandle*)h)->render->RenderFrame(); return 0; } catch (std::exception& e) { g_error = e.what(); return -1; }
 }
 int rth_render_request_reset(void* h) { ((RenderHandle*)h)->render->NotifyCameraChanged(); return 0; }
+// nodes of the BVH that Render built (Render owns its acceleration structure, render.hpp:87)
+int rth_render_nodes(void* h, const void** ptr, size_t* count)
+{
+    auto const& n = ((RenderHandle*)h)->render->GetAccelerationStructure().GetNodes();
+    *ptr = n.data(); *count = n.size(); return 0;
+}
 const float* rth_render_image(void* h) { return ((RenderHandle*)h)->render->GetImage().data(); }
 void* rth_render_context(void* h) { return static_cast<CUDAPathTraceIntegrator&>(((RenderHandle*)h)->render->GetIntegrator()).Context(); }
 

@@ -42,6 +42,7 @@ def load_library():
     L.rth_render_set_sampler.argtypes = [C.c_void_p, C.c_int]
     L.rth_render_frame.argtypes = [C.c_void_p]
     L.rth_render_request_reset.argtypes = [C.c_void_p]
+    L.rth_render_nodes.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.rth_render_image.restype = C.POINTER(C.c_float)
     L.rth_render_image.argtypes = [C.c_void_p]
     L.rth_render_context.restype = C.c_void_p
@@ -149,6 +150,12 @@ class HostRender:
     def image(self):
         p = self.L.rth_render_image(self.h)
         return np.ctypeslib.as_array(p, shape=(self.height, self.width, 4)).copy()
+
+    def nodes(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self.L.rth_render_nodes(self.h, C.byref(p), C.byref(n))
+        buf = (C.c_char * (n.value * NODE_DT.itemsize)).from_address(p.value)
+        return np.frombuffer(bytes(buf), dtype=NODE_DT).copy()
 
     def context_handle(self): return self.L.rth_render_context(self.h)
 

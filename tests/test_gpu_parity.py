@@ -91,14 +91,16 @@ def test_fused_and_stepwise_match_oracle(name, w, h, mb, traversal):
     o = Oracle(sc)
     oacc = np.zeros((h, w, 4), dtype="<f4")
     ctxs = {}
-    for mode in ("fused", "stepwise"):
+    for mode in ("fused", "monolithic", "stepwise"):
         c = make_ctx(name, w, h)
         c.set_option(capi.OPT_TRAVERSAL, traversal)
+        c.set_option(capi.OPT_FUSION, 1 if mode == "monolithic" else 0)
         c.reset()
         ctxs[mode] = c
     for sample in range(2):
         oacc, ohits, ost = o.render(cam, w, h, mb, sample_idx=sample, radiance=oacc)
         ctxs["fused"].integrate(mb)
+        ctxs["monolithic"].integrate(mb)
         ctxs["stepwise"].integrate_stepwise(mb)
         for mode, c in ctxs.items():
             check_stats(c.frame_stats(), ost, mb)

@@ -156,7 +156,8 @@ def test_render_kcuda_backend_matches_oracle(tmp_path, stepwise):
     s.add_point_light((0.5, 0.2, 2.0), (4, 4, 6))
     r = hostapi.HostRender(s, w, h, env_path, stepwise=stepwise)
     r.set_max_bounces(mb)
-    a = s.arrays()                       # after Render built the BVH and finalized the scene
+    a = s.arrays()                       # after Render built the BVH (reordering the triangles) and finalized the scene
+    a["nodes"] = r.nodes()               # Render owns the acceleration structure
     o = Oracle(a)
     cam = hostapi.default_camera(w, h)
     acc = np.zeros((h, w, 4), dtype="<f4")
