@@ -35,7 +35,20 @@ WORKLOADS = {
     "CornellBox": ("CornellBox", 1920, 1080, 8),          # BASELINE configs[1] — the headline
     "ShaderBalls": ("ShaderBalls", 1920, 1080, 8),        # configs[2]
     "CornellBox_Dragon": ("CornellBox_Dragon", 3840, 2160, 16),   # configs[3]
+    "Synthetic10M": ("Synthetic10M", 1920, 1080, 8),      # configs[4]: 183 x ShaderBalls = 10 026 570 triangles
 }
+
+
+def load_workload_scene(name, w, h, copies=183):
+    """Scene arrays + camera of a workload.  Synthetic10M is generated (raytracing_b200/synthetic.py) and its BVH
+    is built on the host by every rank (deterministic, so all ranks hold identical bytes)."""
+    from raytracing_b200 import scene_io
+    from raytracing_b200.camera import default_camera
+    if name == "Synthetic10M":
+        from raytracing_b200 import synthetic
+        sc = synthetic.bistro_scale_scene(scene_io.load_scene("ShaderBalls"), copies, w, h)
+        return sc, sc["camera_pose"]
+    return scene_io.load_scene(name), default_camera(w, h)
 
 
 def algorithmic_bytes(st, mb, n_pix):
@@ -139,11 +152,8 @@ def run_reference_arm(args, workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from raytracing_b200 import scene_io
-    from raytracing_b200.camera import default_camera
     name, w, h, mb = workload
-    scene = scene_io.load_scene(name)
-    cam = default_camera(w, h)
+    scene, cam = load_workload_scene(name, w, h, args.copies)
     cores = os.cpu_count() or 1
     total_budget = 150.0
     per_step = max(2.0, total_budget / (args.steps + args.warmup))
@@ -177,6 +187,7 @@ def main():
     ap.add_argument("--stepwise", action="store_true", help="time the one-kernel-per-reference-step schedule instead of the fused one")
     ap.add_argument("--monolithic", action="store_true", help="fused schedule with ONE extend+shade kernel instead of trace -> queues -> shade")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--copies", type=int, default=183, help="Synthetic10M: number of ShaderBalls copies (183 = 10 026 570 triangles)")
     args = ap.parse_args()
     workload = WORKLOADS[args.scene]
     if args.impl == "reference":
@@ -186,8 +197,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from raytracing_b200 import capi, scene_io
-    from raytracing_b200.camera import default_camera
+    from raytracing_b200 import capi
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,8 +212,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     name, w, h, mb = workload
-    scene = scene_io.load_scene(name)
-    cam = default_camera(w, h)
+    scene, cam = load_workload_scene(name, w, h, args.copies)
     ctx = capi.Context(w, h, device=local_rank, rank=rank, world=world)
     ctx.upload_scene(scene)
     ctx.set_camera(cam)
@@ -308,7 +317,7 @@ def main():
             "metric": "Mrays/sec @1920x1080x8-bounce", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{name} {w}x{h} 1spp {mb}-bounce, default camera, sample_idx 0, Reset+Integrate per step",
+            "config": {"workload": f"{name} {w}x{h} 1spp {mb}-bounce, {len(scene['triangles'])} triangles, sample_idx 0, Reset+Integrate per step",
                        "schedule": "stepwise" if args.stepwise else ("fused-monolithic" if args.monolithic else "fused: trace -> hit/miss queues -> shade, shadow+accumulate"), "partition": f"scanline y%{world}",
                        "rays_per_step": rays_per_frame,
                        "l2": "per-step working set (ray/shadow queues + radiance, ~365 MB at 1080p) exceeds the 126 MB L2; no explicit flush"},

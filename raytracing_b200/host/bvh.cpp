@@ -1,8 +1,12 @@
 #include "bvh.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cassert>
 #include <cfloat>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -37,18 +41,19 @@ struct Builder
 {
     const std::vector<Triangle>& tris;
     std::vector<Prim> prims;
-    std::vector<Rec> recs;
-    std::vector<Triangle> ordered;
+    std::vector<Rec> recs;            // pre-sized arena; records are claimed with an atomic cursor
+    std::vector<Triangle> ordered;    // pre-sized; every leaf knows its offset before it is built
+    std::atomic<int> next_rec{ 0 };
 
     explicit Builder(const std::vector<Triangle>& t) : tris(t) {}
 
-    int leaf(int rec, unsigned start, unsigned end, const Box& box)
+    int leaf(int rec, unsigned start, unsigned end, const Box& box, unsigned first)
     {
-        recs[rec].first = (int)ordered.size();
+        recs[rec].first = (int)first;
         recs[rec].count = (int)(end - start);
         recs[rec].box = box;
         recs[rec].child[0] = recs[rec].child[1] = -1;
-        for (unsigned i = start; i < end; ++i) ordered.push_back(tris[prims[i].index]);
+        for (unsigned i = start; i < end; ++i) ordered[first + (i - start)] = tris[prims[i].index];
         return rec;
     }
 
@@ -62,19 +67,22 @@ struct Builder
         return b == 12 ? 11 : b;
     }
 
-    int build(unsigned start, unsigned end)
+    // `first`: where this subtree's triangles start in the leaf-ordered output.  The reference appends leaves in
+    // construction order and constructs the SECOND child first (see below), so the second child's triangles
+    // occupy [first, first + (end-mid)) and the first child's follow — known before either child is built,
+    // which is what lets the two children be built as independent OpenMP tasks with an identical result.
+    int build(unsigned start, unsigned end, unsigned first)
     {
-        int rec = (int)recs.size();
-        recs.push_back(Rec());
+        int rec = next_rec.fetch_add(1);
         Box box;
         for (unsigned i = start; i < end; ++i) box.grow(prims[i].box);
         unsigned n = end - start;
-        if (n == 1) return leaf(rec, start, end, box);
+        if (n == 1) return leaf(rec, start, end, box, first);
 
         Box cb;
         for (unsigned i = start; i < end; ++i) cb.grow(prims[i].centroid);
         unsigned dim = cb.widest();
-        if (component(cb.hi, dim) == component(cb.lo, dim)) return leaf(rec, start, end, box);   // all centroids coincide
+        if (component(cb.hi, dim) == component(cb.lo, dim)) return leaf(rec, start, end, box, first);   // all centroids coincide
 
         unsigned mid = (start + end) / 2;
         if (n <= 2)
@@ -93,15 +101,20 @@ struct Builder
                 ++count[b];
                 bbox[b].grow(prims[i].box);
             }
+            // cost[i] = 1 + (n0 * area(U b[0..i]) + n1 * area(U b[i+1..11])) / area(node)   (bvh.cpp:149-166).
+            // The reference recomputes both unions from scratch for every i (O(buckets^2) per node, which
+            // dominates the build of the many small nodes); min/max are exact and associative, so prefix and
+            // suffix unions give the same boxes in O(buckets).
+            Box left[kBuckets], right[kBuckets];
+            int nleft[kBuckets], nright[kBuckets];
+            left[0] = bbox[0]; nleft[0] = count[0];
+            for (int j = 1; j < kBuckets; ++j) { left[j] = left[j - 1]; left[j].grow(bbox[j]); nleft[j] = nleft[j - 1] + count[j]; }
+            right[kBuckets - 1] = bbox[kBuckets - 1]; nright[kBuckets - 1] = count[kBuckets - 1];
+            for (int j = kBuckets - 2; j >= 0; --j) { right[j] = right[j + 1]; right[j].grow(bbox[j]); nright[j] = nright[j + 1] + count[j]; }
             float cost[kBuckets - 1];
+            const float node_area = box.area();
             for (int i = 0; i < kBuckets - 1; ++i)
-            {
-                Box b0, b1;
-                int c0 = 0, c1 = 0;
-                for (int j = 0; j <= i; ++j) { b0.grow(bbox[j]); c0 += count[j]; }
-                for (int j = i + 1; j < kBuckets; ++j) { b1.grow(bbox[j]); c1 += count[j]; }
-                cost[i] = 1.0f + (c0 * b0.area() + c1 * b1.area()) / box.area();
-            }
+                cost[i] = 1.0f + (nleft[i] * left[i].area() + nright[i + 1] * right[i + 1].area()) / node_area;
             float min_cost = cost[0];
             int split = 0;
             for (int i = 1; i < kBuckets - 1; ++i)
@@ -112,12 +125,25 @@ struct Builder
                                           [&](const Prim& p) { return bucket_of(cb, p.centroid, dim) <= split; });
                 mid = (unsigned)(pm - &prims[0]);
             }
-            else return leaf(rec, start, end, box);
+            else return leaf(rec, start, end, box, first);
         }
         // The reference builds both children as arguments of one call (bvh.cpp:212-216); with g++ (and MSVC)
         // the SECOND argument is evaluated first, which decides the leaf order of the triangle array.
-        int c1 = build(mid, end);
-        int c0 = build(start, mid);
+        int c0 = -1, c1 = -1;
+        const unsigned kTaskThreshold = 8192;
+        if (n > kTaskThreshold)
+        {
+#pragma omp task shared(c1) firstprivate(mid, end, first)
+            c1 = build(mid, end, first);
+#pragma omp task shared(c0) firstprivate(start, mid, end, first)
+            c0 = build(start, mid, first + (end - mid));
+#pragma omp taskwait
+        }
+        else
+        {
+            c1 = build(mid, end, first);
+            c0 = build(start, mid, first + (end - mid));
+        }
         recs[rec].child[0] = c0; recs[rec].child[1] = c1;
         recs[rec].axis = (int)dim; recs[rec].count = 0;
         Box u = recs[c0].box; u.grow(recs[c1].box);
@@ -131,6 +157,14 @@ struct Builder
 void Bvh::BuildCPU(std::vector<Triangle>& triangles)
 {
     if (triangles.empty()) throw std::runtime_error("Bvh::BuildCPU: no triangles");
+    const bool verbose = getenv("RT_BVH_VERBOSE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!verbose) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bvh] %-10s %.2f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    };
     Builder b(triangles);
     b.prims.resize(triangles.size());
     for (unsigned i = 0; i < triangles.size(); ++i)
@@ -141,10 +175,15 @@ void Bvh::BuildCPU(std::vector<Triangle>& triangles)
         b.prims[i].index = i; b.prims[i].box = bx;
         b.prims[i].centroid = bx.lo * 0.5f + bx.hi * 0.5f;
     }
-    b.recs.reserve(2 * triangles.size());
-    b.ordered.reserve(triangles.size());
-    // explicit stack instead of recursion depth problems: build() recurses at most tree depth (<= ~64 for sane input)
-    int root = b.build(0, (unsigned)triangles.size());
+    lap("prims");
+    b.recs.resize(2 * triangles.size());          // a binary tree over n >= 1 primitives has at most 2n-1 nodes
+    b.ordered.resize(triangles.size(), triangles[0]);
+    int root = 0;
+#pragma omp parallel
+#pragma omp single
+    root = b.build(0, (unsigned)triangles.size(), 0);
+    lap("build");
+    b.recs.resize((size_t)b.next_rec.load());
     triangles.swap(b.ordered);
 
     // depth-first flattening (bvh.cpp:223-245): first child follows its parent, `offset` = second child
@@ -179,6 +218,7 @@ void Bvh::BuildCPU(std::vector<Triangle>& triangles)
         }
     }
     assert(next == nodes_.size());
+    lap("flatten");
 }
 
 } // namespace rt_host

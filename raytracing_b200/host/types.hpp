@@ -33,8 +33,11 @@ inline float3 operator+(const float3& a, const float3& b) { return make_float3(a
 inline float3 operator-(const float3& a, const float3& b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
 inline float3 operator*(const float3& a, float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
 inline float component(const float3& v, unsigned i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
-inline float3 vmin(const float3& a, const float3& b) { return make_float3(std::fmin(a.x, b.x), std::fmin(a.y, b.y), std::fmin(a.z, b.z)); }
-inline float3 vmax(const float3& a, const float3& b) { return make_float3(std::fmax(a.x, b.x), std::fmax(a.y, b.y), std::fmax(a.z, b.z)); }
+// std::min / std::max semantics, as the reference's Min/Max (mathlib.hpp:125-133); these inline to minss/maxss
+inline float fmin2(float a, float b) { return (b < a) ? b : a; }
+inline float fmax2(float a, float b) { return (a < b) ? b : a; }
+inline float3 vmin(const float3& a, const float3& b) { return make_float3(fmin2(a.x, b.x), fmin2(a.y, b.y), fmin2(a.z, b.z)); }
+inline float3 vmax(const float3& a, const float3& b) { return make_float3(fmax2(a.x, b.x), fmax2(a.y, b.y), fmax2(a.z, b.z)); }
 inline float3 cross(const float3& a, const float3& b) { return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 
 } // namespace rt_host

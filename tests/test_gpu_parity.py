@@ -179,6 +179,26 @@ def test_full_size_properties_1080p():
     a.destroy(); b.destroy()
 
 
+def test_synthetic_field_matches_oracle():
+    """BASELINE config C5 at reduced scale: 4 copies of ShaderBalls (219 160 triangles, BVH built by the host builder),
+    raised camera; CUDA == oracle bit for bit."""
+    from raytracing_b200 import scene_io, synthetic
+    w, h, mb = 320, 180, 8
+    sc = synthetic.bistro_scale_scene(scene_io.load_scene("ShaderBalls"), 4, w, h)
+    cam = sc["camera_pose"]
+    orad, ohits, ost = Oracle(sc).render(cam, w, h, mb)
+    c = capi.Context(w, h)
+    c.upload_scene(sc); c.set_camera(cam); c.reset()
+    c.generate_rays(); c.intersect(0)
+    hits, pix = c.read_hits(0)
+    prim = np.zeros(w * h, dtype=np.uint32); prim[pix] = hits["primitive_id"]
+    assert np.array_equal(prim, ohits["primitive_id"])
+    c.reset(); c.integrate(mb)
+    check_stats(c.frame_stats(), ost, mb)
+    assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(orad[..., :3]))
+    c.destroy()
+
+
 def test_error_behaviour():
     c = capi.Context(32, 32)
     with pytest.raises(capi.RtError):
