@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--stepwise", action="store_true", help="time the one-kernel-per-reference-step schedule instead of the fused one")
     ap.add_argument("--monolithic", action="store_true", help="fused schedule with ONE extend+shade kernel instead of trace -> queues -> shade")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traversal", type=int, default=None, help="RT_OPT_TRAVERSAL override (0 literal, 1 fast, 2 per-lane refill)")
+    ap.add_argument("--refill-min", type=int, default=None, help="RT_OPT_REFILL_MIN override")
     ap.add_argument("--copies", type=int, default=183, help="Synthetic10M: number of ShaderBalls copies (183 = 10 026 570 triangles)")
     args = ap.parse_args()
     workload = WORKLOADS[args.scene]
@@ -218,6 +220,10 @@ def main():
     ctx.set_camera(cam)
     if args.monolithic:
         ctx.set_option(capi.OPT_FUSION, 1)
+    if args.traversal is not None:
+        ctx.set_option(capi.OPT_TRAVERSAL, args.traversal)
+    if args.refill_min is not None:
+        ctx.set_option(capi.OPT_REFILL_MIN, args.refill_min)
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
 
     # the local radiance slab as a torch tensor (zero copy) for the NCCL gather

@@ -67,7 +67,9 @@ typedef enum RtOption {
                                    the algorithmic-bytes figure of the roofline)     */
     RT_OPT_KERNEL_TIMING = 17,  /* 1: bracket every launch with CUDA events on the context's stream */
     RT_OPT_TRAVERSAL = 18,      /* 0: literal reference-order traversal on the reference node layout,
-                                   1: optimised traversal (default); results are bit-identical */
+                                   1: child-box node layout, one ray per lane per grab,
+                                   2: same traversal with per-lane ray refill (default); results are bit-identical */
+    RT_OPT_REFILL_MIN = 20,     /* traversal mode 2: refill a warp when at least this many lanes are idle (1..32) */
     RT_OPT_FUSION = 19          /* rt_extend_shade: 0 = traversal kernel + hit/miss queue compaction + shading kernel
                                    (default), 1 = one monolithic kernel; results are bit-identical */
 } RtOption;

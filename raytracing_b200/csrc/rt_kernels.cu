@@ -47,10 +47,10 @@ struct DevCounters
 {
     uint32_t q_count[RT_MAX_BOUNCES + 2];        // rays entering bounce b
     uint32_t shadow_count[RT_MAX_BOUNCES + 1];
-    uint32_t n_miss[RT_MAX_BOUNCES + 1];
+    struct HitMiss { uint32_t hit, miss; };      // adjacent so that one 64-bit atomic can advance both
+    HitMiss hm[RT_MAX_BOUNCES + 1];              // hit-queue entries / misses of bounce b
     uint32_t n_emissive[RT_MAX_BOUNCES + 1];
     uint32_t n_unoccluded[RT_MAX_BOUNCES + 1];
-    uint32_t hit_count[RT_MAX_BOUNCES + 1];      // entries of the hit queue (queue-split schedule)
     uint32_t work_ext[RT_MAX_BOUNCES + 1];       // persistent-kernel work cursors
     uint32_t work_shade[RT_MAX_BOUNCES + 1];
     uint32_t work_shadow[RT_MAX_BOUNCES + 1];
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(256) k_shade_miss(FrameParams p, DevScene sc, 
             shade_miss(sc, p, radiance, __float_as_uint(a.w), mk3(b), mk3(c));
         }
     }
-    warp_count(&ctr->n_miss[bounce], miss);
+    warp_count(&ctr->hm[bounce].miss, miss);
 }
 
 __device__ __forceinline__ void emit_rays(const FrameParams& p, Queues& q, DevCounters* ctr, float4* radiance, uint32_t bounce,
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(256) k_extend_shade(FrameParams p, DevScene sc
             if (miss) shade_miss(sc, p, radiance, pixel, mk3(b), mk3(c));
             else shade_hit(sc, p, bounce, pixel, mk3(b), mk3(c), prim, bu, bv, so);
         }
-        warp_count(&ctr->n_miss[bounce], miss);
+        warp_count(&ctr->hm[bounce].miss, miss);
         emit_rays(p, q, ctr, radiance, bounce, pixel, hit, so);
     }
     if (COUNT) { warp_sum64(&ctr->nodes_ext[bounce], nv); warp_sum64(&ctr->tris_ext[bounce], nt); }
@@ -626,19 +626,225 @@ __global__ void __launch_bounds__(256) k_trace_closest(FrameParams p, DevScene s
             prim = trace<false, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
             hit = prim != RT_INVALID_ID;
         }
-        uint32_t hi = warp_append(&ctr->hit_count[bounce], hit);
+        uint32_t hi = warp_append(&ctr->hm[bounce].hit, hit);
         if (hit) q.hitq[hi] = make_float4(bu, bv, __uint_as_float(prim), __uint_as_float(i));
         bool miss = live && !hit;
-        uint32_t mi = warp_append(&ctr->n_miss[bounce], miss);
+        uint32_t mi = warp_append(&ctr->hm[bounce].miss, miss);
         if (miss) q.missq[mi] = i;
     }
     if (COUNT) { warp_sum64(&ctr->nodes_ext[bounce], nv); warp_sum64(&ctr->tris_ext[bounce], nt); }
 }
 
+
+// ---- traversal with per-lane ray refill ------------------------------------------------------------------
+// After the first diffuse bounce the rays of a warp are incoherent: their traversals have very different lengths and
+// a warp that waits for its slowest ray runs at ~13 of 32 lanes (ncu, profiles/r01b_trace_summary.txt).  Here a warp is
+// a pool of 32 traversal slots: a lane whose ray terminates parks its result, and as soon as `refill_min` lanes are
+// idle the warp (1) compacts the parked results into the hit / miss queues with ONE 64-bit atomic (hits in the low
+// word, misses in the high word; __ballot + __popc give every lane its slot), and (2) hands the idle lanes new rays
+// from a warp-level reservation of the global queue (one atomic per 128 rays).  The traversal itself is the same
+// while-while loop in the same order with the same arithmetic as trace_fast, so results are bit-identical.
+// ANY = shadow rays: first hit terminates; an unoccluded ray adds its light sample to the radiance (fused
+// AccumulateDirectSamples) instead of producing queue entries.
+template <bool ANY>
+__global__ void __launch_bounds__(256) k_trace_refill(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance,
+                                                      uint32_t bounce, int refill_min)
+{
+    const uint32_t n = ANY ? ctr->shadow_count[bounce] : ctr->q_count[bounce];
+    uint32_t* cursor = ANY ? &ctr->work_shadow[bounce] : &ctr->work_ext[bounce];
+    const float4* __restrict__ A = ANY ? q.sA : q.A[bounce & 1];
+    const float4* __restrict__ B = ANY ? q.sB : q.B[bounce & 1];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t kReserve = 128;
+
+    uint32_t res_next = 0, res_end = 0;          // warp-uniform reservation [res_next, res_end) of queue slots
+    bool exhausted = false;                      // warp-uniform: the global queue has no more rays
+    bool has = false, parked = false, finish_now = false;
+    uint32_t ray_i = 0, prim = RT_INVALID_ID;
+    float bu = 0.0f, bv = 0.0f, t_max = 0.0f;
+    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), inv = mk3(0, 0, 0);
+    bool sx = false, sy = false, sz = false;
+    int cur = 0, sp = 0;
+    int stack_ref[64];
+    float stack_t[64];
+
+    for (;;)
+    {
+        const unsigned idle = __ballot_sync(0xffffffffu, !has);
+        if (idle != 0u && (__popc(idle) >= refill_min || idle == 0xffffffffu))
+        {
+            // (1) emit parked results
+            if (!ANY)
+            {
+                const unsigned hmask = __ballot_sync(0xffffffffu, parked && prim != RT_INVALID_ID);
+                const unsigned mmask = __ballot_sync(0xffffffffu, parked && prim == RT_INVALID_ID);
+                if ((hmask | mmask) != 0u)
+                {
+                    unsigned long long base = 0ull;
+                    if (lane == 0)
+                        base = atomicAdd((unsigned long long*)&ctr->hm[bounce], (unsigned long long)__popc(hmask) | ((unsigned long long)__popc(mmask) << 32));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (parked)
+                    {
+                        if (prim != RT_INVALID_ID)
+                            q.hitq[(uint32_t)base + __popc(hmask & lt_mask)] = make_float4(bu, bv, __uint_as_float(prim), __uint_as_float(ray_i));
+                        else
+                            q.missq[(uint32_t)(base >> 32) + __popc(mmask & lt_mask)] = ray_i;
+                    }
+                }
+            }
+            else
+            {
+                const bool un = parked && prim == RT_INVALID_ID;
+                if (un)
+                {   // accumulate_direct_samples.cl:27-53
+                    float4 a = A[ray_i], c = q.sC[ray_i];
+                    uint32_t li = local_index(p, __float_as_uint(a.w));
+                    float4 r = radiance[li];
+                    r.x += c.x; r.y += c.y; r.z += c.z;
+                    radiance[li] = r;
+                }
+                warp_count(&ctr->n_unoccluded[bounce], un);
+            }
+            parked = false;
+
+            // (2) refill idle lanes from the warp's reservation
+            unsigned need = idle;
+            while (need != 0u)
+            {
+                if (res_next == res_end)
+                {
+                    if (exhausted) break;
+                    uint32_t b = 0;
+                    if (lane == 0) b = atomicAdd(cursor, kReserve);
+                    b = __shfl_sync(0xffffffffu, b, 0);
+                    if (b >= n) { exhausted = true; break; }
+                    res_next = b; res_end = (b + kReserve < n) ? b + kReserve : n;
+                }
+                const uint32_t avail = res_end - res_next;
+                const uint32_t rank = (uint32_t)__popc(need & lt_mask);
+                const bool take = ((need >> lane) & 1u) && rank < avail;
+                if (take)
+                {
+                    ray_i = res_next + rank;
+                    float4 a = A[ray_i], b = B[ray_i];
+                    o = mk3(a); d = mk3(b); t_max = b.w;
+                    prim = RT_INVALID_ID; bu = 0.0f; bv = 0.0f;
+                    has = true; finish_now = false;
+                    float fin = ((o.x + o.y) + o.z) + ((d.x + d.y) + d.z);
+                    if (!(fabsf(fin) <= 3.0e38f))
+                    {   // non-finite ray: literal reference-order traversal (see trace_fast), result ready at once
+                        float bt = 0.0f; uint32_t nv = 0, nt = 0;
+                        prim = trace_literal<ANY, false>(sc, o, d, 0.0f, t_max, bu, bv, bt, nv, nt);
+                        finish_now = true;
+                    }
+                    else
+                    {
+                        inv = splat(1.0f) / d;
+                        sx = inv.x < 0; sy = inv.y < 0; sz = inv.z < 0;
+                        sp = 0; cur = sc.root_ref;
+                        // the reference tests every node it visits, including the root (trace_bvh.cl:144-148)
+                        float4 r0 = __ldg(sc.nodes_ref), r1 = __ldg(sc.nodes_ref + 1);
+                        f3 t0 = (mk3(r0) - o) * inv, t1 = (mk3(r1) - o) * inv;
+                        float lo = fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z));
+                        float hi = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
+                        if (!(fminf(hi, t_max) >= fmaxf(lo, 0.0f))) finish_now = true;
+                    }
+                }
+                const uint32_t wanted = (uint32_t)__popc(need);
+                res_next += wanted < avail ? wanted : avail;
+                need = __ballot_sync(0xffffffffu, ((need >> lane) & 1u) && !take);
+            }
+            if (__ballot_sync(0xffffffffu, has) == 0u) break;      // nothing in flight and nothing left to fetch
+        }
+
+        if (has)
+        {
+            bool finished = finish_now;
+            if (!finished)
+            {
+                while (cur >= 0)
+                {
+                    const float4* np = sc.wnodes + (size_t)cur * 4;
+                    float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2), m = __ldg(np + 3);
+                    f3 t00 = (mk3(a.x, a.y, a.z) - o) * inv, t01 = (mk3(a.w, b.x, b.y) - o) * inv;
+                    f3 t10 = (mk3(b.z, b.w, c.x) - o) * inv, t11 = (mk3(c.y, c.z, c.w) - o) * inv;
+                    float lo0 = fmaxf(fmaxf(fmaxf(fminf(t00.x, t01.x), fminf(t00.y, t01.y)), fminf(t00.z, t01.z)), 0.0f);
+                    float hi0 = fminf(fminf(fmaxf(t00.x, t01.x), fmaxf(t00.y, t01.y)), fmaxf(t00.z, t01.z));
+                    float lo1 = fmaxf(fmaxf(fmaxf(fminf(t10.x, t11.x), fminf(t10.y, t11.y)), fminf(t10.z, t11.z)), 0.0f);
+                    float hi1 = fminf(fminf(fmaxf(t10.x, t11.x), fmaxf(t10.y, t11.y)), fmaxf(t10.z, t11.z));
+                    bool h0 = fminf(hi0, t_max) >= lo0, h1 = fminf(hi1, t_max) >= lo1;
+                    int r0 = __float_as_int(m.x), r1 = __float_as_int(m.y);
+                    uint32_t axis = __float_as_uint(m.z);
+                    bool swap = axis == 0 ? sx : (axis == 1 ? sy : sz);
+                    int near_ref = swap ? r1 : r0, far_ref = swap ? r0 : r1;
+                    bool near_hit = swap ? h1 : h0, far_hit = swap ? h0 : h1;
+                    float far_lo = swap ? lo0 : lo1;
+                    if (near_hit)
+                    {
+                        if (far_hit) { stack_ref[sp] = far_ref; stack_t[sp] = far_lo; ++sp; }
+                        cur = near_ref;
+                    }
+                    else if (far_hit) cur = far_ref;
+                    else
+                    {
+                        bool found = false;
+                        while (sp > 0) { --sp; if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; } }
+                        if (!found) { finished = true; break; }
+                    }
+                }
+                if (!finished)
+                {
+                    uint32_t ti = (uint32_t)(~cur);
+                    for (;;)
+                    {
+                        const float4* tp = sc.wtris + (size_t)ti * 3;
+                        float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+                        f3 p1 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
+                        bool last = __float_as_uint(q2.y) != 0u;
+                        f3 pvec = cross(d, e2);
+                        float det = dot(e1, pvec);
+                        if (!(det < 1e-8f || -det > 1e-8f))
+                        {
+                            float inv_det = 1.0f / det;
+                            f3 tvec = o - p1;
+                            float u = dot(tvec, pvec) * inv_det;
+                            if (!(u < 0.0f || u > 1.0f))
+                            {
+                                f3 qvec = cross(tvec, e1);
+                                float v = dot(d, qvec) * inv_det;
+                                if (!(v < 0.0f || u + v > 1.0f))
+                                {
+                                    float t = dot(e2, qvec) * inv_det;
+                                    if (!(t < 0.0f || t > t_max))
+                                    {
+                                        bu = u; bv = v; prim = ANY ? 0u : ti; t_max = t;
+                                        if (ANY) { finished = true; break; }
+                                    }
+                                }
+                            }
+                        }
+                        if (last) break;
+                        ++ti;
+                    }
+                    if (!finished)
+                    {
+                        bool found = false;
+                        while (sp > 0) { --sp; if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; } }
+                        if (!found) finished = true;
+                    }
+                }
+            }
+            if (finished) { has = false; parked = true; }
+        }
+    }
+}
+
 // ShadeSurfaceHits over the hit queue, then ShadeMissedRays over the miss queue (independent pixels).
 __global__ void __launch_bounds__(256) k_shade_queues(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
 {
-    const uint32_t n_hit = ctr->hit_count[bounce], n_miss = ctr->n_miss[bounce];
+    const uint32_t n_hit = ctr->hm[bounce].hit, n_miss = ctr->hm[bounce].miss;
     const uint32_t hit_span = (n_hit + 31u) & ~31u;            // warps never mix hits and misses
     const uint32_t total = hit_span + n_miss;
     const int in = bounce & 1;
@@ -714,7 +920,7 @@ struct rt_ctx
     std::string error;
 
     // options
-    int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 1, fusion = 0;
+    int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 2, fusion = 0, refill_min = 8;
 
     // per-pixel buffers
     Queues q = {};
@@ -1022,8 +1228,11 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
         if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "fusion mode must be 0 or 1");
         c->fusion = (int)value; return RT_OK;
     case RT_OPT_TRAVERSAL:
-        if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "traversal mode must be 0 or 1");
+        if (value > 2) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "traversal mode must be 0, 1 or 2");
         c->traversal = (int)value; return RT_OK;
+    case RT_OPT_REFILL_MIN:
+        if (value < 1 || value > 32) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "refill threshold must be 1..32 lanes");
+        c->refill_min = (int)value; return RT_OK;
     }
     RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "unknown option key %d", key);
 }
@@ -1123,6 +1332,13 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
         else k_extend_shade<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
         return post_launch(c, "k_extend_shade");
     }
+    if (c->traversal == 2 && !c->count_traversal)
+    {
+        TimedLaunch t(c, RT_K_TRACE_CLOSEST);
+        k_trace_refill<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, c->refill_min);
+        int rc = post_launch(c, "k_trace_refill<closest>"); if (rc) return rc;
+    }
+    else
     {
         TimedLaunch t(c, RT_K_TRACE_CLOSEST);
         if (c->count_traversal) k_trace_closest<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
@@ -1139,6 +1355,11 @@ int rt_shadow_accumulate(rt_ctx* c, uint32_t bounce)
     RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
     TimedLaunch t(c, RT_K_SHADOW_ACCUMULATE);
     int grid = persistent_grid(c);
+    if (c->traversal == 2 && !c->count_traversal)
+    {
+        k_trace_refill<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, c->refill_min);
+        return post_launch(c, "k_trace_refill<any>");
+    }
     if (c->count_traversal) k_shadow_accumulate<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
     else k_shadow_accumulate<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
     return post_launch(c, "k_shadow_accumulate");
@@ -1255,7 +1476,7 @@ int rt_read_frame_stats(rt_ctx* c, RtFrameStats* out)
     memset(out, 0, sizeof(*out));
     for (uint32_t b = 0; b <= RT_MAX_BOUNCES; ++b)
     {
-        out->n_ext[b] = h.q_count[b]; out->n_miss[b] = h.n_miss[b]; out->n_emissive_hits[b] = h.n_emissive[b];
+        out->n_ext[b] = h.q_count[b]; out->n_miss[b] = h.hm[b].miss; out->n_emissive_hits[b] = h.n_emissive[b];
         out->n_shadow[b] = h.shadow_count[b]; out->n_cont[b] = h.q_count[b + 1]; out->n_unoccluded[b] = h.n_unoccluded[b];
         out->nodes_ext[b] = h.nodes_ext[b]; out->tris_ext[b] = h.tris_ext[b];
         out->nodes_shadow[b] = h.nodes_shadow[b]; out->tris_shadow[b] = h.tris_shadow[b];

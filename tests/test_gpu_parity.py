@@ -83,7 +83,7 @@ def test_matches_reference_golden(path, fused):
     ("ShaderBalls", 480, 270, 8),
     ("CornellBox_Dragon", 384, 216, 16),
 ])
-@pytest.mark.parametrize("traversal", [0, 1], ids=["literal", "fast"])
+@pytest.mark.parametrize("traversal", [0, 1, 2], ids=["literal", "fast", "refill"])
 def test_fused_and_stepwise_match_oracle(name, w, h, mb, traversal):
     """CUDA (both schedules, both traversal kernels) vs the CPU oracle, live, two accumulated samples."""
     sc = scene(name)
@@ -107,6 +107,21 @@ def test_fused_and_stepwise_match_oracle(name, w, h, mb, traversal):
             assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(oacc[..., :3])), (mode, sample)
     for c in ctxs.values():
         c.destroy()
+
+
+@pytest.mark.parametrize("refill_min", [1, 5, 32])
+def test_refill_threshold_does_not_change_results(refill_min):
+    """Per-lane ray refill (traversal mode 2) with extreme thresholds: compaction order changes, per-pixel results must not."""
+    name, w, h, mb = "ShaderBalls", 257, 131, 6
+    cam = default_camera(w, h)
+    orad, _, ost = Oracle(scene(name)).render(cam, w, h, mb)
+    c = make_ctx(name, w, h)
+    c.set_option(capi.OPT_TRAVERSAL, 2)
+    c.set_option(capi.OPT_REFILL_MIN, refill_min)
+    c.reset(); c.integrate(mb)
+    check_stats(c.frame_stats(), ost, mb)
+    assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(orad[..., :3]))
+    c.destroy()
 
 
 def test_traversal_work_counters_match_oracle():
