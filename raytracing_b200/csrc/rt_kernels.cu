@@ -47,7 +47,7 @@ struct DevCounters
 {
     uint32_t q_count[RT_MAX_BOUNCES + 2];        // rays entering bounce b
     uint32_t shadow_count[RT_MAX_BOUNCES + 1];
-    struct HitMiss { uint32_t hit, miss; };      // adjacent so that one 64-bit atomic can advance both
+    struct alignas(8) HitMiss { uint32_t hit, miss; };   // adjacent + 8-byte aligned: one 64-bit atomic advances both
     HitMiss hm[RT_MAX_BOUNCES + 1];              // hit-queue entries / misses of bounce b
     uint32_t n_emissive[RT_MAX_BOUNCES + 1];
     uint32_t n_unoccluded[RT_MAX_BOUNCES + 1];
