@@ -61,14 +61,17 @@ typedef struct RtSceneDesc {
 typedef enum RtOption {
     RT_OPT_WHITE_FURNACE = 0,   /* EnableWhiteFurnace(bool)                          */
     RT_OPT_SAMPLER = 1,         /* SetSamplerType: 0 = kRandom, 1 = kBlueNoise (unsupported yet) */
-    RT_OPT_AOV = 2,             /* SetAOV: 0 shaded colour .. 4 motion vectors       */
-    RT_OPT_DENOISER = 3,        /* EnableDenoiser(bool)                              */
+    RT_OPT_AOV = 2,             /* SetAOV: 0 shaded colour, 1 albedo, 2 depth, 3 normal, 4 motion vectors (view used by rt_resolve) */
+    RT_OPT_DENOISER = 3,        /* EnableDenoiser(bool): temporal accumulation (single-GPU only) */
     RT_OPT_COUNT_TRAVERSAL = 16,/* 1: kernels also count BVH nodes visited / triangles tested (slower; for
                                    the algorithmic-bytes figure of the roofline)     */
     RT_OPT_KERNEL_TIMING = 17,  /* 1: bracket every launch with CUDA events on the context's stream */
     RT_OPT_TRAVERSAL = 18,      /* 0: literal reference-order traversal on the reference node layout,
-                                   1: child-box node layout, one ray per lane per grab,
-                                   2: same traversal with per-lane ray refill (default); results are bit-identical */
+                                   1: child-box node layout, one ray per lane per grab (default),
+                                   2: same traversal with per-lane ray refill (experiment, measured slower: DESIGN.md);
+                                   results are bit-identical */
+    RT_OPT_AOV_ALWAYS = 21,     /* 1: produce the AOV buffers every frame even with the shaded-colour view (the reference always
+                                   does; here they are skipped unless a view or the denoiser needs them) */
     RT_OPT_REFILL_MIN = 20,     /* traversal mode 2: refill a warp when at least this many lanes are idle (1..32) */
     RT_OPT_FUSION = 19          /* rt_extend_shade: 0 = traversal kernel + hit/miss queue compaction + shading kernel
                                    (default), 1 = one monolithic kernel; results are bit-identical */
@@ -123,7 +126,7 @@ int rt_reset(rt_ctx* ctx);                                      /* Reset: sample
 int rt_advance_sample_count(rt_ctx* ctx);                       /* AdvanceSampleCount */
 int rt_generate_rays(rt_ctx* ctx);                              /* GenerateRays   -> raygeneration.cl:65-139 */
 int rt_intersect(rt_ctx* ctx, uint32_t bounce);                 /* IntersectRays  -> trace_bvh.cl:99-211 */
-int rt_compute_aovs(rt_ctx* ctx);                               /* ComputeAOVs    -> aov.cl:44-110 */
+int rt_compute_aovs(rt_ctx* ctx);                               /* ComputeAOVs    -> aov.cl:44-110 (done inside the bounce-0 shading pass) */
 int rt_shade_miss(rt_ctx* ctx, uint32_t bounce);                /* ShadeMissedRays -> miss.cl:41-77 */
 int rt_clear_outgoing_counter(rt_ctx* ctx, uint32_t bounce);    /* ClearOutgoingRayCounter (counters are per bounce here: no-op) */
 int rt_clear_shadow_counter(rt_ctx* ctx);                       /* ClearShadowRayCounter   (no-op, same reason) */

@@ -705,4 +705,101 @@ void orc_render(const OrcScene* scene, const RtCamera* cam, uint32_t width, uint
     }
 }
 
+/* ---- "next" rows: AOVs, temporal denoiser, resolve -------------------------------------------- */
+
+// kernels/cl/aov.cl:30-42
+static V2 ProjectScreen(V3 position, const RtCamera& cam)
+{
+    V3 d = normalize(position - v3(cam.position));
+    V3 ipd = d / dot(v3(cam.front), d);
+    float angle = rt_tanf(0.5f * cam.fov);
+    V3 right = cross(v3(cam.front), v3(cam.up));
+    float u = dot(right, ipd) / (angle * cam.aspect_ratio);
+    float v = dot(v3(cam.up), ipd) / (angle);
+    return V2{ u * 0.5f + 0.5f, v * 0.5f + 0.5f };
+}
+
+/* GenerateAOV (kernels/cl/aov.cl:44-110) on top of the initial values RayGeneration writes
+ * (raygeneration.cl:129-133): albedo float4/pixel, depth float/pixel, normal float4/pixel, velocity float2/pixel. */
+void orc_aovs(const OrcScene* scene, const RtCamera* cam, const RtCamera* prev_cam, uint32_t width, uint32_t height,
+              uint32_t sample_idx, float* albedo, float* depth, float* normal, float* velocity)
+{
+    Scene sc = to_scene(scene);
+    size_t n = (size_t)width * height;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long long i = 0; i < (long long)n; ++i)
+    {
+        albedo[4 * i] = albedo[4 * i + 1] = albedo[4 * i + 2] = 0.0f; albedo[4 * i + 3] = 0.0f;
+        depth[i] = RT_MAX_RENDER_DIST;
+        normal[4 * i] = normal[4 * i + 1] = normal[4 * i + 2] = 0.0f; normal[4 * i + 3] = 0.0f;
+        velocity[2 * i] = velocity[2 * i + 1] = 0.0f;
+        Ray ray = RayGeneration((uint32_t)i, width, height, *cam, sample_idx);
+        RtHit hit;
+        TraceBvh(sc, ray, false, &hit, nullptr);
+        if (hit.primitive_id == RT_INVALID_ID) continue;
+        const RtTriangle& tri = sc.triangles[hit.primitive_id];
+        float u = hit.bc.x, v = hit.bc.y, w0 = 1.0f - u - v;
+        V3 position = Interp(v3(tri.v1.position), v3(tri.v2.position), v3(tri.v3.position), u, v);
+        V2 texcoord = { tri.v1.texcoord.x * w0 + tri.v2.texcoord.x * u + tri.v3.texcoord.x * v,
+                        tri.v1.texcoord.y * w0 + tri.v2.texcoord.y * u + tri.v3.texcoord.y * v };
+        V3 nrm = normalize(Interp(v3(tri.v1.normal), v3(tri.v2.normal), v3(tri.v3.normal), u, v));
+        Material m = ApplyTextures(sc, sc.materials[tri.mtlIndex], texcoord);
+        albedo[4 * i] = m.diffuse_albedo.x; albedo[4 * i + 1] = m.diffuse_albedo.y; albedo[4 * i + 2] = m.diffuse_albedo.z;
+        depth[i] = length(ray.o - position);
+        normal[4 * i] = nrm.x; normal[4 * i + 1] = nrm.y; normal[4 * i + 2] = nrm.z;
+        V2 a = ProjectScreen(position, *cam), b = ProjectScreen(position, *prev_cam);
+        velocity[2 * i] = a.x - b.x; velocity[2 * i + 1] = a.y - b.y;
+    }
+}
+
+/* TemporalAccumulation (kernels/cl/denoiser.cl:27-79): radiance.xyz = mix(radiance, prev_radiance[reprojected], 0.9) */
+void orc_temporal_accumulation(uint32_t width, uint32_t height, float* radiance, const float* prev_radiance,
+                               const float* depth, const float* prev_depth, const float* velocity)
+{
+    for (uint32_t idx = 0; idx < width * height; ++idx)
+    {
+        int x = (int)(idx % width), y = (int)(idx / width);
+        float dv = depth[idx];
+        if (dv == RT_MAX_RENDER_DIST) continue;
+        float pu = ((float)x + 0.5f) / (float)width - velocity[2 * idx];
+        float pv = ((float)y + 0.5f) / (float)height - velocity[2 * idx + 1];
+        float fx = pu * (float)width, fy = pv * (float)height;
+        if (!(fx == fx) || !(fy == fy) || fabsf(fx) > 1.0e9f || fabsf(fy) > 1.0e9f) continue;   // NaN/overflow guard: out of range
+        int px = (int)fx, py = (int)fy;
+        if (px < 0 || px >= (int)width || py < 0 || py >= (int)height) continue;
+        int pidx = py * (int)width + px;
+        float pd = prev_depth[pidx];
+        if (fabsf(dv - pd) / dv > 0.1f) continue;
+        for (int c = 0; c < 3; ++c)
+        {
+            float cur = radiance[4 * idx + c], prev = prev_radiance[4 * pidx + c];
+            radiance[4 * idx + c] = cur + (prev - cur) * 0.9f;
+        }
+    }
+}
+
+/* ResolveRadiance (kernels/cl/resolve_radiance.cl:31-86); aov: 0 shaded colour, 1 albedo, 2 depth, 3 normal, 4 motion */
+void orc_resolve(uint32_t width, uint32_t height, uint32_t aov, const float* radiance, const float* albedo, const float* depth,
+                 const float* normal, const float* velocity, uint32_t sample_count, int denoiser, float* out)
+{
+    for (uint32_t i = 0; i < width * height; ++i)
+    {
+        float* o = out + 4 * (size_t)i;
+        o[3] = 1.0f;
+        if (aov == 1) { o[0] = albedo[4 * i]; o[1] = albedo[4 * i + 1]; o[2] = albedo[4 * i + 2]; }
+        else if (aov == 2) { float d = depth[i] * 0.1f; o[0] = o[1] = o[2] = d; }
+        else if (aov == 3) { for (int c = 0; c < 3; ++c) o[c] = normal[4 * i + c] * 0.5f + 0.5f; }
+        else if (aov == 4) { o[0] = velocity[2 * i]; o[1] = velocity[2 * i + 1]; o[2] = 0.0f; }
+        else
+        {
+            for (int c = 0; c < 3; ++c)
+            {
+                float hdr = radiance[4 * i + c];
+                if (!denoiser) hdr = hdr / (float)sample_count;
+                o[c] = hdr / (hdr + 1.0f);
+            }
+        }
+    }
+}
+
 } // extern "C"

@@ -50,6 +50,9 @@ class Oracle:
         L.orc_sample_sky.argtypes = [C.POINTER(OrcScene), C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_render.argtypes = [C.POINTER(OrcScene), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
                                  C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_aovs.argtypes = [C.POINTER(OrcScene), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32] + [C.c_void_p] * 4
+        L.orc_temporal_accumulation.argtypes = [C.c_uint32, C.c_uint32] + [C.c_void_p] * 5
+        L.orc_resolve.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint32, C.c_int, C.c_void_p]
         a = self._a = {
             "triangles": np.ascontiguousarray(scene["triangles"], dtype=TRIANGLE_DT),
             "nodes": np.ascontiguousarray(scene["nodes"], dtype=NODE_DT),
@@ -96,6 +99,30 @@ class Oracle:
         d = np.ascontiguousarray(dirs, dtype="<f4").reshape(-1, 3)
         out = np.zeros_like(d)
         self.lib.orc_sample_sky(C.byref(self.scene), d.ctypes.data, d.shape[0], out.ctypes.data)
+        return out
+
+    def aovs(self, cam, prev_cam, width, height, sample_idx=0):
+        """-> albedo[h,w,4], depth[h,w], normal[h,w,4], velocity[h,w,2] as GenerateAOV leaves them."""
+        c = np.ascontiguousarray(cam, dtype=CAMERA_DT); pc = np.ascontiguousarray(prev_cam, dtype=CAMERA_DT)
+        al = np.zeros((height, width, 4), "<f4"); de = np.zeros((height, width), "<f4")
+        no = np.zeros((height, width, 4), "<f4"); ve = np.zeros((height, width, 2), "<f4")
+        self.lib.orc_aovs(C.byref(self.scene), c.ctypes.data, pc.ctypes.data, width, height, sample_idx,
+                          al.ctypes.data, de.ctypes.data, no.ctypes.data, ve.ctypes.data)
+        return al, de, no, ve
+
+    def temporal_accumulation(self, radiance, prev_radiance, depth, prev_depth, velocity):
+        h, w = depth.shape
+        r = np.ascontiguousarray(radiance, "<f4").copy()
+        pr = np.ascontiguousarray(prev_radiance, "<f4"); d = np.ascontiguousarray(depth, "<f4")
+        pd = np.ascontiguousarray(prev_depth, "<f4"); v = np.ascontiguousarray(velocity, "<f4")
+        self.lib.orc_temporal_accumulation(w, h, r.ctypes.data, pr.ctypes.data, d.ctypes.data, pd.ctypes.data, v.ctypes.data)
+        return r
+
+    def resolve(self, aov, radiance, albedo, depth, normal, velocity, sample_count, denoiser=False):
+        h, w = depth.shape
+        out = np.zeros((h, w, 4), "<f4")
+        arrs = [np.ascontiguousarray(x, "<f4") for x in (radiance, albedo, depth, normal, velocity)]
+        self.lib.orc_resolve(w, h, aov, *[x.ctypes.data for x in arrs], sample_count, int(denoiser), out.ctypes.data)
         return out
 
     def render(self, cam, width, height, max_bounces, sample_idx=0, white_furnace=False, row_first=0, row_step=1,

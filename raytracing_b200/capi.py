@@ -12,11 +12,12 @@ import numpy as np
 from .layouts import (CAMERA_DT, HIT_DT, LIGHT_DT, MATERIAL_DT, NODE_DT, RAY_DT, SCENE_INFO_DT, TEXTURE_DT, TRIANGLE_DT)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librt_b200.so")
+LIB_PATH = os.environ.get("RT_B200_LIB", os.path.join(HERE, "librt_b200.so"))   # override: tuning variants
 MAX_BOUNCES = 255
 
 OPT_WHITE_FURNACE, OPT_SAMPLER, OPT_AOV, OPT_DENOISER = 0, 1, 2, 3
 OPT_COUNT_TRAVERSAL, OPT_KERNEL_TIMING, OPT_TRAVERSAL, OPT_FUSION, OPT_REFILL_MIN = 16, 17, 18, 19, 20
+OPT_AOV_ALWAYS = 21
 KERNEL_CLASSES = ["raygen", "intersect", "miss", "hit", "intersect_shadow", "accumulate", "extend_shade",
                   "shadow_accumulate", "resolve", "aov", "misc", "trace_closest", "shade_queues"]
 
@@ -226,6 +227,16 @@ class Context:
         st = np.zeros((), dtype=FRAME_STATS_DT)
         self._ck(self.lib.rt_read_frame_stats(self.h, st.ctypes.data))
         return st
+
+    def denoise(self): self._ck(self.lib.rt_denoise(self.h))
+    def copy_history(self): self._ck(self.lib.rt_copy_history(self.h))
+
+    def read_aovs(self):
+        """-> albedo[h,w,4], depth[h,w], normal[h,w,4], velocity[h,w,2] (rows of other ranks left zero)."""
+        al = np.zeros((self.height, self.width, 4), "<f4"); de = np.zeros((self.height, self.width), "<f4")
+        no = np.zeros((self.height, self.width, 4), "<f4"); ve = np.zeros((self.height, self.width, 2), "<f4")
+        self._ck(self.lib.rt_read_aovs(self.h, al.ctypes.data, de.ctypes.data, no.ctypes.data, ve.ctypes.data))
+        return al, de, no, ve
 
     def sample_count(self):
         n = C.c_uint32()

@@ -39,6 +39,15 @@
 
 using namespace rt;
 
+// minimum resident CTAs per SM requested from ptxas for the hot kernels (register budget = 65536 / (256 * N)):
+// tuned on B200, see DESIGN.md section 6
+#ifndef RT_MINB_TRACE
+#define RT_MINB_TRACE 5
+#endif
+#ifndef RT_MINB_SHADE
+#define RT_MINB_SHADE 4
+#endif
+
 namespace
 {
 
@@ -73,6 +82,26 @@ struct FrameParams
     uint32_t width, height, rank, world, n_local, sample_idx;
     int white_furnace;
 };
+
+// AOV outputs of bounce 0 (kernels/cl/aov.cl:44-110), written by the bounce-0 shading pass when enabled
+struct AovCam { f3 position, front, up, right; float angle, aspect_ratio; };
+struct AovParams
+{
+    int enabled;
+    AovCam cam, prev;
+    float4* albedo; float* depth; float4* normal; float2* velocity;
+};
+
+// kernels/cl/aov.cl:30-42
+__device__ __forceinline__ f2 project_screen(f3 position, const AovCam& c)
+{
+    f3 d = normalize(position - c.position);
+    f3 ipd = d / dot(c.front, d);
+    float u = dot(c.right, ipd) / (c.angle * c.aspect_ratio);
+    float v = dot(c.up, ipd) / (c.angle);
+    f2 r; r.x = u * 0.5f + 0.5f; r.y = v * 0.5f + 0.5f;
+    return r;
+}
 
 __device__ __forceinline__ uint32_t pack_pixel(uint32_t px, uint32_t py) { return px | (py << 16); }
 __device__ __forceinline__ uint32_t local_index(const FrameParams& p, uint32_t pxy)
@@ -316,8 +345,8 @@ __device__ __forceinline__ void shade_miss(const DevScene& sc, const FrameParams
 }
 
 // kernels/cl/hit_surface.cl:30-186
-__device__ __forceinline__ void shade_hit(const DevScene& sc, const FrameParams& p, uint32_t bounce, uint32_t pxy,
-                                          f3 ray_dir, f3 hit_throughput, uint32_t prim, float u, float v, ShadeOut& out)
+__device__ __forceinline__ void shade_hit(const DevScene& sc, const FrameParams& p, const AovParams& aov, uint32_t bounce, uint32_t pxy,
+                                          f3 ray_origin, f3 ray_dir, f3 hit_throughput, uint32_t prim, float u, float v, ShadeOut& out)
 {
     f3 incoming = -ray_dir;
     uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
@@ -336,6 +365,16 @@ __device__ __forceinline__ void shade_hit(const DevScene& sc, const FrameParams&
         texcoord.x = r4.w * w0 + r6.x * u + r6.z * v; texcoord.y = r5.w * w0 + r6.y * u + r6.w * v;
     }
     Material material = load_material(sc, mtl, texcoord);
+
+    if (bounce == 0 && aov.enabled)
+    {   // GenerateAOV, aov.cl:106-109
+        uint32_t li = local_index(p, pxy);
+        aov.albedo[li] = make_float4(material.diffuse_albedo.x, material.diffuse_albedo.y, material.diffuse_albedo.z, 0.0f);
+        aov.depth[li] = length(ray_origin - position);
+        aov.normal[li] = make_float4(normal.x, normal.y, normal.z, 0.0f);
+        f2 s0 = project_screen(position, aov.cam), s1 = project_screen(position, aov.prev);
+        aov.velocity[li] = make_float2(s0.x - s1.x, s0.y - s1.y);
+    }
 
     out.emissive = false;
     if (!p.white_furnace && dot(material.emission, splat(1.0f)) > 0.0f)
@@ -377,7 +416,7 @@ __global__ void __launch_bounds__(256) k_reset(float4* radiance, uint32_t n)
 }
 
 // raygeneration.cl:65-139.  One thread per LOCAL pixel; slot i of queue 0 = local pixel i.
-__global__ void __launch_bounds__(256) k_raygen(FrameParams p, RayGenConsts c, Queues q, DevCounters* ctr)
+__global__ void __launch_bounds__(256) k_raygen(FrameParams p, RayGenConsts c, Queues q, DevCounters* ctr, AovParams aov)
 {
     uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li == 0) ctr->q_count[0] = p.n_local;
@@ -389,6 +428,13 @@ __global__ void __launch_bounds__(256) k_raygen(FrameParams p, RayGenConsts c, Q
     q.A[0][li] = make_float4(o.x, o.y, o.z, __uint_as_float(pack_pixel(px, py)));
     q.B[0][li] = make_float4(d.x, d.y, d.z, RT_MAX_RENDER_DIST);
     q.C[0][li] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    if (aov.enabled)
+    {   // raygeneration.cl:129-133
+        aov.albedo[li] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        aov.depth[li] = RT_MAX_RENDER_DIST;
+        aov.normal[li] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        aov.velocity[li] = make_float2(0.0f, 0.0f);
+    }
 }
 
 // IntersectRays (stepwise): closest hit of every live ray of bounce b -> hits[]
@@ -460,7 +506,7 @@ __device__ __forceinline__ void emit_rays(const FrameParams& p, Queues& q, DevCo
 }
 
 // ShadeSurfaceHits (stepwise)
-__global__ void __launch_bounds__(256) k_shade_hits(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
+__global__ void __launch_bounds__(256) k_shade_hits(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce, AovParams aov)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = ctr->q_count[bounce];
@@ -478,7 +524,7 @@ __global__ void __launch_bounds__(256) k_shade_hits(FrameParams p, DevScene sc, 
         {
             float4 a = q.A[in][i], b = q.B[in][i], c = q.C[in][i];
             pixel = __float_as_uint(a.w);
-            shade_hit(sc, p, bounce, pixel, mk3(b), mk3(c), prim, h.x, h.y, so);
+            shade_hit(sc, p, aov, bounce, pixel, mk3(a), mk3(b), mk3(c), prim, h.x, h.y, so);
         }
     }
     emit_rays(p, q, ctr, radiance, bounce, pixel, hit, so);
@@ -527,7 +573,7 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams p, Queues q, Dev
 // (work_ext[bounce]), 32 consecutive rays per grab, so the launch is sized by the machine
 // (SMs x resident CTAs), not by the image.
 template <bool COUNT>
-__global__ void __launch_bounds__(256) k_extend_shade(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
+__global__ void __launch_bounds__(256) k_extend_shade(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce, AovParams aov)
 {
     const uint32_t n = ctr->q_count[bounce];
     const int in = bounce & 1;
@@ -553,7 +599,7 @@ __global__ void __launch_bounds__(256) k_extend_shade(FrameParams p, DevScene sc
             hit = prim != RT_INVALID_ID;
             miss = !hit;
             if (miss) shade_miss(sc, p, radiance, pixel, mk3(b), mk3(c));
-            else shade_hit(sc, p, bounce, pixel, mk3(b), mk3(c), prim, bu, bv, so);
+            else shade_hit(sc, p, aov, bounce, pixel, mk3(a), mk3(b), mk3(c), prim, bu, bv, so);
         }
         warp_count(&ctr->hm[bounce].miss, miss);
         emit_rays(p, q, ctr, radiance, bounce, pixel, hit, so);
@@ -563,7 +609,7 @@ __global__ void __launch_bounds__(256) k_extend_shade(FrameParams p, DevScene sc
 
 // Fused IntersectShadowRays + AccumulateDirectSamples, persistent like k_extend_shade.
 template <bool COUNT>
-__global__ void __launch_bounds__(256) k_shadow_accumulate(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
+__global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
 {
     const uint32_t n = ctr->shadow_count[bounce];
     const int lane = threadIdx.x & 31;
@@ -604,7 +650,7 @@ __global__ void __launch_bounds__(256) k_shadow_accumulate(FrameParams p, DevSce
 // mix the two and idle through each other's code.  Both kernels drain their queues through a global atomic
 // cursor, 32 entries per grab.
 template <bool COUNT>
-__global__ void __launch_bounds__(256) k_trace_closest(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, uint32_t bounce)
+__global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_closest(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, uint32_t bounce)
 {
     const uint32_t n = ctr->q_count[bounce];
     const int in = bounce & 1;
@@ -844,7 +890,7 @@ __global__ void __launch_bounds__(256) k_trace_refill(FrameParams p, DevScene sc
 }
 
 // ShadeSurfaceHits over the hit queue, then ShadeMissedRays over the miss queue (independent pixels).
-__global__ void __launch_bounds__(256) k_shade_queues(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
+__global__ void __launch_bounds__(256, RT_MINB_SHADE) k_shade_queues(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce, AovParams aov)
 {
     const uint32_t n_hit = ctr->hm[bounce].hit, n_miss = ctr->hm[bounce].miss;
     const uint32_t hit_span = (n_hit + 31u) & ~31u;            // warps never mix hits and misses
@@ -870,7 +916,7 @@ __global__ void __launch_bounds__(256) k_shade_queues(FrameParams p, DevScene sc
                 uint32_t i = __float_as_uint(h.w);
                 float4 a = q.A[in][i], b = q.B[in][i], c = q.C[in][i];
                 pixel = __float_as_uint(a.w);
-                shade_hit(sc, p, bounce, pixel, mk3(b), mk3(c), __float_as_uint(h.z), h.x, h.y, so);
+                shade_hit(sc, p, aov, bounce, pixel, mk3(a), mk3(b), mk3(c), __float_as_uint(h.z), h.x, h.y, so);
             }
             emit_rays(p, q, ctr, radiance, bounce, pixel, hit, so);
         }
@@ -887,16 +933,49 @@ __global__ void __launch_bounds__(256) k_shade_queues(FrameParams p, DevScene sc
     }
 }
 
-// resolve_radiance.cl:31-86 (shaded colour): hdr = radiance / sample_count; ldr = hdr / (hdr + 1)
-__global__ void __launch_bounds__(256) k_resolve(const float4* radiance, float4* out, uint32_t n, uint32_t sample_count, int denoiser)
+// resolve_radiance.cl:31-86: shaded colour (radiance / sample_count unless the denoiser is on, then Reinhard x/(1+x))
+// or one of the AOV views
+__global__ void __launch_bounds__(256) k_resolve(const float4* radiance, float4* out, uint32_t n, uint32_t sample_count, int denoiser,
+                                                 int aov_index, AovParams aov)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 r = radiance[i];
-    f3 hdr = mk3(r);
-    if (!denoiser) hdr = hdr / (float)sample_count;
-    f3 ldr = hdr / (mk3(hdr.x + 1.0f, hdr.y + 1.0f, hdr.z + 1.0f));
-    out[i] = make_float4(ldr.x, ldr.y, ldr.z, 1.0f);
+    if (aov_index == 1) { float4 a = aov.albedo[i]; out[i] = make_float4(a.x, a.y, a.z, 1.0f); }
+    else if (aov_index == 2) { float d = aov.depth[i] * 0.1f; out[i] = make_float4(d, d, d, 1.0f); }
+    else if (aov_index == 3) { float4 nn = aov.normal[i]; out[i] = make_float4(nn.x * 0.5f + 0.5f, nn.y * 0.5f + 0.5f, nn.z * 0.5f + 0.5f, 1.0f); }
+    else if (aov_index == 4) { float2 v = aov.velocity[i]; out[i] = make_float4(v.x, v.y, 0.0f, 1.0f); }
+    else
+    {
+        float4 r = radiance[i];
+        f3 hdr = mk3(r);
+        if (!denoiser) hdr = hdr / (float)sample_count;
+        f3 ldr = hdr / (mk3(hdr.x + 1.0f, hdr.y + 1.0f, hdr.z + 1.0f));
+        out[i] = make_float4(ldr.x, ldr.y, ldr.z, 1.0f);
+    }
+}
+
+// TemporalAccumulation, denoiser.cl:27-79 (single-GPU only: the reprojected pixel may be any pixel of the image)
+__global__ void __launch_bounds__(256) k_temporal(uint32_t width, uint32_t height, float4* radiance, const float4* prev_radiance,
+                                                  const float* depth, const float* prev_depth, const float2* velocity)
+{
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= width * height) return;
+    int x = (int)(idx % width), y = (int)(idx / width);
+    float dv = depth[idx];
+    if (dv == RT_MAX_RENDER_DIST) return;
+    float2 mv = velocity[idx];
+    float pu = ((float)x + 0.5f) / (float)width - mv.x;
+    float pv = ((float)y + 0.5f) / (float)height - mv.y;
+    float fx = pu * (float)width, fy = pv * (float)height;
+    if (!(fx == fx) || !(fy == fy) || fabsf(fx) > 1.0e9f || fabsf(fy) > 1.0e9f) return;      // NaN / overflow: out of range
+    int px = (int)fx, py = (int)fy;
+    if (px < 0 || px >= (int)width || py < 0 || py >= (int)height) return;
+    int pidx = py * (int)width + px;
+    float pd = prev_depth[pidx];
+    if (fabsf(dv - pd) / dv > 0.1f) return;
+    float4 cur = radiance[idx], prev = prev_radiance[pidx];
+    cur.x = cur.x + (prev.x - cur.x) * 0.9f; cur.y = cur.y + (prev.y - cur.y) * 0.9f; cur.z = cur.z + (prev.z - cur.z) * 0.9f;
+    radiance[idx] = cur;
 }
 
 __global__ void k_unpack_rays(const float4* A, const float4* B, const uint32_t* count, uint32_t width, RtRay* rays, uint32_t* pixels)
@@ -922,12 +1001,17 @@ struct rt_ctx
     std::string error;
 
     // options
-    int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 2, fusion = 0, refill_min = 8;
+    int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 1, fusion = 0, refill_min = 8;
 
     // per-pixel buffers
     Queues q = {};
     float4* radiance = nullptr;
     float4* resolved = nullptr;
+    // AOV + denoiser buffers (allocated on first use)
+    float4* aov_albedo = nullptr; float* aov_depth = nullptr; float4* aov_normal = nullptr; float2* aov_velocity = nullptr;
+    float4* prev_radiance = nullptr; float* prev_depth = nullptr;
+    int aov_always = 0;
+    RtCamera prev_camera = {}, aov_prev_camera = {};
     DevCounters* counters = nullptr;
     void* scratch = nullptr; size_t scratch_bytes = 0;
 
@@ -1016,6 +1100,8 @@ int require_ready(rt_ctx* c)
     return RT_OK;
 }
 
+void free_aov_buffers(rt_ctx* c);
+
 int alloc_frame_buffers(rt_ctx* c)
 {
     auto freep = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
@@ -1023,6 +1109,7 @@ int alloc_frame_buffers(rt_ctx* c)
     freep(c->q.sA); freep(c->q.sB); freep(c->q.sC); freep(c->q.hits); freep(c->q.shadow_flags);
     freep(c->q.hitq); freep(c->q.missq);
     freep(c->radiance); freep(c->resolved);
+    free_aov_buffers(c);
     c->local_rows = (c->height > c->rank) ? (c->height - c->rank + c->world - 1) / c->world : 0;
     c->n_local = c->local_rows * c->width;
     size_t n = c->n_local ? c->n_local : 1;
@@ -1038,7 +1125,52 @@ int alloc_frame_buffers(rt_ctx* c)
     return RT_OK;
 }
 
-int persistent_grid(rt_ctx* c) { return c->num_sms * 8; }   // 8 CTAs x 256 threads = full occupancy target per SM
+int persistent_grid(rt_ctx* c) { return c->num_sms * 8; }
+
+bool aov_wanted(const rt_ctx* c) { return c->aov != 0 || c->denoiser != 0 || c->aov_always != 0; }
+
+AovCam aov_cam(const RtCamera& cam)
+{
+    AovCam a;
+    a.position = f3{ cam.position.x, cam.position.y, cam.position.z };
+    a.front = f3{ cam.front.x, cam.front.y, cam.front.z };
+    a.up = f3{ cam.up.x, cam.up.y, cam.up.z };
+    a.right = f3{ a.front.y * a.up.z - a.front.z * a.up.y, a.front.z * a.up.x - a.front.x * a.up.z, a.front.x * a.up.y - a.front.y * a.up.x };
+    a.angle = rt_tanf(0.5f * cam.fov);          // aov.cl:35
+    a.aspect_ratio = cam.aspect_ratio;
+    return a;
+}
+
+AovParams aov_params(const rt_ctx* c)
+{
+    AovParams a;
+    memset(&a, 0, sizeof(a));
+    a.enabled = (aov_wanted(c) && c->aov_albedo) ? 1 : 0;
+    a.cam = aov_cam(c->camera); a.prev = aov_cam(c->aov_prev_camera);
+    a.albedo = c->aov_albedo; a.depth = c->aov_depth; a.normal = c->aov_normal; a.velocity = c->aov_velocity;
+    return a;
+}
+
+int ensure_aov_buffers(rt_ctx* c)
+{
+    if (c->aov_albedo) return RT_OK;
+    size_t n = c->n_local ? c->n_local : 1;
+    RT_CUDA(c, cudaMalloc(&c->aov_albedo, n * 16)); RT_CUDA(c, cudaMalloc(&c->aov_depth, n * 4));
+    RT_CUDA(c, cudaMalloc(&c->aov_normal, n * 16)); RT_CUDA(c, cudaMalloc(&c->aov_velocity, n * 8));
+    RT_CUDA(c, cudaMalloc(&c->prev_radiance, n * 16)); RT_CUDA(c, cudaMalloc(&c->prev_depth, n * 4));
+    RT_CUDA(c, cudaMemsetAsync(c->aov_albedo, 0, n * 16, c->stream)); RT_CUDA(c, cudaMemsetAsync(c->aov_depth, 0, n * 4, c->stream));
+    RT_CUDA(c, cudaMemsetAsync(c->aov_normal, 0, n * 16, c->stream)); RT_CUDA(c, cudaMemsetAsync(c->aov_velocity, 0, n * 8, c->stream));
+    RT_CUDA(c, cudaMemsetAsync(c->prev_radiance, 0, n * 16, c->stream)); RT_CUDA(c, cudaMemsetAsync(c->prev_depth, 0, n * 4, c->stream));
+    return RT_OK;
+}
+
+void free_aov_buffers(rt_ctx* c)
+{
+    cudaFree(c->aov_albedo); cudaFree(c->aov_depth); cudaFree(c->aov_normal); cudaFree(c->aov_velocity);
+    cudaFree(c->prev_radiance); cudaFree(c->prev_depth);
+    c->aov_albedo = nullptr; c->aov_depth = nullptr; c->aov_normal = nullptr; c->aov_velocity = nullptr;
+    c->prev_radiance = nullptr; c->prev_depth = nullptr;
+}   // 8 CTAs x 256 threads = full occupancy target per SM
 
 } // namespace
 
@@ -1086,6 +1218,7 @@ int rt_destroy(rt_ctx* c)
     cudaFree(c->q.sA); cudaFree(c->q.sB); cudaFree(c->q.sC); cudaFree(c->q.hits); cudaFree(c->q.shadow_flags);
     cudaFree(c->q.hitq); cudaFree(c->q.missq);
     cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->counters); cudaFree(c->scratch);
+    free_aov_buffers(c);
     for (void* p : c->scene_allocs) cudaFree(p);
     for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
@@ -1193,6 +1326,8 @@ int rt_set_camera(rt_ctx* c, const RtCamera* cam)
     RT_CHECK_CTX(c);
     if (!cam) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_set_camera: null camera");
     c->camera = *cam;
+    c->aov_prev_camera = c->prev_camera;        // the AOV kernel sees the camera of the previous SetCameraData call
+    c->prev_camera = *cam;                      // (cl_pt_integrator.cpp:365-371; zero-initialised before the first call)
     RayGenConsts& r = c->raygen;
     r.position = f3{ cam->position.x, cam->position.y, cam->position.z };
     r.front = f3{ cam->front.x, cam->front.y, cam->front.z };
@@ -1219,11 +1354,19 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
         c->sampler = 0; return RT_OK;
     case RT_OPT_AOV:
         if (value > 4) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "AOV index out of range");
-        if (value != 0) RT_FAIL(c, RT_ERR_UNSUPPORTED, "AOV views are not implemented yet (SURVEY 8f rank 2)");
-        c->aov = (int)value; return RT_OK;
+        c->aov = (int)value;
+        if (aov_wanted(c)) { RT_CUDA(c, cudaSetDevice(c->device)); return ensure_aov_buffers(c); }
+        return RT_OK;
     case RT_OPT_DENOISER:
-        if (value != 0) RT_FAIL(c, RT_ERR_UNSUPPORTED, "temporal denoiser is not implemented yet (SURVEY 8f rank 4)");
-        c->denoiser = 0; return RT_OK;
+        if (value != 0 && c->world != 1)
+            RT_FAIL(c, RT_ERR_UNSUPPORTED, "the temporal denoiser reprojects across the whole image and is not available with a multi-GPU partition");
+        c->denoiser = value != 0;
+        if (aov_wanted(c)) { RT_CUDA(c, cudaSetDevice(c->device)); return ensure_aov_buffers(c); }
+        return RT_OK;
+    case RT_OPT_AOV_ALWAYS:
+        c->aov_always = value != 0;
+        if (aov_wanted(c)) { RT_CUDA(c, cudaSetDevice(c->device)); return ensure_aov_buffers(c); }
+        return RT_OK;
     case RT_OPT_COUNT_TRAVERSAL: c->count_traversal = value != 0; return RT_OK;
     case RT_OPT_KERNEL_TIMING: c->kernel_timing = value != 0; return RT_OK;
     case RT_OPT_FUSION:
@@ -1258,7 +1401,7 @@ int rt_generate_rays(rt_ctx* c)
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(DevCounters), c->stream));
     TimedLaunch t(c, RT_K_RAYGEN);
-    k_raygen<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->raygen, c->q, c->counters);
+    k_raygen<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->raygen, c->q, c->counters, aov_params(c));
     c->frame_started = true;
     return post_launch(c, "k_raygen");
 }
@@ -1280,7 +1423,16 @@ int rt_intersect(rt_ctx* c, uint32_t bounce)
     return post_launch(c, "k_intersect");
 }
 
-int rt_compute_aovs(rt_ctx* c) { RT_CHECK_CTX(c); return RT_OK; }   /* AOVs not produced yet: empty step, like gl_pt_integrator.cpp:230-243 */
+/* ComputeAOVs: the AOV outputs are produced by the bounce-0 shading pass (it already holds the hit, the interpolated
+ * normal and the unpacked material), so this step only makes sure the buffers exist when a view or the denoiser
+ * needs them; with the default view (shaded colour, no denoiser) no AOV work is done at all. */
+int rt_compute_aovs(rt_ctx* c)
+{
+    RT_CHECK_CTX(c);
+    if (!aov_wanted(c)) return RT_OK;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    return ensure_aov_buffers(c);
+}
 
 int rt_shade_miss(rt_ctx* c, uint32_t bounce)
 {
@@ -1298,7 +1450,7 @@ int rt_shade_hits(rt_ctx* c, uint32_t bounce)
     RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
     c->cur_bounce = bounce;
     TimedLaunch t(c, RT_K_HIT);
-    k_shade_hits<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce);
+    k_shade_hits<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, aov_params(c));
     return post_launch(c, "k_shade_hits");
 }
 
@@ -1319,8 +1471,28 @@ int rt_accumulate_direct(rt_ctx* c)
     return post_launch(c, "k_accumulate");
 }
 
-int rt_denoise(rt_ctx* c) { RT_CHECK_CTX(c); return RT_OK; }
-int rt_copy_history(rt_ctx* c) { RT_CHECK_CTX(c); return RT_OK; }
+int rt_denoise(rt_ctx* c)
+{
+    RT_CHECK_CTX(c);
+    if (!c->denoiser) return RT_OK;
+    if (c->world != 1) RT_FAIL(c, RT_ERR_UNSUPPORTED, "temporal denoiser is single-GPU only");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_aov_buffers(c); if (rc) return rc;
+    TimedLaunch t(c, RT_K_MISC);
+    k_temporal<<<grid_for(c->n_local), 256, 0, c->stream>>>(c->width, c->height, c->radiance, c->prev_radiance, c->aov_depth, c->prev_depth, c->aov_velocity);
+    return post_launch(c, "k_temporal");
+}
+
+int rt_copy_history(rt_ctx* c)
+{   // cl_pt_integrator.cpp:670-675
+    RT_CHECK_CTX(c);
+    if (!c->denoiser) return RT_OK;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_aov_buffers(c); if (rc) return rc;
+    RT_CUDA(c, cudaMemcpyAsync(c->prev_radiance, c->radiance, (size_t)c->n_local * 16, cudaMemcpyDeviceToDevice, c->stream));
+    RT_CUDA(c, cudaMemcpyAsync(c->prev_depth, c->aov_depth, (size_t)c->n_local * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return RT_OK;
+}
 
 int rt_extend_shade(rt_ctx* c, uint32_t bounce)
 {
@@ -1330,8 +1502,8 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
     if (c->fusion == 1)
     {   // monolithic variant: trace + miss + shade in one kernel
         TimedLaunch t(c, RT_K_EXTEND_SHADE);
-        if (c->count_traversal) k_extend_shade<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-        else k_extend_shade<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+        if (c->count_traversal) k_extend_shade<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce, aov_params(c));
+        else k_extend_shade<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce, aov_params(c));
         return post_launch(c, "k_extend_shade");
     }
     if (c->traversal == 2 && !c->count_traversal)
@@ -1348,7 +1520,7 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
         int rc = post_launch(c, "k_trace_closest"); if (rc) return rc;
     }
     TimedLaunch t(c, RT_K_SHADE_QUEUES);
-    k_shade_queues<<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce);
+    k_shade_queues<<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, aov_params(c));
     return post_launch(c, "k_shade_queues");
 }
 
@@ -1386,7 +1558,8 @@ int rt_resolve(rt_ctx* c, float* dst)
     RT_CUDA(c, cudaSetDevice(c->device));
     {
         TimedLaunch t(c, RT_K_RESOLVE);
-        k_resolve<<<grid_for(c->n_local), 256, 0, c->stream>>>(c->radiance, c->resolved, c->n_local, c->sample_count, c->denoiser);
+        k_resolve<<<grid_for(c->n_local), 256, 0, c->stream>>>(c->radiance, c->resolved, c->n_local, c->sample_count, c->denoiser,
+                                                                  aov_params(c).enabled ? c->aov : 0, aov_params(c));
         int rc = post_launch(c, "k_resolve"); if (rc) return rc;
     }
     if (dst && c->local_rows)
@@ -1488,7 +1661,22 @@ int rt_read_frame_stats(rt_ctx* c, RtFrameStats* out)
 
 int rt_read_sample_count(rt_ctx* c, uint32_t* out) { RT_CHECK_CTX(c); if (!out) return RT_ERR_INVALID_ARGUMENT; *out = c->sample_count; return RT_OK; }
 
-int rt_read_aovs(rt_ctx* c, float*, float*, float*, float*) { RT_CHECK_CTX(c); RT_FAIL(c, RT_ERR_UNSUPPORTED, "AOV buffers are not implemented yet (SURVEY 8f rank 2)"); }
+int rt_read_aovs(rt_ctx* c, float* albedo, float* depth, float* normal, float* velocity)
+{
+    RT_CHECK_CTX(c);
+    if (!c->aov_albedo) RT_FAIL(c, RT_ERR_NOT_READY, "AOV buffers do not exist: select an AOV view, enable the denoiser or set RT_OPT_AOV_ALWAYS first");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    auto rows = [&](void* dst, const void* src, size_t elem) -> int {
+        if (dst && c->local_rows)
+            RT_CUDA(c, cudaMemcpy2DAsync((char*)dst + (size_t)c->rank * c->width * elem, (size_t)c->world * c->width * elem, src,
+                                         (size_t)c->width * elem, (size_t)c->width * elem, c->local_rows, cudaMemcpyDeviceToHost, c->stream));
+        return RT_OK;
+    };
+    int rc;
+    if ((rc = rows(albedo, c->aov_albedo, 16)) || (rc = rows(depth, c->aov_depth, 4)) || (rc = rows(normal, c->aov_normal, 16)) || (rc = rows(velocity, c->aov_velocity, 8))) return rc;
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
 
 int rt_kernel_times(rt_ctx* c, float* ms, uint32_t* launches)
 {

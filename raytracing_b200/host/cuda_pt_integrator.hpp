@@ -14,6 +14,8 @@
  *                     end of each loop iteration of Integrate() the device state is the same as with
  *                     the stepwise schedule, bit for bit.
  *   kStepwise         one kernel per virtual, like the OpenCL backend.
+ * AOVs (ComputeAOVs) are produced inside the bounce-0 shading pass, and only when SetAOV selected a view other than
+ * the shaded colour or the denoiser is on.  SetSamplerType(kBlueNoise) is not supported (throws).
  * The last constructor argument of the OpenCL backend is a GL texture to resolve into
  * (cl_pt_integrator.hpp:33-34); here ResolveRadiance() writes to a host RGBA32F image instead
  * (SetResolveTarget), or only resolves on the device if none is set.

@@ -214,6 +214,51 @@ def test_synthetic_field_matches_oracle():
     c.destroy()
 
 
+def test_aovs_denoiser_and_views_match_oracle():
+    """GenerateAOV (aov.cl), TemporalAccumulation (denoiser.cl), ResolveRadiance views — three frames with
+    a moving camera and the denoiser on (sample index keeps counting, radiance is re-initialised every frame)."""
+    name, w, h, mb = "ShaderBalls", 192, 108, 3
+    sc = scene(name)
+    o = Oracle(sc)
+    c = capi.Context(w, h)
+    c.upload_scene(sc)
+    c.set_option(capi.OPT_DENOISER, 1)
+    cams = [default_camera(w, h), default_camera(w, h, position=(0.05, -1.02, 1.01)), default_camera(w, h, position=(0.05, -1.02, 1.01))]
+    prev_cam = np.zeros((), dtype=cams[0].dtype)
+    prev_rad = np.zeros((h, w, 4), "<f4"); prev_depth = np.zeros((h, w), "<f4")
+    for f, cam in enumerate(cams):
+        c.set_camera(cam)
+        # Integrator::Integrate with the denoiser enabled (integrator.cpp:27-59)
+        c.reset(); c.generate_rays()
+        for b in range(mb + 1):
+            c.intersect(b)
+            if b == 0:
+                c.compute_aovs()
+            c.shade_miss(b); c.shade_hits(b); c.intersect_shadow(); c.accumulate_direct()
+        c.advance_sample_count(); c.denoise(); c.copy_history()
+        img = c.resolve()
+        rad, _, _ = o.render(cam, w, h, mb, sample_idx=f)
+        al, de, no, ve = o.aovs(cam, prev_cam, w, h, sample_idx=f)
+        gal, gde, gno, gve = c.read_aovs()
+        assert np.array_equal(bits(gal[..., :3]), bits(al[..., :3])) and np.array_equal(bits(gde), bits(de))
+        assert np.array_equal(bits(gno[..., :3]), bits(no[..., :3])) and np.array_equal(bits(gve), bits(ve))
+        den = o.temporal_accumulation(rad, prev_rad, de, prev_depth, ve)
+        assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(den[..., :3])), f
+        assert np.array_equal(bits(img), bits(o.resolve(0, den, al, de, no, ve, f + 1, denoiser=True))), f
+        prev_rad, prev_depth, prev_cam = den, de, cam
+    for view in (1, 2, 3, 4):
+        c.set_option(capi.OPT_AOV, view)
+        assert np.array_equal(bits(c.resolve()), bits(o.resolve(view, den, al, de, no, ve, 3, denoiser=True))), view
+    c.destroy()
+    # fused schedule + AOV view without the denoiser
+    c = make_ctx(name, w, h)
+    c.set_option(capi.OPT_AOV, 3)
+    c.reset(); c.integrate(mb)
+    al, de, no, ve = o.aovs(default_camera(w, h), np.zeros((), dtype=cams[0].dtype), w, h)
+    assert np.array_equal(bits(c.resolve()[..., :3]), bits(no[..., :3] * np.float32(0.5) + np.float32(0.5)))
+    c.destroy()
+
+
 def test_error_behaviour():
     c = capi.Context(32, 32)
     with pytest.raises(capi.RtError):
@@ -227,4 +272,10 @@ def test_error_behaviour():
         c.integrate(3)                        # no camera yet
     with pytest.raises(capi.RtError):
         c.set_option(capi.OPT_SAMPLER, 1)     # blue noise not implemented: loud, not silent
+    c.destroy()
+    c = capi.Context(32, 32, rank=1, world=2)
+    with pytest.raises(capi.RtError):
+        c.set_option(capi.OPT_DENOISER, 1)    # temporal reprojection needs the whole image on one GPU
+    with pytest.raises(capi.RtError):
+        capi.Context(70000, 16)               # pixel coordinates are packed in 16 + 16 bits
     c.destroy()
