@@ -35,4 +35,8 @@ def load_golden(path):
 
 
 def bits(a):
-    return np.ascontiguousarray(a, dtype="<f4").view("<u4")
+    """Bit pattern of a float32 array for exact comparisons.  NaNs are canonicalised first: the payload/sign of a NaN
+    produced by an invalid operation is not specified by IEEE 754 (x86 gives 0xFFC00000, sm_100a 0x7FFFFFFF)."""
+    u = np.ascontiguousarray(a, dtype="<f4").copy().view("<u4")
+    u[(u & 0x7FFFFFFF) > 0x7F800000] = 0x7FC00000
+    return u
