@@ -72,6 +72,8 @@ typedef enum RtOption {
                                    results are bit-identical */
     RT_OPT_AOV_ALWAYS = 21,     /* 1: produce the AOV buffers every frame even with the shaded-colour view (the reference always
                                    does; here they are skipped unless a view or the denoiser needs them) */
+    RT_OPT_SMEM_BVH = 22,       /* 1 (default): scenes whose traversal records fit 40 KB are staged into shared memory by a TMA
+                                   bulk copy at the start of every traversal kernel; 0: always fetch through L1 */
     RT_OPT_REFILL_MIN = 20,     /* traversal mode 2: refill a warp when at least this many lanes are idle (1..32) */
     RT_OPT_FUSION = 19          /* rt_extend_shade: 0 = traversal kernel + hit/miss queue compaction + shading kernel
                                    (default), 1 = one monolithic kernel; results are bit-identical */

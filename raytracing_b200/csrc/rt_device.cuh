@@ -127,6 +127,7 @@ struct DevScene
     // optimised traversal layout (built at upload, see rt_bvh_layout.h)
     const float4* wnodes;          // 4 x float4 per interior node
     const float4* wtris;           // 3 x float4 per triangle: p1, e1, e2 (+ end-of-leaf flag)
+    uint32_t wnodes_f4, wtris_f4;  // sizes of the two arrays in float4 (for the TMA staging of small scenes)
     int root_ref;
 };
 

@@ -137,6 +137,44 @@ __device__ __forceinline__ void warp_sum64(unsigned long long* counter, uint32_t
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(counter, (unsigned long long)v);
 }
 
+// ------------------------------------------------------------------------------------ TMA staging of a small BVH
+// When the whole traversal structure (interior records + triangle records) is small enough, every CTA of a
+// traversal kernel copies it ONCE into shared memory with two TMA bulk copies (cp.async.bulk, completion signalled
+// through an mbarrier transaction count) issued by one elected thread, and all node / triangle fetches of the
+// kernel become shared-memory loads: the L1 data pipe is the second-busiest unit of the traversal kernels (ncu:
+// l1tex data-pipe wavefronts ~58 % of peak, a divergent LDG.128 touches one 128-byte line per active lane), while a
+// 16-byte LDS from 32 different records needs 4 conflict-free wavefronts.  The kernels are persistent, so the copy
+// is amortised over every ray the CTA traces.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_stage_bvh(float4* dst, const DevScene& sc, uint64_t* mbar)
+{
+    const uint32_t bar = smem_u32(mbar);
+    const uint32_t nodes_bytes = sc.wnodes_f4 * 16u, tris_bytes = sc.wtris_f4 * 16u;
+    if (threadIdx.x == 0)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nodes_bytes + tris_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst)), "l"(sc.wnodes), "r"(nodes_bytes), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst + sc.wnodes_f4)), "l"(sc.wtris), "r"(tris_bytes), "r"(bar) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(0) : "memory");
+}
+
+template <bool SMEM>
+__device__ __forceinline__ float4 ld_bvh(const float4* p) { return SMEM ? *p : __ldg(p); }
+
 // ------------------------------------------------------------------------------------ traversal
 // Literal restatement of kernels/cl/trace_bvh.cl:99-211 on the reference node layout: per-ray
 // DFS, 64-entry private stack, far child pushed unconditionally and box-tested when popped,
@@ -212,8 +250,8 @@ __device__ __forceinline__ uint32_t trace_literal(const DevScene& sc, f3 o, f3 d
 // the same arithmetic per box / triangle test as trace_literal, so results are bit-identical
 // for finite rays; non-finite rays (NaN/inf components; their traversal is garbage-in but must
 // still match) take the literal path.
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, f3 o, f3 d, float t_min, float t_max,
+template <bool ANY, bool COUNT, bool SMEM>
+__device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4* wnodes, const float4* wtris, f3 o, f3 d, float t_min, float t_max,
                                                float& bu, float& bv, float& bt, uint32_t& nv, uint32_t& nt)
 {
     float fin = ((o.x + o.y) + o.z) + ((d.x + d.y) + d.z);
@@ -247,8 +285,8 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, f3 o, f3 d, f
     {
         while (cur >= 0)
         {
-            const float4* np = sc.wnodes + (size_t)cur * 4;
-            float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2), m = __ldg(np + 3);
+            const float4* np = wnodes + (size_t)cur * 4;
+            float4 a = ld_bvh<SMEM>(np), b = ld_bvh<SMEM>(np + 1), c = ld_bvh<SMEM>(np + 2), m = ld_bvh<SMEM>(np + 3);
             // child 0 box: min (a.x,a.y,a.z) max (a.w,b.x,b.y); child 1 box: min (b.z,b.w,c.x) max (c.y,c.z,c.w)
             f3 t00 = (mk3(a.x, a.y, a.z) - o) * inv, t01 = (mk3(a.w, b.x, b.y) - o) * inv;
             f3 t10 = (mk3(b.z, b.w, c.x) - o) * inv, t11 = (mk3(c.y, c.z, c.w) - o) * inv;
@@ -281,8 +319,8 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, f3 o, f3 d, f
         uint32_t ti = (uint32_t)(~cur);
         for (;;)
         {
-            const float4* tp = sc.wtris + (size_t)ti * 3;
-            float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+            const float4* tp = wtris + (size_t)ti * 3;
+            float4 q0 = ld_bvh<SMEM>(tp), q1 = ld_bvh<SMEM>(tp + 1), q2 = ld_bvh<SMEM>(tp + 2);
             f3 p1 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
             bool last = __float_as_uint(q2.y) != 0u;
             f3 pvec = cross(d, e2);
@@ -321,7 +359,7 @@ __device__ __forceinline__ uint32_t trace(const DevScene& sc, int mode, f3 o, f3
                                           float& bu, float& bv, float& bt, uint32_t& nv, uint32_t& nt)
 {
     if (mode == 0) return trace_literal<ANY, COUNT>(sc, o, d, t_min, t_max, bu, bv, bt, nv, nt);
-    return trace_fast<ANY, COUNT>(sc, o, d, t_min, t_max, bu, bv, bt, nv, nt);
+    return trace_fast<ANY, COUNT, false>(sc, sc.wnodes, sc.wtris, o, d, t_min, t_max, bu, bv, bt, nv, nt);
 }
 
 // ------------------------------------------------------------------------------------ shading
@@ -608,9 +646,12 @@ __global__ void __launch_bounds__(256) k_extend_shade(FrameParams p, DevScene sc
 }
 
 // Fused IntersectShadowRays + AccumulateDirectSamples, persistent like k_extend_shade.
-template <bool COUNT>
+template <bool COUNT, bool SMEM>
 __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
 {
+    extern __shared__ __align__(128) float4 s_bvh[];
+    __shared__ uint64_t s_mbar;
+    if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
     const uint32_t n = ctr->shadow_count[bounce];
     const int lane = threadIdx.x & 31;
     uint32_t nv = 0, nt = 0;
@@ -626,7 +667,8 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameP
         {
             float4 a = q.sA[i], b = q.sB[i];
             float bu, bv, bt;
-            un = trace<true, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
+            if (SMEM) un = trace_fast<true, false, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
+            else un = trace<true, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
             if (un)
             {
                 float4 c = q.sC[i];
@@ -649,9 +691,12 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameP
 // warps of hits (Lambert/GGX + NEE) and full warps of misses (environment lookup) instead of warps that
 // mix the two and idle through each other's code.  Both kernels drain their queues through a global atomic
 // cursor, 32 entries per grab.
-template <bool COUNT>
+template <bool COUNT, bool SMEM>
 __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_closest(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, uint32_t bounce)
 {
+    extern __shared__ __align__(128) float4 s_bvh[];
+    __shared__ uint64_t s_mbar;
+    if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
     const uint32_t n = ctr->q_count[bounce];
     const int in = bounce & 1;
     const int lane = threadIdx.x & 31;
@@ -669,7 +714,8 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_closest(FrameParam
         if (live)
         {
             float4 a = q.A[in][i], b = q.B[in][i];
-            prim = trace<false, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
+            if (SMEM) prim = trace_fast<false, false, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
+            else prim = trace<false, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
             hit = prim != RT_INVALID_ID;
         }
         uint32_t hi = warp_append(&ctr->hm[bounce].hit, hit);
@@ -1001,7 +1047,7 @@ struct rt_ctx
     std::string error;
 
     // options
-    int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 1, fusion = 0, refill_min = 8;
+    int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 1, fusion = 0, refill_min = 8, smem_bvh = 1;
 
     // per-pixel buffers
     Queues q = {};
@@ -1126,6 +1172,15 @@ int alloc_frame_buffers(rt_ctx* c)
 }
 
 int persistent_grid(rt_ctx* c) { return c->num_sms * 8; }
+
+// Bytes of dynamic shared memory for the TMA-staged BVH, or 0 when staging does not apply: only the optimised
+// traversal (mode 1) on a scene whose records fit 40 KB (5 resident CTAs x 40 KB stay under the 227 KB of an SM).
+size_t smem_stage_bytes(const rt_ctx* c)
+{
+    if (!c->smem_bvh || c->traversal != 1) return 0;
+    size_t bytes = ((size_t)c->scene.wnodes_f4 + c->scene.wtris_f4) * 16;
+    return bytes <= 40 * 1024 ? bytes : 0;
+}
 
 bool aov_wanted(const rt_ctx* c) { return c->aov != 0 || c->denoiser != 0 || c->aov_always != 0; }
 
@@ -1316,6 +1371,7 @@ int rt_upload_scene(rt_ctx* c, const RtSceneDesc* s)
         if ((rc = upload(wl.nodes.data(), wl.nodes.size() * 16, (const void**)&ds.wnodes))) return rc;
         if ((rc = upload(wl.tris.data(), wl.tris.size() * 16, (const void**)&ds.wtris))) return rc;
         ds.root_ref = wl.root_ref;
+        ds.wnodes_f4 = (uint32_t)wl.nodes.size(); ds.wtris_f4 = (uint32_t)wl.tris.size();
     }
     c->scene_ready = true;
     return RT_OK;
@@ -1369,6 +1425,7 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
         return RT_OK;
     case RT_OPT_COUNT_TRAVERSAL: c->count_traversal = value != 0; return RT_OK;
     case RT_OPT_KERNEL_TIMING: c->kernel_timing = value != 0; return RT_OK;
+    case RT_OPT_SMEM_BVH: c->smem_bvh = value != 0; return RT_OK;
     case RT_OPT_FUSION:
         if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "fusion mode must be 0 or 1");
         c->fusion = (int)value; return RT_OK;
@@ -1515,8 +1572,10 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
     else
     {
         TimedLaunch t(c, RT_K_TRACE_CLOSEST);
-        if (c->count_traversal) k_trace_closest<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
-        else k_trace_closest<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
+        size_t stage = smem_stage_bytes(c);
+        if (c->count_traversal) k_trace_closest<true, false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
+        else if (stage) k_trace_closest<false, true><<<grid, 256, stage, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
+        else k_trace_closest<false, false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
         int rc = post_launch(c, "k_trace_closest"); if (rc) return rc;
     }
     TimedLaunch t(c, RT_K_SHADE_QUEUES);
@@ -1534,8 +1593,10 @@ int rt_shadow_accumulate(rt_ctx* c, uint32_t bounce)
         k_trace_refill<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, c->refill_min);
         return post_launch(c, "k_trace_refill<any>");
     }
-    if (c->count_traversal) k_shadow_accumulate<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-    else k_shadow_accumulate<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    size_t stage = smem_stage_bytes(c);
+    if (c->count_traversal) k_shadow_accumulate<true, false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    else if (stage) k_shadow_accumulate<false, true><<<grid, 256, stage, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    else k_shadow_accumulate<false, false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
     return post_launch(c, "k_shadow_accumulate");
 }
 
