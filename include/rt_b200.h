@@ -142,6 +142,11 @@ int rt_copy_history(rt_ctx* ctx);                               /* CopyHistoryBu
  * (the reference's only Finish(), cl_pt_integrator.cpp:677-684). */
 int rt_resolve(rt_ctx* ctx, float* dst_rgba);
 
+/* Pipelined read-back for frame loops: resolve on the render stream, device->host copy on a second stream (overlaps the
+ * next frame's kernels).  dst must stay untouched until rt_resolve_wait() returns. */
+int rt_resolve_async(rt_ctx* ctx, float* dst_rgba);
+int rt_resolve_wait(rt_ctx* ctx);
+
 /* ---- fused steps (same per-pixel results, fewer passes over HBM) ------------------ */
 int rt_extend_shade(rt_ctx* ctx, uint32_t bounce);              /* IntersectRays + ShadeMissedRays + ShadeSurfaceHits */
 int rt_shadow_accumulate(rt_ctx* ctx, uint32_t bounce);         /* IntersectShadowRays + AccumulateDirectSamples */

@@ -25,7 +25,7 @@ KERNEL_CLASSES = ["raygen", "intersect", "miss", "hit", "intersect_shadow", "acc
 SYMBOLS = ["rt_create", "rt_destroy", "rt_last_error", "rt_set_partition", "rt_upload_scene", "rt_set_camera", "rt_set_option",
            "rt_reset", "rt_advance_sample_count", "rt_generate_rays", "rt_intersect", "rt_compute_aovs", "rt_shade_miss",
            "rt_clear_outgoing_counter", "rt_clear_shadow_counter", "rt_shade_hits", "rt_intersect_shadow",
-           "rt_accumulate_direct", "rt_denoise", "rt_copy_history", "rt_resolve", "rt_extend_shade", "rt_shadow_accumulate",
+           "rt_accumulate_direct", "rt_denoise", "rt_copy_history", "rt_resolve", "rt_resolve_async", "rt_resolve_wait", "rt_extend_shade", "rt_shadow_accumulate",
            "rt_integrate", "rt_sync", "rt_read_hits", "rt_read_rays", "rt_read_radiance", "rt_read_frame_stats",
            "rt_read_sample_count", "rt_read_aovs", "rt_kernel_times", "rt_launch_count", "rt_local_pixel_count",
            "rt_radiance_device_ptr", "rt_stream_handle"]
@@ -79,6 +79,8 @@ def load_library():
                  "rt_shadow_accumulate", "rt_integrate"):
         getattr(L, name).argtypes = [C.c_void_p, C.c_uint32]
     L.rt_resolve.argtypes = [C.c_void_p, C.c_void_p]
+    L.rt_resolve_async.argtypes = [C.c_void_p, C.c_void_p]
+    L.rt_resolve_wait.argtypes = [C.c_void_p]
     L.rt_read_hits.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
     L.rt_read_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
     L.rt_read_radiance.argtypes = [C.c_void_p, C.c_void_p]
@@ -194,6 +196,12 @@ class Context:
             out = np.zeros((self.height, self.width, 4), dtype="<f4")
         self._ck(self.lib.rt_resolve(self.h, out.ctypes.data))
         return out
+
+    def resolve_async(self, out):
+        """out: pinned/contiguous (h, w, 4) float32 host array that stays alive and untouched until resolve_wait()."""
+        self._ck(self.lib.rt_resolve_async(self.h, out.ctypes.data))
+
+    def resolve_wait(self): self._ck(self.lib.rt_resolve_wait(self.h))
 
     # ---- taps
     def local_pixel_count(self):

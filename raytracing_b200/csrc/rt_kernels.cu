@@ -657,10 +657,13 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameP
     uint32_t nv = 0, nt = 0;
     for (;;)
     {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->work_shadow[bounce], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
+        uint32_t base0 = 0;
+        if (lane == 0) base0 = atomicAdd(&ctr->work_shadow[bounce], 64u);
+        base0 = __shfl_sync(0xffffffffu, base0, 0);
+        if (base0 >= n) break;
+#pragma unroll 1
+      for (uint32_t base = base0; base < base0 + 64u && base < n; base += 32u)
+      {
         uint32_t i = base + lane;
         bool un = false;
         if (i < n)
@@ -680,6 +683,7 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameP
             }
         }
         warp_count(&ctr->n_unoccluded[bounce], un);
+      }
     }
     if (COUNT) { warp_sum64(&ctr->nodes_shadow[bounce], nv); warp_sum64(&ctr->tris_shadow[bounce], nt); }
 }
@@ -700,29 +704,38 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_closest(FrameParam
     const uint32_t n = ctr->q_count[bounce];
     const int in = bounce & 1;
     const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t nv = 0, nt = 0;
     for (;;)
     {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->work_ext[bounce], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + lane;
-        bool live = i < n, hit = false;
-        float bu = 0.0f, bv = 0.0f, bt = 0.0f;
-        uint32_t prim = RT_INVALID_ID;
-        if (live)
+        // one cursor atomic per 64 rays (two rounds of 32), one 64-bit atomic per round for BOTH queue appends
+        uint32_t base0 = 0;
+        if (lane == 0) base0 = atomicAdd(&ctr->work_ext[bounce], 64u);
+        base0 = __shfl_sync(0xffffffffu, base0, 0);
+        if (base0 >= n) break;
+#pragma unroll 1
+        for (uint32_t base = base0; base < base0 + 64u && base < n; base += 32u)
         {
-            float4 a = q.A[in][i], b = q.B[in][i];
-            if (SMEM) prim = trace_fast<false, false, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
-            else prim = trace<false, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
-            hit = prim != RT_INVALID_ID;
+            uint32_t i = base + lane;
+            bool live = i < n, hit = false;
+            float bu = 0.0f, bv = 0.0f, bt = 0.0f;
+            uint32_t prim = RT_INVALID_ID;
+            if (live)
+            {
+                float4 a = q.A[in][i], b = q.B[in][i];
+                if (SMEM) prim = trace_fast<false, false, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
+                else prim = trace<false, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
+                hit = prim != RT_INVALID_ID;
+            }
+            const unsigned hmask = __ballot_sync(0xffffffffu, hit);
+            const unsigned mmask = __ballot_sync(0xffffffffu, live && !hit);
+            unsigned long long slot = 0ull;
+            if (lane == 0)
+                slot = atomicAdd((unsigned long long*)&ctr->hm[bounce], (unsigned long long)__popc(hmask) | ((unsigned long long)__popc(mmask) << 32));
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (hit) q.hitq[(uint32_t)slot + __popc(hmask & lt_mask)] = make_float4(bu, bv, __uint_as_float(prim), __uint_as_float(i));
+            else if (live) q.missq[(uint32_t)(slot >> 32) + __popc(mmask & lt_mask)] = i;
         }
-        uint32_t hi = warp_append(&ctr->hm[bounce].hit, hit);
-        if (hit) q.hitq[hi] = make_float4(bu, bv, __uint_as_float(prim), __uint_as_float(i));
-        bool miss = live && !hit;
-        uint32_t mi = warp_append(&ctr->hm[bounce].miss, miss);
-        if (miss) q.missq[mi] = i;
     }
     if (COUNT) { warp_sum64(&ctr->nodes_ext[bounce], nv); warp_sum64(&ctr->tris_ext[bounce], nt); }
 }
@@ -1053,6 +1066,12 @@ struct rt_ctx
     Queues q = {};
     float4* radiance = nullptr;
     float4* resolved = nullptr;
+    // pipelined read-back (rt_resolve_async): second resolve buffer, copy stream, events
+    float4* resolved2 = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t resolve_done[2] = { nullptr, nullptr }, copy_done[2] = { nullptr, nullptr };
+    bool copy_pending[2] = { false, false };
+    uint32_t async_index = 0;
     // AOV + denoiser buffers (allocated on first use)
     float4* aov_albedo = nullptr; float* aov_depth = nullptr; float4* aov_normal = nullptr; float2* aov_velocity = nullptr;
     float4* prev_radiance = nullptr; float* prev_depth = nullptr;
@@ -1154,7 +1173,7 @@ int alloc_frame_buffers(rt_ctx* c)
     for (int i = 0; i < 2; ++i) { freep(c->q.A[i]); freep(c->q.B[i]); freep(c->q.C[i]); }
     freep(c->q.sA); freep(c->q.sB); freep(c->q.sC); freep(c->q.hits); freep(c->q.shadow_flags);
     freep(c->q.hitq); freep(c->q.missq);
-    freep(c->radiance); freep(c->resolved);
+    freep(c->radiance); freep(c->resolved); freep(c->resolved2);
     free_aov_buffers(c);
     c->local_rows = (c->height > c->rank) ? (c->height - c->rank + c->world - 1) / c->world : 0;
     c->n_local = c->local_rows * c->width;
@@ -1272,7 +1291,9 @@ int rt_destroy(rt_ctx* c)
     for (int i = 0; i < 2; ++i) { cudaFree(c->q.A[i]); cudaFree(c->q.B[i]); cudaFree(c->q.C[i]); }
     cudaFree(c->q.sA); cudaFree(c->q.sB); cudaFree(c->q.sC); cudaFree(c->q.hits); cudaFree(c->q.shadow_flags);
     cudaFree(c->q.hitq); cudaFree(c->q.missq);
-    cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->counters); cudaFree(c->scratch);
+    cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->resolved2); cudaFree(c->counters); cudaFree(c->scratch);
+    for (int i = 0; i < 2; ++i) { if (c->resolve_done[i]) cudaEventDestroy(c->resolve_done[i]); if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]); }
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     free_aov_buffers(c);
     for (void* p : c->scene_allocs) cudaFree(p);
     for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -1627,6 +1648,53 @@ int rt_resolve(rt_ctx* c, float* dst)
         RT_CUDA(c, cudaMemcpy2DAsync(dst + (size_t)c->rank * c->width * 4, (size_t)c->world * c->width * 16, c->resolved,
                                      (size_t)c->width * 16, (size_t)c->width * 16, c->local_rows, cudaMemcpyDeviceToHost, c->stream));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+/* Pipelined variant of rt_resolve for frame loops that do not need the image before submitting the next frame:
+ * resolves on the render stream, then copies device->host on a second stream so that the PCIe transfer of frame i
+ * overlaps the kernels of frame i+1.  Two resolve buffers alternate; the host buffer handed to call i must stay
+ * untouched until rt_resolve_wait() (or the second-next rt_resolve_async) returns. */
+int rt_resolve_async(rt_ctx* c, float* dst)
+{
+    RT_CHECK_CTX(c);
+    if (!dst) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_resolve_async: null destination");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    if (!c->copy_stream)
+    {
+        RT_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i)
+        {
+            RT_CUDA(c, cudaEventCreateWithFlags(&c->resolve_done[i], cudaEventDisableTiming));
+            RT_CUDA(c, cudaEventCreateWithFlags(&c->copy_done[i], cudaEventDisableTiming));
+        }
+    }
+    if (!c->resolved2) RT_CUDA(c, cudaMalloc(&c->resolved2, (size_t)(c->n_local ? c->n_local : 1) * 16));
+    const int k = (int)(c->async_index++ & 1u);
+    float4* buf = k ? c->resolved2 : c->resolved;
+    if (c->copy_pending[k]) RT_CUDA(c, cudaStreamWaitEvent(c->stream, c->copy_done[k], 0));   // buffer k is being re-used
+    {
+        TimedLaunch t(c, RT_K_RESOLVE);
+        AovParams ap = aov_params(c);
+        k_resolve<<<grid_for(c->n_local), 256, 0, c->stream>>>(c->radiance, buf, c->n_local, c->sample_count, c->denoiser, ap.enabled ? c->aov : 0, ap);
+        int rc = post_launch(c, "k_resolve"); if (rc) return rc;
+    }
+    RT_CUDA(c, cudaEventRecord(c->resolve_done[k], c->stream));
+    RT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->resolve_done[k], 0));
+    if (c->local_rows)
+        RT_CUDA(c, cudaMemcpy2DAsync(dst + (size_t)c->rank * c->width * 4, (size_t)c->world * c->width * 16, buf,
+                                     (size_t)c->width * 16, (size_t)c->width * 16, c->local_rows, cudaMemcpyDeviceToHost, c->copy_stream));
+    RT_CUDA(c, cudaEventRecord(c->copy_done[k], c->copy_stream));
+    c->copy_pending[k] = true;
+    return RT_OK;
+}
+
+int rt_resolve_wait(rt_ctx* c)
+{
+    RT_CHECK_CTX(c);
+    RT_CUDA(c, cudaSetDevice(c->device));
+    if (c->copy_stream) RT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    c->copy_pending[0] = c->copy_pending[1] = false;
     return RT_OK;
 }
 
