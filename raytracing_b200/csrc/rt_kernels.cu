@@ -54,8 +54,12 @@ namespace
 // ------------------------------------------------------------------------------------ device state
 struct DevCounters
 {
-    uint32_t q_count[RT_MAX_BOUNCES + 2];        // rays entering bounce b
-    uint32_t shadow_count[RT_MAX_BOUNCES + 1];
+    uint32_t n_primary;                          // rays entering bounce 0
+    uint32_t pad0;
+    // rays spawned by the shading pass of bounce b: shadow rays and continuation rays (= the rays entering bounce b+1).
+    // Adjacent + 8-byte aligned so that ONE 64-bit atomic reserves slots in both output queues.
+    struct alignas(8) Emit { uint32_t shadow, next; };
+    Emit emit[RT_MAX_BOUNCES + 1];
     struct alignas(8) HitMiss { uint32_t hit, miss; };   // adjacent + 8-byte aligned: one 64-bit atomic advances both
     HitMiss hm[RT_MAX_BOUNCES + 1];              // hit-queue entries / misses of bounce b
     uint32_t n_emissive[RT_MAX_BOUNCES + 1];
@@ -66,6 +70,11 @@ struct DevCounters
     unsigned long long nodes_ext[RT_MAX_BOUNCES + 1], tris_ext[RT_MAX_BOUNCES + 1];
     unsigned long long nodes_shadow[RT_MAX_BOUNCES + 1], tris_shadow[RT_MAX_BOUNCES + 1];
 };
+
+__host__ __device__ __forceinline__ const uint32_t* in_count_ptr(const DevCounters* c, uint32_t bounce)
+{
+    return bounce == 0 ? &c->n_primary : &c->emit[bounce - 1].next;
+}
 
 struct Queues
 {
@@ -108,20 +117,6 @@ __device__ __forceinline__ uint32_t local_index(const FrameParams& p, uint32_t p
 {
     uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
     return (p.world == 1 ? py : py / p.world) * p.width + px;
-}
-
-// warp-aggregated append: one atomic per warp, lanes get consecutive slots (coalesced stores).
-// Must be called by all 32 lanes of the warp.
-__device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred)
-{
-    unsigned mask = __ballot_sync(0xffffffffu, pred);
-    if (mask == 0) return 0;
-    int lane = threadIdx.x & 31;
-    int leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
 }
 
 __device__ __forceinline__ void warp_count(uint32_t* counter, bool pred)
@@ -457,7 +452,7 @@ __global__ void __launch_bounds__(256) k_reset(float4* radiance, uint32_t n)
 __global__ void __launch_bounds__(256) k_raygen(FrameParams p, RayGenConsts c, Queues q, DevCounters* ctr, AovParams aov)
 {
     uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li == 0) ctr->q_count[0] = p.n_local;
+    if (li == 0) ctr->n_primary = p.n_local;
     if (li >= p.n_local) return;
     uint32_t px = li % p.width, py = (li / p.width) * p.world + p.rank;
     uint32_t pixel = py * p.width + px;
@@ -480,7 +475,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(256) k_intersect(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, uint32_t bounce)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n = ctr->q_count[bounce];
+    uint32_t n = *in_count_ptr(ctr, bounce);
     int in = bounce & 1;
     uint32_t nv = 0, nt = 0;
     if (i < n)
@@ -497,7 +492,7 @@ __global__ void __launch_bounds__(256) k_intersect(FrameParams p, DevScene sc, i
 __global__ void __launch_bounds__(256) k_shade_miss(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n = ctr->q_count[bounce];
+    uint32_t n = *in_count_ptr(ctr, bounce);
     int in = bounce & 1;
     bool miss = false;
     if (i < n)
@@ -525,18 +520,29 @@ __device__ __forceinline__ void emit_rays(const FrameParams& p, Queues& q, DevCo
         radiance[li] = r;
     }
     warp_count(&ctr->n_emissive[bounce], hit && so.emissive);
-    bool ss = hit && so.spawn_shadow;
-    uint32_t si = warp_append(&ctr->shadow_count[bounce], ss);
+    // hit/miss stream compaction of the two output streams: __ballot + __popc give every lane its slot, ONE 64-bit
+    // atomic per warp reserves the slots of both queues (shadow count in the low word, continuation count in the high)
+    const bool ss = hit && so.spawn_shadow, sn = hit && so.spawn_next;
+    const unsigned smask = __ballot_sync(0xffffffffu, ss), nmask = __ballot_sync(0xffffffffu, sn);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned long long slot = 0ull;
+    if ((smask | nmask) != 0u)
+    {
+        if (lane == 0)
+            slot = atomicAdd((unsigned long long*)&ctr->emit[bounce], (unsigned long long)__popc(smask) | ((unsigned long long)__popc(nmask) << 32));
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+    }
     if (ss)
     {
+        uint32_t si = (uint32_t)slot + __popc(smask & lt_mask);
         q.sA[si] = make_float4(so.s_origin.x, so.s_origin.y, so.s_origin.z, __uint_as_float(pixel));
         q.sB[si] = make_float4(so.s_dir.x, so.s_dir.y, so.s_dir.z, so.s_tmax);
         q.sC[si] = make_float4(so.s_sample.x, so.s_sample.y, so.s_sample.z, 0.0f);
     }
-    bool sn = hit && so.spawn_next;
-    uint32_t ni = warp_append(&ctr->q_count[bounce + 1], sn);
     if (sn)
     {
+        uint32_t ni = (uint32_t)(slot >> 32) + __popc(nmask & lt_mask);
         q.A[out][ni] = make_float4(so.n_origin.x, so.n_origin.y, so.n_origin.z, __uint_as_float(pixel));
         q.B[out][ni] = make_float4(so.n_dir.x, so.n_dir.y, so.n_dir.z, RT_MAX_RENDER_DIST);
         q.C[out][ni] = make_float4(so.n_throughput.x, so.n_throughput.y, so.n_throughput.z, 0.0f);
@@ -547,7 +553,7 @@ __device__ __forceinline__ void emit_rays(const FrameParams& p, Queues& q, DevCo
 __global__ void __launch_bounds__(256) k_shade_hits(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce, AovParams aov)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n = ctr->q_count[bounce];
+    uint32_t n = *in_count_ptr(ctr, bounce);
     int in = bounce & 1;
     bool hit = false;
     uint32_t pixel = 0;
@@ -573,7 +579,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(256) k_intersect_shadow(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, uint32_t bounce)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n = ctr->shadow_count[bounce];
+    uint32_t n = ctr->emit[bounce].shadow;
     uint32_t nv = 0, nt = 0;
     if (i < n)
     {
@@ -588,7 +594,7 @@ __global__ void __launch_bounds__(256) k_intersect_shadow(FrameParams p, DevScen
 __global__ void __launch_bounds__(256) k_accumulate(FrameParams p, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n = ctr->shadow_count[bounce];
+    uint32_t n = ctr->emit[bounce].shadow;
     bool un = false;
     if (i < n)
     {
@@ -613,7 +619,7 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams p, Queues q, Dev
 template <bool COUNT>
 __global__ void __launch_bounds__(256) k_extend_shade(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce, AovParams aov)
 {
-    const uint32_t n = ctr->q_count[bounce];
+    const uint32_t n = *in_count_ptr(ctr, bounce);
     const int in = bounce & 1;
     const int lane = threadIdx.x & 31;
     uint32_t nv = 0, nt = 0;
@@ -652,15 +658,16 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameP
     extern __shared__ __align__(128) float4 s_bvh[];
     __shared__ uint64_t s_mbar;
     if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
-    const uint32_t n = ctr->shadow_count[bounce];
+    const uint32_t n = ctr->emit[bounce].shadow;
     const int lane = threadIdx.x & 31;
     uint32_t nv = 0, nt = 0;
+    uint32_t pending = 0;
+    if (lane == 0) pending = atomicAdd(&ctr->work_shadow[bounce], 32u);
     for (;;)
     {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->work_shadow[bounce], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t base = __shfl_sync(0xffffffffu, pending, 0);
         if (base >= n) break;
+        if (lane == 0) pending = atomicAdd(&ctr->work_shadow[bounce], 32u);      // next round's grab, latency hidden
       {
         uint32_t i = base + lane;
         bool un = false;
@@ -699,18 +706,20 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_closest(FrameParam
     extern __shared__ __align__(128) float4 s_bvh[];
     __shared__ uint64_t s_mbar;
     if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
-    const uint32_t n = ctr->q_count[bounce];
+    const uint32_t n = *in_count_ptr(ctr, bounce);
     const int in = bounce & 1;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t nv = 0, nt = 0;
+    // 32 rays per cursor grab (64 per grab measured slower: coarser tail).  The grab for the NEXT round is issued before
+    // this round's traversal, so the ~700-cycle round trip of the atomic is hidden behind it.
+    uint32_t pending = 0;
+    if (lane == 0) pending = atomicAdd(&ctr->work_ext[bounce], 32u);
     for (;;)
     {
-        // 32 rays per cursor grab (64 per grab measured slower: coarser tail), one 64-bit atomic for BOTH queue appends
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->work_ext[bounce], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t base = __shfl_sync(0xffffffffu, pending, 0);
         if (base >= n) break;
+        if (lane == 0) pending = atomicAdd(&ctr->work_ext[bounce], 32u);
         {
             uint32_t i = base + lane;
             bool live = i < n, hit = false;
@@ -751,7 +760,7 @@ template <bool ANY>
 __global__ void __launch_bounds__(256) k_trace_refill(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance,
                                                       uint32_t bounce, int refill_min)
 {
-    const uint32_t n = ANY ? ctr->shadow_count[bounce] : ctr->q_count[bounce];
+    const uint32_t n = ANY ? ctr->emit[bounce].shadow : *in_count_ptr(ctr, bounce);
     uint32_t* cursor = ANY ? &ctr->work_shadow[bounce] : &ctr->work_ext[bounce];
     const float4* __restrict__ A = ANY ? q.sA : q.A[bounce & 1];
     const float4* __restrict__ B = ANY ? q.sB : q.B[bounce & 1];
@@ -952,12 +961,13 @@ __global__ void __launch_bounds__(256, RT_MINB_SHADE) k_shade_queues(FrameParams
     const uint32_t total = hit_span + n_miss;
     const int in = bounce & 1;
     const int lane = threadIdx.x & 31;
+    uint32_t pending = 0;
+    if (lane == 0) pending = atomicAdd(&ctr->work_shade[bounce], 32u);
     for (;;)
     {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->work_shade[bounce], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t base = __shfl_sync(0xffffffffu, pending, 0);
         if (base >= total) break;
+        if (lane == 0) pending = atomicAdd(&ctr->work_shade[bounce], 32u);       // next round's grab, latency hidden
         if (base < hit_span)
         {
             uint32_t k = base + lane;
@@ -1718,7 +1728,7 @@ int rt_read_hits(rt_ctx* c, uint32_t bounce, RtHit* hits, uint32_t* pixels, uint
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     uint32_t n = 0;
-    RT_CUDA(c, cudaMemcpy(&n, &c->counters->q_count[bounce], 4, cudaMemcpyDeviceToHost));
+    RT_CUDA(c, cudaMemcpy(&n, in_count_ptr(c->counters, bounce), 4, cudaMemcpyDeviceToHost));
     *n_out = n;
     if (hits && n) RT_CUDA(c, cudaMemcpy(hits, c->q.hits, (size_t)n * 16, cudaMemcpyDeviceToHost));   // same 16-byte layout as RtHit
     if (pixels && n)
@@ -1738,12 +1748,12 @@ int rt_read_rays(rt_ctx* c, uint32_t bounce, RtRay* rays, uint32_t* pixels, uint
     int rc = ensure_scratch(c, (size_t)c->n_local * (sizeof(RtRay) + 4) + 64); if (rc) return rc;
     RtRay* drays = (RtRay*)c->scratch;
     uint32_t* dpix = (uint32_t*)((char*)c->scratch + (size_t)c->n_local * sizeof(RtRay));
-    k_unpack_rays<<<grid_for(c->n_local), 256, 0, c->stream>>>(c->q.A[bounce & 1], c->q.B[bounce & 1], &c->counters->q_count[bounce], c->width, drays, dpix);
+    k_unpack_rays<<<grid_for(c->n_local), 256, 0, c->stream>>>(c->q.A[bounce & 1], c->q.B[bounce & 1], in_count_ptr(c->counters, bounce), c->width, drays, dpix);
     ++c->launches;
     if ((rc = post_launch(c, "k_unpack_rays"))) return rc;
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     uint32_t n = 0;
-    RT_CUDA(c, cudaMemcpy(&n, &c->counters->q_count[bounce], 4, cudaMemcpyDeviceToHost));
+    RT_CUDA(c, cudaMemcpy(&n, in_count_ptr(c->counters, bounce), 4, cudaMemcpyDeviceToHost));
     *n_out = n;
     if (n)
     {
@@ -1776,8 +1786,8 @@ int rt_read_frame_stats(rt_ctx* c, RtFrameStats* out)
     memset(out, 0, sizeof(*out));
     for (uint32_t b = 0; b <= RT_MAX_BOUNCES; ++b)
     {
-        out->n_ext[b] = h.q_count[b]; out->n_miss[b] = h.hm[b].miss; out->n_emissive_hits[b] = h.n_emissive[b];
-        out->n_shadow[b] = h.shadow_count[b]; out->n_cont[b] = h.q_count[b + 1]; out->n_unoccluded[b] = h.n_unoccluded[b];
+        out->n_ext[b] = (b == 0) ? h.n_primary : h.emit[b - 1].next; out->n_miss[b] = h.hm[b].miss; out->n_emissive_hits[b] = h.n_emissive[b];
+        out->n_shadow[b] = h.emit[b].shadow; out->n_cont[b] = h.emit[b].next; out->n_unoccluded[b] = h.n_unoccluded[b];
         out->nodes_ext[b] = h.nodes_ext[b]; out->tris_ext[b] = h.tris_ext[b];
         out->nodes_shadow[b] = h.nodes_shadow[b]; out->tris_shadow[b] = h.tris_shadow[b];
     }
