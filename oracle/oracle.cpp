@@ -557,6 +557,14 @@ void orc_sample_sky(const OrcScene* scene, const float* dirs, uint32_t n, float*
  * Compaction is a deterministic in-order scan (the reference uses atomic appends; the
  * per-pixel results do not depend on ray order).
  */
+/* Analysis hook (profiling studies only): when set, orc_render copies the rays entering bounce g_dump_bounce and their
+ * per-ray traversal work (nodes visited, triangles tested) into the caller's arrays. */
+static int g_dump_bounce = -1;
+static RtRay* g_dump_rays = nullptr;
+static uint32_t* g_dump_work = nullptr;   /* 2 per ray */
+static uint32_t* g_dump_count = nullptr;
+void orc_set_dump(int bounce, RtRay* rays, uint32_t* work, uint32_t* count) { g_dump_bounce = bounce; g_dump_rays = rays; g_dump_work = work; g_dump_count = count; }
+
 void orc_render(const OrcScene* scene, const RtCamera* cam, uint32_t width, uint32_t height,
                 uint32_t max_bounces, uint32_t sample_idx, int white_furnace,
                 uint32_t row_first, uint32_t row_step,
@@ -597,6 +605,13 @@ void orc_render(const OrcScene* scene, const RtCamera* cam, uint32_t width, uint
             const Ray& ray = rays[i];
             TraceBvh(sc, ray, false, &hit, &c);
             nv += c.nodes_visited; nt += c.tris_tested;
+            if ((int)bounce == g_dump_bounce && g_dump_rays)
+            {
+                g_dump_rays[i].origin = RtFloat3{ ray.o.x, ray.o.y, ray.o.z, 0.0f };
+                g_dump_rays[i].direction = RtFloat3{ ray.d.x, ray.d.y, ray.d.z, ray.tmax };
+                g_dump_work[2 * i] = (uint32_t)c.nodes_visited; g_dump_work[2 * i + 1] = (uint32_t)c.tris_tested;
+                if (i == 0) *g_dump_count = (uint32_t)n_live;
+            }
             hits[i] = hit;
             uint32_t pixel = pix[i];
             float* rad = radiance + (size_t)pixel * 4;
