@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traversal", type=int, default=None, help="RT_OPT_TRAVERSAL override (0 literal, 1 fast, 2 per-lane refill)")
     ap.add_argument("--refill-min", type=int, default=None, help="RT_OPT_REFILL_MIN override")
+    ap.add_argument("--no-overlap", action="store_true", help="RT_OPT_OVERLAP=0: shadow pass on the render stream (no concurrency with the next traversal)")
     ap.add_argument("--no-smem-bvh", action="store_true", help="RT_OPT_SMEM_BVH=0: fetch BVH records through L1 even for small scenes")
     ap.add_argument("--copies", type=int, default=183, help="Synthetic10M: number of ShaderBalls copies (183 = 10 026 570 triangles)")
     args = ap.parse_args()
@@ -224,6 +225,8 @@ def main():
         ctx.set_option(capi.OPT_FUSION, 1)
     if args.traversal is not None:
         ctx.set_option(capi.OPT_TRAVERSAL, args.traversal)
+    if args.no_overlap:
+        ctx.set_option(capi.OPT_OVERLAP, 0)
     if args.no_smem_bvh:
         ctx.set_option(capi.OPT_SMEM_BVH, 0)
     if args.refill_min is not None:

@@ -1070,6 +1070,11 @@ struct rt_ctx
     Queues q = {};
     float4* radiance = nullptr;
     float4* resolved = nullptr;
+    // shadow pass on a second stream (RT_OPT_OVERLAP): k_shadow_accumulate(b) runs concurrently with k_trace_closest(b+1)
+    int overlap = 1;
+    cudaStream_t shadow_stream = nullptr;
+    cudaEvent_t ev_shaded = nullptr, ev_shadowed = nullptr;
+    bool shadow_pending = false;
     // pipelined read-back (rt_resolve_async): second resolve buffer, copy stream, events
     float4* resolved2 = nullptr;
     cudaStream_t copy_stream = nullptr;
@@ -1128,24 +1133,36 @@ namespace
 
 struct TimedLaunch
 {
-    rt_ctx* c; int cls; cudaEvent_t a = nullptr, b = nullptr;
-    TimedLaunch(rt_ctx* ctx, int k) : c(ctx), cls(k)
+    rt_ctx* c; int cls; cudaEvent_t a = nullptr, b = nullptr; cudaStream_t st;
+    TimedLaunch(rt_ctx* ctx, int k, cudaStream_t stream = nullptr) : c(ctx), cls(k), st(stream ? stream : ctx->stream)
     {
         ++c->launches;
         if (!c->kernel_timing) return;
         auto get = [&]() { cudaEvent_t e; if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
         a = get(); b = get();
-        cudaEventRecord(a, c->stream);
+        cudaEventRecord(a, st);
     }
     ~TimedLaunch()
     {
         if (!a) return;
-        cudaEventRecord(b, c->stream);
+        cudaEventRecord(b, st);
         c->timed.push_back({ a, b, cls });
     }
 };
 
 inline dim3 grid_for(uint32_t n, uint32_t block = 256) { return dim3((n + block - 1) / block); }
+
+// Work submitted to the shadow stream must be ordered before anything on the render stream that touches the radiance
+// buffer, the shadow queue or the counters again.
+int join_shadow(rt_ctx* c)
+{
+    if (c->shadow_pending)
+    {
+        RT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_shadowed, 0));
+        c->shadow_pending = false;
+    }
+    return RT_OK;
+}
 
 int post_launch(rt_ctx* c, const char* what)
 {
@@ -1173,6 +1190,9 @@ void free_aov_buffers(rt_ctx* c);
 
 int alloc_frame_buffers(rt_ctx* c)
 {
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->shadow_stream) cudaStreamSynchronize(c->shadow_stream);
+    c->shadow_pending = false;
     auto freep = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     for (int i = 0; i < 2; ++i) { freep(c->q.A[i]); freep(c->q.B[i]); freep(c->q.C[i]); }
     freep(c->q.sA); freep(c->q.sB); freep(c->q.sC); freep(c->q.hits); freep(c->q.shadow_flags);
@@ -1292,10 +1312,14 @@ int rt_destroy(rt_ctx* c)
     if (!c) return RT_ERR_INVALID_ARGUMENT;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->shadow_stream) cudaStreamSynchronize(c->shadow_stream);
     for (int i = 0; i < 2; ++i) { cudaFree(c->q.A[i]); cudaFree(c->q.B[i]); cudaFree(c->q.C[i]); }
     cudaFree(c->q.sA); cudaFree(c->q.sB); cudaFree(c->q.sC); cudaFree(c->q.hits); cudaFree(c->q.shadow_flags);
     cudaFree(c->q.hitq); cudaFree(c->q.missq);
     cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->resolved2); cudaFree(c->counters); cudaFree(c->scratch);
+    if (c->shadow_stream) { cudaStreamSynchronize(c->shadow_stream); cudaStreamDestroy(c->shadow_stream); }
+    if (c->ev_shaded) cudaEventDestroy(c->ev_shaded);
+    if (c->ev_shadowed) cudaEventDestroy(c->ev_shadowed);
     for (int i = 0; i < 2; ++i) { if (c->resolve_done[i]) cudaEventDestroy(c->resolve_done[i]); if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]); }
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     free_aov_buffers(c);
@@ -1451,6 +1475,7 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
     case RT_OPT_COUNT_TRAVERSAL: c->count_traversal = value != 0; return RT_OK;
     case RT_OPT_KERNEL_TIMING: c->kernel_timing = value != 0; return RT_OK;
     case RT_OPT_SMEM_BVH: c->smem_bvh = value != 0; return RT_OK;
+    case RT_OPT_OVERLAP: { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; c->overlap = value != 0; return RT_OK; }
     case RT_OPT_FUSION:
         if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "fusion mode must be 0 or 1");
         c->fusion = (int)value; return RT_OK;
@@ -1467,6 +1492,7 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
 int rt_reset(rt_ctx* c)
 {
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     RT_CUDA(c, cudaSetDevice(c->device));
     if (!c->denoiser) c->sample_count = 0;                                   // cl_pt_integrator.cpp:499-504
     TimedLaunch t(c, RT_K_MISC);
@@ -1479,6 +1505,7 @@ int rt_advance_sample_count(rt_ctx* c) { RT_CHECK_CTX(c); ++c->sample_count; ret
 int rt_generate_rays(rt_ctx* c)
 {
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     int rc = require_ready(c); if (rc) return rc;
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(DevCounters), c->stream));
@@ -1498,7 +1525,8 @@ int rt_generate_rays(rt_ctx* c)
 
 int rt_intersect(rt_ctx* c, uint32_t bounce)
 {
-    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
+    RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; } RT_BOUNCE_CHECK(c, bounce);
     TimedLaunch t(c, RT_K_INTERSECT);
     if (c->count_traversal) k_intersect<true><<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
     else k_intersect<false><<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
@@ -1518,7 +1546,8 @@ int rt_compute_aovs(rt_ctx* c)
 
 int rt_shade_miss(rt_ctx* c, uint32_t bounce)
 {
-    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
+    RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; } RT_BOUNCE_CHECK(c, bounce);
     TimedLaunch t(c, RT_K_MISS);
     k_shade_miss<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce);
     return post_launch(c, "k_shade_miss");
@@ -1529,7 +1558,8 @@ int rt_clear_shadow_counter(rt_ctx* c) { RT_CHECK_CTX(c); return RT_OK; }
 
 int rt_shade_hits(rt_ctx* c, uint32_t bounce)
 {
-    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
+    RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; } RT_BOUNCE_CHECK(c, bounce);
     c->cur_bounce = bounce;
     TimedLaunch t(c, RT_K_HIT);
     k_shade_hits<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, aov_params(c));
@@ -1538,7 +1568,8 @@ int rt_shade_hits(rt_ctx* c, uint32_t bounce)
 
 int rt_intersect_shadow(rt_ctx* c)
 {
-    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, c->cur_bounce);
+    RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; } RT_BOUNCE_CHECK(c, c->cur_bounce);
     TimedLaunch t(c, RT_K_INTERSECT_SHADOW);
     if (c->count_traversal) k_intersect_shadow<true><<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->cur_bounce);
     else k_intersect_shadow<false><<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->cur_bounce);
@@ -1547,7 +1578,8 @@ int rt_intersect_shadow(rt_ctx* c)
 
 int rt_accumulate_direct(rt_ctx* c)
 {
-    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, c->cur_bounce);
+    RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; } RT_BOUNCE_CHECK(c, c->cur_bounce);
     TimedLaunch t(c, RT_K_ACCUMULATE);
     k_accumulate<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->q, c->counters, c->radiance, c->cur_bounce);
     return post_launch(c, "k_accumulate");
@@ -1556,6 +1588,7 @@ int rt_accumulate_direct(rt_ctx* c)
 int rt_denoise(rt_ctx* c)
 {
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!c->denoiser) return RT_OK;
     if (c->world != 1) RT_FAIL(c, RT_ERR_UNSUPPORTED, "temporal denoiser is single-GPU only");
     RT_CUDA(c, cudaSetDevice(c->device));
@@ -1568,6 +1601,7 @@ int rt_denoise(rt_ctx* c)
 int rt_copy_history(rt_ctx* c)
 {   // cl_pt_integrator.cpp:670-675
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!c->denoiser) return RT_OK;
     RT_CUDA(c, cudaSetDevice(c->device));
     int rc = ensure_aov_buffers(c); if (rc) return rc;
@@ -1583,6 +1617,7 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
     int grid = persistent_grid(c);
     if (c->fusion == 1)
     {   // monolithic variant: trace + miss + shade in one kernel
+        { int rc = join_shadow(c); if (rc) return rc; }
         TimedLaunch t(c, RT_K_EXTEND_SHADE);
         if (c->count_traversal) k_extend_shade<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce, aov_params(c));
         else k_extend_shade<false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce, aov_params(c));
@@ -1603,6 +1638,7 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
         else k_trace_closest<false, false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
         int rc = post_launch(c, "k_trace_closest"); if (rc) return rc;
     }
+    { int rc = join_shadow(c); if (rc) return rc; }     // the shading pass accumulates into radiance and refills the shadow queue
     TimedLaunch t(c, RT_K_SHADE_QUEUES);
     k_shade_queues<<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, aov_params(c));
     return post_launch(c, "k_shade_queues");
@@ -1611,18 +1647,40 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
 int rt_shadow_accumulate(rt_ctx* c, uint32_t bounce)
 {
     RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
-    TimedLaunch t(c, RT_K_SHADOW_ACCUMULATE);
-    int grid = persistent_grid(c);
-    if (c->traversal == 2 && !c->count_traversal)
+    int rc = join_shadow(c); if (rc) return rc;
+    // The shadow pass of bounce b only shares the radiance buffer with LATER shading passes, so it is submitted to a second
+    // stream and overlaps the closest-hit traversal of bounce b+1 (which touches neither); join_shadow() orders it before
+    // the next kernel that needs its results.  Both kernels are persistent, so the second fills the SMs as the first drains.
+    cudaStream_t st = c->stream;
+    if (c->overlap)
     {
-        k_trace_refill<true><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, c->refill_min);
-        return post_launch(c, "k_trace_refill<any>");
+        if (!c->shadow_stream)
+        {
+            RT_CUDA(c, cudaStreamCreateWithFlags(&c->shadow_stream, cudaStreamNonBlocking));
+            RT_CUDA(c, cudaEventCreateWithFlags(&c->ev_shaded, cudaEventDisableTiming));
+            RT_CUDA(c, cudaEventCreateWithFlags(&c->ev_shadowed, cudaEventDisableTiming));
+        }
+        st = c->shadow_stream;
+        RT_CUDA(c, cudaEventRecord(c->ev_shaded, c->stream));
+        RT_CUDA(c, cudaStreamWaitEvent(st, c->ev_shaded, 0));
     }
-    size_t stage = smem_stage_bytes(c);
-    if (c->count_traversal) k_shadow_accumulate<true, false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-    else if (stage) k_shadow_accumulate<false, true><<<grid, 256, stage, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-    else k_shadow_accumulate<false, false><<<grid, 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-    return post_launch(c, "k_shadow_accumulate");
+    {
+        TimedLaunch t(c, RT_K_SHADOW_ACCUMULATE, st);
+        int grid = persistent_grid(c);
+        size_t stage = smem_stage_bytes(c);
+        if (c->traversal == 2 && !c->count_traversal)
+            k_trace_refill<true><<<grid, 256, 0, st>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, c->refill_min);
+        else if (c->count_traversal) k_shadow_accumulate<true, false><<<grid, 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+        else if (stage) k_shadow_accumulate<false, true><<<grid, 256, stage, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+        else k_shadow_accumulate<false, false><<<grid, 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+        rc = post_launch(c, "k_shadow_accumulate"); if (rc) return rc;
+    }
+    if (c->overlap)
+    {
+        RT_CUDA(c, cudaEventRecord(c->ev_shadowed, st));
+        c->shadow_pending = true;
+    }
+    return RT_OK;
 }
 
 int rt_integrate(rt_ctx* c, uint32_t max_bounces)
@@ -1641,6 +1699,7 @@ int rt_integrate(rt_ctx* c, uint32_t max_bounces)
 int rt_resolve(rt_ctx* c, float* dst)
 {
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     RT_CUDA(c, cudaSetDevice(c->device));
     {
         TimedLaunch t(c, RT_K_RESOLVE);
@@ -1662,6 +1721,7 @@ int rt_resolve(rt_ctx* c, float* dst)
 int rt_resolve_async(rt_ctx* c, float* dst)
 {
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!dst) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_resolve_async: null destination");
     RT_CUDA(c, cudaSetDevice(c->device));
     if (!c->copy_stream)
@@ -1705,6 +1765,7 @@ int rt_resolve_wait(rt_ctx* c)
 int rt_sync(rt_ctx* c)
 {
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     return RT_OK;
@@ -1722,6 +1783,7 @@ static int ensure_scratch(rt_ctx* c, size_t bytes)
 int rt_read_hits(rt_ctx* c, uint32_t bounce, RtHit* hits, uint32_t* pixels, uint32_t* n_out)
 {
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (bounce > RT_MAX_BOUNCES || !n_out) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_hits: bad arguments");
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1741,6 +1803,7 @@ int rt_read_hits(rt_ctx* c, uint32_t bounce, RtHit* hits, uint32_t* pixels, uint
 int rt_read_rays(rt_ctx* c, uint32_t bounce, RtRay* rays, uint32_t* pixels, uint32_t* n_out)
 {
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (bounce > RT_MAX_BOUNCES || !n_out || !rays || !pixels) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_rays: bad arguments");
     RT_CUDA(c, cudaSetDevice(c->device));
     int rc = ensure_scratch(c, (size_t)c->n_local * (sizeof(RtRay) + 4) + 64); if (rc) return rc;
@@ -1764,6 +1827,7 @@ int rt_read_rays(rt_ctx* c, uint32_t bounce, RtRay* rays, uint32_t* pixels, uint
 int rt_read_radiance(rt_ctx* c, float* dst)
 {
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!dst) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_radiance: null destination");
     RT_CUDA(c, cudaSetDevice(c->device));
     if (c->local_rows)
@@ -1776,6 +1840,7 @@ int rt_read_radiance(rt_ctx* c, float* dst)
 int rt_read_frame_stats(rt_ctx* c, RtFrameStats* out)
 {
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!out) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_frame_stats: null destination");
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1797,6 +1862,7 @@ int rt_read_sample_count(rt_ctx* c, uint32_t* out) { RT_CHECK_CTX(c); if (!out) 
 int rt_read_aovs(rt_ctx* c, float* albedo, float* depth, float* normal, float* velocity)
 {
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!c->aov_albedo) RT_FAIL(c, RT_ERR_NOT_READY, "AOV buffers do not exist: select an AOV view, enable the denoiser or set RT_OPT_AOV_ALWAYS first");
     RT_CUDA(c, cudaSetDevice(c->device));
     auto rows = [&](void* dst, const void* src, size_t elem) -> int {
@@ -1814,6 +1880,7 @@ int rt_read_aovs(rt_ctx* c, float* albedo, float* depth, float* normal, float* v
 int rt_kernel_times(rt_ctx* c, float* ms, uint32_t* launches)
 {
     RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     for (auto& t : c->timed)
