@@ -292,10 +292,24 @@ def main():
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms_total[0]) / args.steps
-    ktimes = ctx.kernel_times()
-    ctx.set_option(capi.OPT_KERNEL_TIMING, 0)
+    ktimes_overlapped = ctx.kernel_times()
     launches = ctx.launch_count() - launches0
     sampler.join(timeout=2)
+    # Per-kernel durations for the roofline: with the shadow pass overlapping the next traversal on a second stream
+    # (RT_OPT_OVERLAP), the CUDA-event duration of one kernel includes the time it shares the SMs with the other, so
+    # the same K steps are run once more, in this same process, with the overlap off and the events on.
+    ctx.set_option(capi.OPT_OVERLAP, 0)
+    for _ in range(2):
+        frame()
+    barrier()
+    ctx.kernel_times()
+    for _ in range(args.steps):
+        frame()
+    barrier()
+    ktimes = ctx.kernel_times()
+    ctx.set_option(capi.OPT_KERNEL_TIMING, 0)
+    if not args.no_overlap:
+        ctx.set_option(capi.OPT_OVERLAP, 1)
     value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
 
     # ---- end to end through the public API with HOST buffers: camera H2D, frame, gather, resolve, image D2H
@@ -377,6 +391,10 @@ def main():
                          "kernel_ms_per_step": dom_ms / args.steps, "kernel_launches_per_step": dom_n / args.steps,
                          "whole_frame_algorithmic_GBs": alg_total / (ms_per_step * 1e-3) / 1e9},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
+            "kernel_ms_per_step_in_timed_region": {k: v[0] / args.steps for k, v in ktimes_overlapped.items() if v[1]},
+            "kernel_timing_note": "kernel_ms_per_step: CUDA events per launch over K extra steps with the two-stream overlap disabled (clean "
+                                  "per-kernel durations, used for the roofline); ..._in_timed_region: the same events inside the timed region, where "
+                                  "k_shadow_accumulate(b) and k_trace_closest(b+1) run concurrently and their durations include each other",
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:

@@ -1500,7 +1500,13 @@ int rt_reset(rt_ctx* c)
     return post_launch(c, "k_reset");
 }
 
-int rt_advance_sample_count(rt_ctx* c) { RT_CHECK_CTX(c); ++c->sample_count; return RT_OK; }
+int rt_advance_sample_count(rt_ctx* c)
+{
+    RT_CHECK_CTX(c);
+    int rc = join_shadow(c); if (rc) return rc;     // end of the bounce loop: everything of this frame is ordered on the render stream
+    ++c->sample_count;
+    return RT_OK;
+}
 
 int rt_generate_rays(rt_ctx* c)
 {
@@ -1693,7 +1699,7 @@ int rt_integrate(rt_ctx* c, uint32_t max_bounces)
         if ((rc = rt_extend_shade(c, b))) return rc;
         if ((rc = rt_shadow_accumulate(c, b))) return rc;
     }
-    return rt_advance_sample_count(c);
+    return rt_advance_sample_count(c);      // joins the shadow stream: the frame is complete in render-stream order
 }
 
 int rt_resolve(rt_ctx* c, float* dst)
