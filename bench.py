@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traversal", type=int, default=None, help="RT_OPT_TRAVERSAL override (0 literal, 1 fast, 2 per-lane refill)")
     ap.add_argument("--refill-min", type=int, default=None, help="RT_OPT_REFILL_MIN override")
+    ap.add_argument("--no-graph", action="store_true", help="RT_OPT_GRAPH=0: launch every kernel of the frame individually")
     ap.add_argument("--no-overlap", action="store_true", help="RT_OPT_OVERLAP=0: shadow pass on the render stream (no concurrency with the next traversal)")
     ap.add_argument("--no-smem-bvh", action="store_true", help="RT_OPT_SMEM_BVH=0: fetch BVH records through L1 even for small scenes")
     ap.add_argument("--copies", type=int, default=183, help="Synthetic10M: number of ShaderBalls copies (183 = 10 026 570 triangles)")
@@ -225,6 +226,8 @@ def main():
         ctx.set_option(capi.OPT_FUSION, 1)
     if args.traversal is not None:
         ctx.set_option(capi.OPT_TRAVERSAL, args.traversal)
+    if args.no_graph:
+        ctx.set_option(capi.OPT_GRAPH, 0)
     if args.no_overlap:
         ctx.set_option(capi.OPT_OVERLAP, 0)
     if args.no_smem_bvh:
@@ -277,8 +280,6 @@ def main():
         frame()
     barrier()
     launches0 = ctx.launch_count()
-    ctx.set_option(capi.OPT_KERNEL_TIMING, 1)
-    ctx.kernel_times()
     sampler = ClockSampler(local_rank); sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -292,12 +293,13 @@ def main():
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms_total[0]) / args.steps
-    ktimes_overlapped = ctx.kernel_times()
     launches = ctx.launch_count() - launches0
     sampler.join(timeout=2)
-    # Per-kernel durations for the roofline: with the shadow pass overlapping the next traversal on a second stream
-    # (RT_OPT_OVERLAP), the CUDA-event duration of one kernel includes the time it shares the SMs with the other, so
-    # the same K steps are run once more, in this same process, with the overlap off and the events on.
+    # Per-kernel durations for the roofline.  In the timed region above the frame is ONE CUDA-graph launch and the shadow
+    # pass overlaps the next traversal on a second stream, so per-launch CUDA events are neither possible (graph) nor clean
+    # (concurrent kernels' durations include each other): the same K steps are run once more, in this same process, with
+    # per-launch events on, individual launches and the overlap off.
+    ctx.set_option(capi.OPT_KERNEL_TIMING, 1)
     ctx.set_option(capi.OPT_OVERLAP, 0)
     for _ in range(2):
         frame()
@@ -391,10 +393,8 @@ def main():
                          "kernel_ms_per_step": dom_ms / args.steps, "kernel_launches_per_step": dom_n / args.steps,
                          "whole_frame_algorithmic_GBs": alg_total / (ms_per_step * 1e-3) / 1e9},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
-            "kernel_ms_per_step_in_timed_region": {k: v[0] / args.steps for k, v in ktimes_overlapped.items() if v[1]},
-            "kernel_timing_note": "kernel_ms_per_step: CUDA events per launch over K extra steps with the two-stream overlap disabled (clean "
-                                  "per-kernel durations, used for the roofline); ..._in_timed_region: the same events inside the timed region, where "
-                                  "k_shadow_accumulate(b) and k_trace_closest(b+1) run concurrently and their durations include each other",
+            "kernel_timing_note": "kernel_ms_per_step: CUDA events per launch over K extra steps of this run with individual launches and the "
+                                  "two-stream overlap disabled (in the timed region the frame is one CUDA-graph launch with two concurrent streams)",
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:

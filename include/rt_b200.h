@@ -76,6 +76,8 @@ typedef enum RtOption {
                                    bulk copy at the start of every traversal kernel; 0: always fetch through L1 */
     RT_OPT_OVERLAP = 23,        /* 1 (default): rt_shadow_accumulate(b) runs on a second stream and overlaps the closest-hit traversal
                                    of bounce b+1; 0: everything on one in-order stream */
+    RT_OPT_GRAPH = 24,          /* 1 (default): rt_integrate replays the frame as one CUDA graph (captured on first use, re-captured when an
+                                   option, the scene or the partition changes; the camera and sample index are a node-parameter update) */
     RT_OPT_REFILL_MIN = 20,     /* traversal mode 2: refill a warp when at least this many lanes are idle (1..32) */
     RT_OPT_FUSION = 19          /* rt_extend_shade: 0 = traversal kernel + hit/miss queue compaction + shading kernel
                                    (default), 1 = one monolithic kernel; results are bit-identical */

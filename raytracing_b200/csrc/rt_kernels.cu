@@ -86,10 +86,16 @@ struct Queues
     uint32_t* missq;
 };
 
+// Per-frame constants that change from frame to frame (sample index, camera): kept in a small device buffer that a
+// 1-thread kernel refreshes at the start of every frame, so that the rest of the frame's launches have frame-invariant
+// arguments and the whole frame can be replayed as ONE CUDA graph (rt_integrate) with a single node-parameter update.
+struct FrameDyn;
+
 struct FrameParams
 {
-    uint32_t width, height, rank, world, n_local, sample_idx;
+    uint32_t width, height, rank, world, n_local;
     int white_furnace;
+    const FrameDyn* dyn;
 };
 
 // AOV outputs of bounce 0 (kernels/cl/aov.cl:44-110), written by the bounce-0 shading pass when enabled
@@ -97,9 +103,17 @@ struct AovCam { f3 position, front, up, right; float angle, aspect_ratio; };
 struct AovParams
 {
     int enabled;
-    AovCam cam, prev;
     float4* albedo; float* depth; float4* normal; float2* velocity;
 };
+
+struct FrameDyn
+{
+    uint32_t sample_idx, pad[3];
+    RayGenConsts raygen;
+    AovCam cam, prev;
+};
+
+__global__ void k_set_frame(FrameDyn* dst, FrameDyn value) { *dst = value; }
 
 // kernels/cl/aov.cl:30-42
 __device__ __forceinline__ f2 project_screen(f3 position, const AovCam& c)
@@ -405,7 +419,7 @@ __device__ __forceinline__ void shade_hit(const DevScene& sc, const FrameParams&
         aov.albedo[li] = make_float4(material.diffuse_albedo.x, material.diffuse_albedo.y, material.diffuse_albedo.z, 0.0f);
         aov.depth[li] = length(ray_origin - position);
         aov.normal[li] = make_float4(normal.x, normal.y, normal.z, 0.0f);
-        f2 s0 = project_screen(position, aov.cam), s1 = project_screen(position, aov.prev);
+        f2 s0 = project_screen(position, p.dyn->cam), s1 = project_screen(position, p.dyn->prev);
         aov.velocity[li] = make_float2(s0.x - s1.x, s0.y - s1.y);
     }
 
@@ -415,7 +429,7 @@ __device__ __forceinline__ void shade_hit(const DevScene& sc, const FrameParams&
         out.emissive = true;
         out.emission_add = hit_throughput * material.emission;
     }
-    uint32_t pixel_seed = sample_seed_pixel(px, py, p.sample_idx);
+    uint32_t pixel_seed = sample_seed_pixel(px, py, p.dyn->sample_idx);
     {   // direct lighting (next-event estimation on analytic lights)
         float s_light = sample_random(pixel_seed, bounce, SAMPLE_LIGHT);
         f3 outgoing; float pdf, distance_to_light;
@@ -449,7 +463,7 @@ __global__ void __launch_bounds__(256) k_reset(float4* radiance, uint32_t n)
 }
 
 // raygeneration.cl:65-139.  One thread per LOCAL pixel; slot i of queue 0 = local pixel i.
-__global__ void __launch_bounds__(256) k_raygen(FrameParams p, RayGenConsts c, Queues q, DevCounters* ctr, AovParams aov)
+__global__ void __launch_bounds__(256) k_raygen(FrameParams p, Queues q, DevCounters* ctr, AovParams aov)
 {
     uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li == 0) ctr->n_primary = p.n_local;
@@ -457,7 +471,7 @@ __global__ void __launch_bounds__(256) k_raygen(FrameParams p, RayGenConsts c, Q
     uint32_t px = li % p.width, py = (li / p.width) * p.world + p.rank;
     uint32_t pixel = py * p.width + px;
     f3 o, d;
-    generate_primary_ray(c, pixel, px, py, p.sample_idx, o, d);
+    generate_primary_ray(p.dyn->raygen, pixel, px, py, p.dyn->sample_idx, o, d);
     q.A[0][li] = make_float4(o.x, o.y, o.z, __uint_as_float(pack_pixel(px, py)));
     q.B[0][li] = make_float4(d.x, d.y, d.z, RT_MAX_RENDER_DIST);
     q.C[0][li] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
@@ -1070,6 +1084,14 @@ struct rt_ctx
     Queues q = {};
     float4* radiance = nullptr;
     float4* resolved = nullptr;
+    // whole-frame CUDA graph (RT_OPT_GRAPH): rt_integrate replays the captured launch sequence; only k_set_frame's
+    // by-value argument (sample index, camera constants) is updated per frame
+    int use_graph = 1;
+    uint64_t config_gen = 1, graph_gen = 0;     // config_gen changes whenever a launch argument other than FrameDyn may change
+    uint32_t graph_max_bounces = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphNode_t graph_set_frame_node = nullptr;
+    uint64_t graph_launches = 0;
     // shadow pass on a second stream (RT_OPT_OVERLAP): k_shadow_accumulate(b) runs concurrently with k_trace_closest(b+1)
     int overlap = 1;
     cudaStream_t shadow_stream = nullptr;
@@ -1087,6 +1109,7 @@ struct rt_ctx
     int aov_always = 0;
     RtCamera prev_camera = {}, aov_prev_camera = {};
     DevCounters* counters = nullptr;
+    FrameDyn* d_dyn = nullptr;
     void* scratch = nullptr; size_t scratch_bytes = 0;
 
     // scene
@@ -1175,7 +1198,7 @@ FrameParams frame_params(const rt_ctx* c)
 {
     FrameParams p;
     p.width = c->width; p.height = c->height; p.rank = c->rank; p.world = c->world; p.n_local = c->n_local;
-    p.sample_idx = c->sample_count; p.white_furnace = c->white_furnace;
+    p.white_furnace = c->white_furnace; p.dyn = c->d_dyn;
     return p;
 }
 
@@ -1193,6 +1216,7 @@ int alloc_frame_buffers(rt_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->shadow_stream) cudaStreamSynchronize(c->shadow_stream);
     c->shadow_pending = false;
+    ++c->config_gen;
     auto freep = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     for (int i = 0; i < 2; ++i) { freep(c->q.A[i]); freep(c->q.B[i]); freep(c->q.C[i]); }
     freep(c->q.sA); freep(c->q.sB); freep(c->q.sC); freep(c->q.hits); freep(c->q.shadow_flags);
@@ -1225,6 +1249,17 @@ size_t smem_stage_bytes(const rt_ctx* c)
     return bytes <= 40 * 1024 ? bytes : 0;
 }
 
+AovCam aov_cam(const RtCamera& cam);
+
+FrameDyn frame_dyn(const rt_ctx* c)
+{
+    FrameDyn dyn;
+    memset(&dyn, 0, sizeof(dyn));
+    dyn.sample_idx = c->sample_count; dyn.raygen = c->raygen;
+    dyn.cam = aov_cam(c->camera); dyn.prev = aov_cam(c->aov_prev_camera);
+    return dyn;
+}
+
 bool aov_wanted(const rt_ctx* c) { return c->aov != 0 || c->denoiser != 0 || c->aov_always != 0; }
 
 AovCam aov_cam(const RtCamera& cam)
@@ -1244,7 +1279,6 @@ AovParams aov_params(const rt_ctx* c)
     AovParams a;
     memset(&a, 0, sizeof(a));
     a.enabled = (aov_wanted(c) && c->aov_albedo) ? 1 : 0;
-    a.cam = aov_cam(c->camera); a.prev = aov_cam(c->aov_prev_camera);
     a.albedo = c->aov_albedo; a.depth = c->aov_depth; a.normal = c->aov_normal; a.velocity = c->aov_velocity;
     return a;
 }
@@ -1252,6 +1286,7 @@ AovParams aov_params(const rt_ctx* c)
 int ensure_aov_buffers(rt_ctx* c)
 {
     if (c->aov_albedo) return RT_OK;
+    ++c->config_gen;
     size_t n = c->n_local ? c->n_local : 1;
     RT_CUDA(c, cudaMalloc(&c->aov_albedo, n * 16)); RT_CUDA(c, cudaMalloc(&c->aov_depth, n * 4));
     RT_CUDA(c, cudaMalloc(&c->aov_normal, n * 16)); RT_CUDA(c, cudaMalloc(&c->aov_velocity, n * 8));
@@ -1300,6 +1335,8 @@ int rt_create(uint32_t width, uint32_t height, int device, rt_ctx** out_ctx)
     c->num_sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaMalloc(&c->counters, sizeof(DevCounters))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
+    if ((e = cudaMalloc(&c->d_dyn, sizeof(FrameDyn))) != cudaSuccess) return fail("cudaMalloc(frame constants)", e);
+    cudaMemsetAsync(c->d_dyn, 0, sizeof(FrameDyn), c->stream);
     cudaMemsetAsync(c->counters, 0, sizeof(DevCounters), c->stream);
     int rc = alloc_frame_buffers(c);
     if (rc != RT_OK) { g_create_error = c->error; rt_destroy(c); return rc; }
@@ -1316,7 +1353,8 @@ int rt_destroy(rt_ctx* c)
     for (int i = 0; i < 2; ++i) { cudaFree(c->q.A[i]); cudaFree(c->q.B[i]); cudaFree(c->q.C[i]); }
     cudaFree(c->q.sA); cudaFree(c->q.sB); cudaFree(c->q.sC); cudaFree(c->q.hits); cudaFree(c->q.shadow_flags);
     cudaFree(c->q.hitq); cudaFree(c->q.missq);
-    cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->resolved2); cudaFree(c->counters); cudaFree(c->scratch);
+    cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->resolved2); cudaFree(c->counters); cudaFree(c->scratch); cudaFree(c->d_dyn);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->shadow_stream) { cudaStreamSynchronize(c->shadow_stream); cudaStreamDestroy(c->shadow_stream); }
     if (c->ev_shaded) cudaEventDestroy(c->ev_shaded);
     if (c->ev_shadowed) cudaEventDestroy(c->ev_shadowed);
@@ -1423,6 +1461,7 @@ int rt_upload_scene(rt_ctx* c, const RtSceneDesc* s)
         ds.wnodes_f4 = (uint32_t)wl.nodes.size(); ds.wtris_f4 = (uint32_t)wl.tris.size();
     }
     c->scene_ready = true;
+    ++c->config_gen;
     return RT_OK;
 }
 
@@ -1451,6 +1490,7 @@ int rt_set_camera(rt_ctx* c, const RtCamera* cam)
 int rt_set_option(rt_ctx* c, int key, uint32_t value)
 {
     RT_CHECK_CTX(c);
+    ++c->config_gen;
     switch (key)
     {
     case RT_OPT_WHITE_FURNACE: c->white_furnace = value != 0; return RT_OK;
@@ -1474,6 +1514,7 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
         return RT_OK;
     case RT_OPT_COUNT_TRAVERSAL: c->count_traversal = value != 0; return RT_OK;
     case RT_OPT_KERNEL_TIMING: c->kernel_timing = value != 0; return RT_OK;
+    case RT_OPT_GRAPH: c->use_graph = value != 0; return RT_OK;
     case RT_OPT_SMEM_BVH: c->smem_bvh = value != 0; return RT_OK;
     case RT_OPT_OVERLAP: { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; c->overlap = value != 0; return RT_OK; }
     case RT_OPT_FUSION:
@@ -1516,7 +1557,12 @@ int rt_generate_rays(rt_ctx* c)
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(DevCounters), c->stream));
     TimedLaunch t(c, RT_K_RAYGEN);
-    k_raygen<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->raygen, c->q, c->counters, aov_params(c));
+    {
+        FrameDyn dyn = frame_dyn(c);
+        k_set_frame<<<1, 1, 0, c->stream>>>(c->d_dyn, dyn);
+        ++c->launches;
+    }
+    k_raygen<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->q, c->counters, aov_params(c));
     c->frame_started = true;
     return post_launch(c, "k_raygen");
 }
@@ -1689,10 +1735,8 @@ int rt_shadow_accumulate(rt_ctx* c, uint32_t bounce)
     return RT_OK;
 }
 
-int rt_integrate(rt_ctx* c, uint32_t max_bounces)
+static int integrate_body(rt_ctx* c, uint32_t max_bounces)
 {
-    RT_CHECK_CTX(c);
-    if (max_bounces > RT_MAX_BOUNCES) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "max_bounces %u exceeds RT_MAX_BOUNCES", max_bounces);
     int rc = rt_generate_rays(c); if (rc) return rc;
     for (uint32_t b = 0; b <= max_bounces; ++b)          // inclusive, integrator.cpp:37
     {
@@ -1700,6 +1744,81 @@ int rt_integrate(rt_ctx* c, uint32_t max_bounces)
         if ((rc = rt_shadow_accumulate(c, b))) return rc;
     }
     return rt_advance_sample_count(c);      // joins the shadow stream: the frame is complete in render-stream order
+}
+
+static void drop_graph(rt_ctx* c)
+{
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    c->graph_exec = nullptr; c->graph_set_frame_node = nullptr; c->graph_gen = 0;
+}
+
+// Captures one frame (both streams) into a graph.  Nothing executes during capture; host-side frame state is restored.
+static int capture_frame_graph(rt_ctx* c, uint32_t max_bounces)
+{
+    drop_graph(c);
+    int rc = join_shadow(c); if (rc) return rc;
+    if (c->overlap && !c->shadow_stream)
+    {   // create the second stream and its events outside the capture
+        RT_CUDA(c, cudaStreamCreateWithFlags(&c->shadow_stream, cudaStreamNonBlocking));
+        RT_CUDA(c, cudaEventCreateWithFlags(&c->ev_shaded, cudaEventDisableTiming));
+        RT_CUDA(c, cudaEventCreateWithFlags(&c->ev_shadowed, cudaEventDisableTiming));
+    }
+    const uint32_t saved_samples = c->sample_count, saved_bounce = c->cur_bounce;
+    const uint64_t saved_launches = c->launches;
+    const bool saved_started = c->frame_started;
+    RT_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    rc = integrate_body(c, max_bounces);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    c->graph_launches = c->launches - saved_launches;
+    c->sample_count = saved_samples; c->cur_bounce = saved_bounce; c->launches = saved_launches; c->frame_started = saved_started;
+    c->shadow_pending = false;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) RT_FAIL(c, RT_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    size_t n_nodes = 0;
+    RT_CUDA(c, cudaGraphGetNodes(graph, nullptr, &n_nodes));
+    std::vector<cudaGraphNode_t> nodes(n_nodes);
+    RT_CUDA(c, cudaGraphGetNodes(graph, nodes.data(), &n_nodes));
+    for (cudaGraphNode_t nd : nodes)
+    {
+        cudaGraphNodeType ty;
+        RT_CUDA(c, cudaGraphNodeGetType(nd, &ty));
+        if (ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        RT_CUDA(c, cudaGraphKernelNodeGetParams(nd, &kp));
+        if (kp.func == (void*)k_set_frame) c->graph_set_frame_node = nd;
+    }
+    if (!c->graph_set_frame_node) { cudaGraphDestroy(graph); RT_FAIL(c, RT_ERR_CUDA, "frame graph has no k_set_frame node"); }
+    e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { c->graph_exec = nullptr; RT_FAIL(c, RT_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    c->graph_gen = c->config_gen; c->graph_max_bounces = max_bounces;
+    return RT_OK;
+}
+
+int rt_integrate(rt_ctx* c, uint32_t max_bounces)
+{
+    RT_CHECK_CTX(c);
+    if (max_bounces > RT_MAX_BOUNCES) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "max_bounces %u exceeds RT_MAX_BOUNCES", max_bounces);
+    if (!c->use_graph || c->kernel_timing || c->count_traversal) return integrate_body(c, max_bounces);
+    int rc = require_ready(c); if (rc) return rc;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    if (!c->graph_exec || c->graph_gen != c->config_gen || c->graph_max_bounces != max_bounces)
+        if ((rc = capture_frame_graph(c, max_bounces))) return rc;
+    if ((rc = join_shadow(c))) return rc;
+    // the one per-frame update: k_set_frame's by-value argument (sample index + camera constants)
+    FrameDyn dyn = frame_dyn(c);
+    FrameDyn* dst = c->d_dyn;
+    void* args[2] = { &dst, &dyn };
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = (void*)k_set_frame; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.sharedMemBytes = 0; kp.kernelParams = args; kp.extra = nullptr;
+    RT_CUDA(c, cudaGraphExecKernelNodeSetParams(c->graph_exec, c->graph_set_frame_node, &kp));
+    RT_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
+    c->launches += c->graph_launches;
+    c->frame_started = true; c->cur_bounce = max_bounces;
+    ++c->sample_count;
+    return RT_OK;
 }
 
 int rt_resolve(rt_ctx* c, float* dst)
