@@ -1089,8 +1089,10 @@ struct rt_ctx
     int use_graph = 1;
     uint64_t config_gen = 1, graph_gen = 0;     // config_gen changes whenever a launch argument other than FrameDyn may change
     uint32_t graph_max_bounces = 0;
+    cudaGraph_t graph = nullptr;                // kept alive: node handles used for parameter updates belong to it
     cudaGraphExec_t graph_exec = nullptr;
     cudaGraphNode_t graph_set_frame_node = nullptr;
+    void* graph_set_frame_func = nullptr;
     uint64_t graph_launches = 0;
     // shadow pass on a second stream (RT_OPT_OVERLAP): k_shadow_accumulate(b) runs concurrently with k_trace_closest(b+1)
     int overlap = 1;
@@ -1355,6 +1357,7 @@ int rt_destroy(rt_ctx* c)
     cudaFree(c->q.hitq); cudaFree(c->q.missq);
     cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->resolved2); cudaFree(c->counters); cudaFree(c->scratch); cudaFree(c->d_dyn);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
     if (c->shadow_stream) { cudaStreamSynchronize(c->shadow_stream); cudaStreamDestroy(c->shadow_stream); }
     if (c->ev_shaded) cudaEventDestroy(c->ev_shaded);
     if (c->ev_shadowed) cudaEventDestroy(c->ev_shadowed);
@@ -1749,7 +1752,8 @@ static int integrate_body(rt_ctx* c, uint32_t max_bounces)
 static void drop_graph(rt_ctx* c)
 {
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
-    c->graph_exec = nullptr; c->graph_set_frame_node = nullptr; c->graph_gen = 0;
+    if (c->graph) cudaGraphDestroy(c->graph);
+    c->graph_exec = nullptr; c->graph = nullptr; c->graph_set_frame_node = nullptr; c->graph_gen = 0;
 }
 
 // Captures one frame (both streams) into a graph.  Nothing executes during capture; host-side frame state is restored.
@@ -1786,12 +1790,15 @@ static int capture_frame_graph(rt_ctx* c, uint32_t max_bounces)
         if (ty != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp;
         RT_CUDA(c, cudaGraphKernelNodeGetParams(nd, &kp));
-        if (kp.func == (void*)k_set_frame) c->graph_set_frame_node = nd;
+        if (kp.gridDim.x == 1 && kp.blockDim.x == 1 && !c->graph_set_frame_node)
+        {   // k_set_frame is the only <<<1,1>>> launch of the frame and the first kernel of it
+            c->graph_set_frame_node = nd; c->graph_set_frame_func = kp.func;
+        }
     }
     if (!c->graph_set_frame_node) { cudaGraphDestroy(graph); RT_FAIL(c, RT_ERR_CUDA, "frame graph has no k_set_frame node"); }
     e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { c->graph_exec = nullptr; RT_FAIL(c, RT_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); c->graph_exec = nullptr; RT_FAIL(c, RT_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    c->graph = graph;
     c->graph_gen = c->config_gen; c->graph_max_bounces = max_bounces;
     return RT_OK;
 }
@@ -1812,7 +1819,7 @@ int rt_integrate(rt_ctx* c, uint32_t max_bounces)
     void* args[2] = { &dst, &dyn };
     cudaKernelNodeParams kp;
     memset(&kp, 0, sizeof(kp));
-    kp.func = (void*)k_set_frame; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.sharedMemBytes = 0; kp.kernelParams = args; kp.extra = nullptr;
+    kp.func = c->graph_set_frame_func; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.sharedMemBytes = 0; kp.kernelParams = args; kp.extra = nullptr;
     RT_CUDA(c, cudaGraphExecKernelNodeSetParams(c->graph_exec, c->graph_set_frame_node, &kp));
     RT_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
     c->launches += c->graph_launches;
