@@ -434,11 +434,19 @@ __device__ __forceinline__ void shade_hit(const DevScene& sc, const FrameParams&
         float s_light = sample_random(pixel_seed, bounce, SAMPLE_LIGHT);
         f3 outgoing; float pdf, distance_to_light;
         f3 light_radiance = light_sample(sc, position, s_light, outgoing, distance_to_light, pdf);
-        f3 brdf = evaluate_material(material, normal, incoming, outgoing);
-        f3 ls = light_radiance * hit_throughput * brdf / pdf * fmaxf(dot(outgoing, normal), 0.0f);
-        out.spawn_shadow = (pdf > 0.0f) && (dot(ls, ls) > 0.0f);
-        out.s_origin = position + normal * RT_EPS;
-        out.s_dir = outgoing; out.s_tmax = distance_to_light; out.s_sample = ls;
+        // light_sample = L * throughput * brdf / pdf * max(n.l, 0); a shadow ray is spawned iff pdf > 0 and
+        // dot(sample, sample) > 0 (hit_surface.cl:127-129).  When max(n.l, 0) is 0 every component of the sample is
+        // +-0 or NaN whatever the BRDF evaluates to, so the ray is never spawned: the BRDF evaluation is skipped then.
+        const float cos_l = fmaxf(dot(outgoing, normal), 0.0f);
+        out.spawn_shadow = false;
+        if (cos_l > 0.0f)
+        {
+            f3 brdf = evaluate_material(material, normal, incoming, outgoing);
+            f3 ls = light_radiance * hit_throughput * brdf / pdf * cos_l;
+            out.spawn_shadow = (pdf > 0.0f) && (dot(ls, ls) > 0.0f);
+            out.s_origin = position + normal * RT_EPS;
+            out.s_dir = outgoing; out.s_tmax = distance_to_light; out.s_sample = ls;
+        }
     }
     {   // BSDF sampling
         f2 s; s.x = sample_random(pixel_seed, bounce, SAMPLE_U); s.y = sample_random(pixel_seed, bounce, SAMPLE_V);

@@ -35,8 +35,11 @@ class RadianceGather:
         """The one collective of the frame.  Returns the list of padded slabs on rank 0, None elsewhere."""
         if self.world == 1:
             return [slab]
-        self.send[: self.n_local].copy_(slab[: self.n_local])
-        dist.gather(self.send, self.recv, dst=0)
+        if self.n_local == self.n_pad and slab.shape[0] == self.n_pad:
+            dist.gather(slab, self.recv, dst=0)                 # every rank owns rows_max rows: gather straight from the device slab
+        else:
+            self.send[: self.n_local].copy_(slab[: self.n_local])
+            dist.gather(self.send, self.recv, dst=0)
         return self.recv
 
     def reassemble(self, slabs) -> np.ndarray:
