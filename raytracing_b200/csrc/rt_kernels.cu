@@ -890,86 +890,76 @@ __global__ void __launch_bounds__(256) k_trace_refill(FrameParams p, DevScene sc
             if (__ballot_sync(0xffffffffu, has) == 0u) break;      // nothing in flight and nothing left to fetch
         }
 
-        // One traversal round for every lane that holds a ray.  The two phases are separated by full-warp
-        // convergence points: without them the compiler lets lanes that leave the interior loop early run the
-        // leaf code on their own (ncu: 3 of 32 lanes active in the triangle test), which is exactly the
-        // divergence this kernel exists to remove.
+        // One traversal ROUND ("if-if"): every lane that holds a ray performs at most one interior-record step and then at
+        // most one triangle test.  No lane ever waits for another lane's loop to finish: a lane inside a 4-triangle leaf
+        // shares its four rounds with other lanes' interior steps, and a lane whose ray terminates becomes refillable
+        // at the next round.  Order of node visits, triangle tests and t_max updates per ray is unchanged.
         bool finished = has && finish_now;
-        const bool act = has && !finish_now;
-
-        // ---- phase A: descend through interior records until this lane reaches a leaf (cur < 0) or terminates
-        if (act)
+        if (has && !finish_now && cur >= 0)
         {
-            while (cur >= 0)
+            const float4* np = sc.wnodes + (size_t)cur * 4;
+            float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2), m = __ldg(np + 3);
+            f3 t00 = (mk3(a.x, a.y, a.z) - o) * inv, t01 = (mk3(a.w, b.x, b.y) - o) * inv;
+            f3 t10 = (mk3(b.z, b.w, c.x) - o) * inv, t11 = (mk3(c.y, c.z, c.w) - o) * inv;
+            float lo0 = fmaxf(fmaxf(fmaxf(fminf(t00.x, t01.x), fminf(t00.y, t01.y)), fminf(t00.z, t01.z)), 0.0f);
+            float hi0 = fminf(fminf(fmaxf(t00.x, t01.x), fmaxf(t00.y, t01.y)), fmaxf(t00.z, t01.z));
+            float lo1 = fmaxf(fmaxf(fmaxf(fminf(t10.x, t11.x), fminf(t10.y, t11.y)), fminf(t10.z, t11.z)), 0.0f);
+            float hi1 = fminf(fminf(fmaxf(t10.x, t11.x), fmaxf(t10.y, t11.y)), fmaxf(t10.z, t11.z));
+            bool h0 = fminf(hi0, t_max) >= lo0, h1 = fminf(hi1, t_max) >= lo1;
+            int r0 = __float_as_int(m.x), r1 = __float_as_int(m.y);
+            uint32_t axis = __float_as_uint(m.z);
+            bool swap = axis == 0 ? sx : (axis == 1 ? sy : sz);
+            int near_ref = swap ? r1 : r0, far_ref = swap ? r0 : r1;
+            bool near_hit = swap ? h1 : h0, far_hit = swap ? h0 : h1;
+            float far_lo = swap ? lo0 : lo1;
+            if (near_hit)
             {
-                const float4* np = sc.wnodes + (size_t)cur * 4;
-                float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2), m = __ldg(np + 3);
-                f3 t00 = (mk3(a.x, a.y, a.z) - o) * inv, t01 = (mk3(a.w, b.x, b.y) - o) * inv;
-                f3 t10 = (mk3(b.z, b.w, c.x) - o) * inv, t11 = (mk3(c.y, c.z, c.w) - o) * inv;
-                float lo0 = fmaxf(fmaxf(fmaxf(fminf(t00.x, t01.x), fminf(t00.y, t01.y)), fminf(t00.z, t01.z)), 0.0f);
-                float hi0 = fminf(fminf(fmaxf(t00.x, t01.x), fmaxf(t00.y, t01.y)), fmaxf(t00.z, t01.z));
-                float lo1 = fmaxf(fmaxf(fmaxf(fminf(t10.x, t11.x), fminf(t10.y, t11.y)), fminf(t10.z, t11.z)), 0.0f);
-                float hi1 = fminf(fminf(fmaxf(t10.x, t11.x), fmaxf(t10.y, t11.y)), fmaxf(t10.z, t11.z));
-                bool h0 = fminf(hi0, t_max) >= lo0, h1 = fminf(hi1, t_max) >= lo1;
-                int r0 = __float_as_int(m.x), r1 = __float_as_int(m.y);
-                uint32_t axis = __float_as_uint(m.z);
-                bool swap = axis == 0 ? sx : (axis == 1 ? sy : sz);
-                int near_ref = swap ? r1 : r0, far_ref = swap ? r0 : r1;
-                bool near_hit = swap ? h1 : h0, far_hit = swap ? h0 : h1;
-                float far_lo = swap ? lo0 : lo1;
-                if (near_hit)
-                {
-                    if (far_hit) { stack_ref[sp] = far_ref; stack_t[sp] = far_lo; ++sp; }
-                    cur = near_ref;
-                }
-                else if (far_hit) cur = far_ref;
-                else
-                {
-                    bool found = false;
-                    while (sp > 0) { --sp; if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; } }
-                    if (!found) { finished = true; break; }
-                }
+                if (far_hit) { stack_ref[sp] = far_ref; stack_t[sp] = far_lo; ++sp; }
+                cur = near_ref;
             }
-        }
-        __syncwarp();
-
-        // ---- phase B: all lanes that reached a leaf test its triangles together (straight-line Moeller-Trumbore:
-        // same operations as trace_bvh.cl:28-73; the early-outs become one predicate, a rejected triangle's
-        // inf/NaN intermediates are never used)
-        if (act && !finished)
-        {
-            uint32_t ti = (uint32_t)(~cur);
-            for (;;)
-            {
-                const float4* tp = sc.wtris + (size_t)ti * 3;
-                float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-                f3 p1 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
-                bool last = __float_as_uint(q2.y) != 0u;
-                f3 pvec = cross(d, e2);
-                float det = dot(e1, pvec);
-                float inv_det = 1.0f / det;
-                f3 tvec = o - p1;
-                float u = dot(tvec, pvec) * inv_det;
-                f3 qvec = cross(tvec, e1);
-                float v = dot(d, qvec) * inv_det;
-                float t = dot(e2, qvec) * inv_det;
-                bool ok = !(det < 1e-8f || -det > 1e-8f) && !(u < 0.0f || u > 1.0f) && !(v < 0.0f || u + v > 1.0f) && !(t < 0.0f || t > t_max);
-                if (ok)
-                {
-                    bu = u; bv = v; prim = ANY ? 0u : ti; t_max = t;
-                    if (ANY) { finished = true; break; }
-                }
-                if (last) break;
-                ++ti;
-            }
-            if (!finished)
+            else if (far_hit) cur = far_ref;
+            else
             {
                 bool found = false;
                 while (sp > 0) { --sp; if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; } }
                 if (!found) finished = true;
             }
         }
-        __syncwarp();
+        else if (has && !finish_now)
+        {   // cur < 0: the next triangle of the current leaf is ~cur
+            const uint32_t ti = (uint32_t)(~cur);
+            const float4* tp = sc.wtris + (size_t)ti * 3;
+            float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+            f3 p1 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
+            const bool last = __float_as_uint(q2.y) != 0u;
+            f3 pvec = cross(d, e2);
+            float det = dot(e1, pvec);
+            bool hit_tri = false;
+            if (!(det < 1e-8f || -det > 1e-8f))
+            {
+                float inv_det = 1.0f / det;
+                f3 tvec = o - p1;
+                float u = dot(tvec, pvec) * inv_det;
+                if (!(u < 0.0f || u > 1.0f))
+                {
+                    f3 qvec = cross(tvec, e1);
+                    float v = dot(d, qvec) * inv_det;
+                    if (!(v < 0.0f || u + v > 1.0f))
+                    {
+                        float t = dot(e2, qvec) * inv_det;
+                        if (!(t < 0.0f || t > t_max)) { bu = u; bv = v; prim = ANY ? 0u : ti; t_max = t; hit_tri = true; }
+                    }
+                }
+            }
+            if (ANY && hit_tri) finished = true;
+            else if (!last) cur = ~(int)(ti + 1u);
+            else
+            {
+                bool found = false;
+                while (sp > 0) { --sp; if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; } }
+                if (!found) finished = true;
+            }
+        }
         if (finished) { has = false; parked = true; }
     }
 }
