@@ -1173,7 +1173,7 @@ struct TimedLaunch
     }
 };
 
-inline dim3 grid_for(uint32_t n, uint32_t block = 256) { return dim3((n + block - 1) / block); }
+inline dim3 grid_for(uint32_t n, uint32_t block = 256) { uint32_t g = (n + block - 1) / block; return dim3(g ? g : 1u); }   // n = 0: one idle block
 
 // Work submitted to the shadow stream must be ordered before anything on the render stream that touches the radiance
 // buffer, the shadow queue or the counters again.

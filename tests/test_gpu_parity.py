@@ -273,6 +273,43 @@ def test_resolve_async_matches_blocking_resolve():
     c.destroy()
 
 
+def test_textured_materials_match_oracle():
+    """Texture sampling path of the shader (per-hit unpack instead of the precomputed material record)."""
+    from tests.scenes_extra import textured_cornell
+    sc = textured_cornell()
+    w, h, mb = 200, 150, 5
+    cam = default_camera(w, h)
+    orad, _, ost = Oracle(sc).render(cam, w, h, mb)
+    for stepwise in (False, True):
+        c = capi.Context(w, h); c.upload_scene(sc); c.set_camera(cam); c.reset()
+        c.integrate_stepwise(mb) if stepwise else c.integrate(mb)
+        check_stats(c.frame_stats(), ost, mb)
+        assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(orad[..., :3]))
+        c.destroy()
+
+
+@pytest.mark.parametrize("n_tris", [1, 2])
+def test_root_leaf_bvh_and_tiny_images(n_tris):
+    """A BVH that is a single leaf, a 1x1 image, and a partition where one rank owns no row at all."""
+    from tests.scenes_extra import single_leaf_scene
+    sc = single_leaf_scene(n_tris)
+    for (w, h) in [(1, 1), (33, 3)]:
+        cam = default_camera(w, h)
+        orad, _, ost = Oracle(sc).render(cam, w, h, 3)
+        for traversal in (0, 1, 2):
+            c = capi.Context(w, h); c.upload_scene(sc); c.set_camera(cam); c.set_option(capi.OPT_TRAVERSAL, traversal)
+            c.reset(); c.integrate(3)
+            check_stats(c.frame_stats(), ost, 3)
+            assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(orad[..., :3]))
+            c.destroy()
+    w, h = 33, 3
+    out = np.zeros((h, w, 4), "<f4")
+    for rank in range(4):                       # rank 3 owns zero rows
+        c = capi.Context(w, h, rank=rank, world=4); c.upload_scene(sc); c.set_camera(default_camera(w, h))
+        c.reset(); c.integrate(3); c.read_radiance(out); c.resolve(); c.destroy()
+    assert np.array_equal(bits(out[..., :3]), bits(orad[..., :3]))
+
+
 def test_error_behaviour():
     c = capi.Context(32, 32)
     with pytest.raises(capi.RtError):

@@ -67,6 +67,24 @@ def test_aov_denoiser_resolve_restatements_vs_reference_kernels(name):
     r.close()
 
 
+def test_textured_materials_bit_exact_vs_reference_kernels():
+    """ApplyTextures / SampleTexture (material.h:251-264,319-369) on every texture slot, wrapped coordinates included."""
+    from tests.scenes_extra import textured_cornell
+    sc = textured_cornell()
+    w, h, mb = 96, 64, 4
+    cam = default_camera(w, h)
+    r = refbind.RefRenderer().open_arrays(sc); r.begin(w, h); r.set_camera(cam); r.set_max_bounces(mb); r.integrate()
+    rad, hits, st = Oracle(sc).render(cam, w, h, mb)
+    rs = r.stats()
+    for k in ("n_ext", "n_miss", "n_shadow", "n_cont", "n_unoccluded"):
+        assert np.array_equal(st[k][: mb + 1], rs[k][: mb + 1]), k
+    assert np.array_equal(bits(rad[..., :3]), bits(r.radiance()[..., :3]))
+    # the textured image must differ from the untextured one (the textures are really used)
+    plain, _, _ = Oracle(scene("CornellBox")).render(cam, w, h, mb)
+    assert not np.array_equal(bits(plain), bits(rad))
+    r.close()
+
+
 def test_math_library_sensitivity_is_small():
     """The OpenCL driver's libm is unpinned.  Swapping include/rt_math.h for glibc's libm inside the
     reference kernels must leave all but a small fraction of pixels within 1e-4 relative."""
