@@ -11,7 +11,7 @@
 
 #include <vector>
 
-#include "acceleration_structure.hpp"
+#include "reference_api.hpp"
 
 namespace rt_host
 {

@@ -2,7 +2,7 @@
 
 #include <stdexcept>
 
-#include "scene.hpp"
+#include "reference_api.hpp"
 
 namespace rt_host
 {

@@ -24,7 +24,7 @@
 
 #include <string>
 
-#include "integrator.hpp"
+#include "reference_api.hpp"
 #include "rt_b200.h"
 
 namespace rt_host

@@ -9,7 +9,7 @@
 
 #include "bvh.hpp"
 #include "render.hpp"
-#include "scene.hpp"
+#include "reference_api.hpp"
 
 using namespace rt_host;
 

@@ -1,4 +1,9 @@
-#include "scene.hpp"
+/*
+ * reference_api.cpp — implementation of the mirrored reference-facing classes declared in reference_api.hpp:
+ *   Scene (OBJ/MTL loader, material packing, lights, emissive list, Radiance .hdr reader)
+ *   Integrator (the per-frame wavefront schedule and the base-class setters)
+ */
+#include "reference_api.hpp"
 
 #include <cmath>
 #include <cstdio>
@@ -338,6 +343,50 @@ bool LoadHDR(const char* filename, Image& res)
     }
     fclose(f);
     return true;
+}
+
+// ================================================================================================ Integrator (base class)
+// The per-frame wavefront schedule, integrator.cpp:27-59: the bounce loop is INCLUSIVE of max_bounces.
+void Integrator::Integrate()
+{
+    if (request_reset_ || enable_denoiser_)
+    {
+        Reset();
+        request_reset_ = false;
+    }
+    GenerateRays();
+    for (std::uint32_t bounce = 0; bounce <= max_bounces_; ++bounce)
+    {
+        IntersectRays(bounce);
+        if (bounce == 0) ComputeAOVs();
+        ShadeMissedRays(bounce);
+        ClearOutgoingRayCounter(bounce);
+        ClearShadowRayCounter();
+        ShadeSurfaceHits(bounce);
+        IntersectShadowRays();
+        AccumulateDirectSamples();
+    }
+    AdvanceSampleCount();
+    if (enable_denoiser_)
+    {
+        Denoise();
+        CopyHistoryBuffers();
+    }
+    ResolveRadiance();
+}
+
+void Integrator::SetMaxBounces(std::uint32_t max_bounces)
+{
+    max_bounces_ = max_bounces;
+    RequestReset();
+}
+
+void Integrator::EnableWhiteFurnace(bool enable)
+{
+    if (enable == enable_white_furnace_) return;
+    enable_white_furnace_ = enable;
+    CreateKernels();
+    RequestReset();
 }
 
 } // namespace rt_host

@@ -14,7 +14,7 @@
 #include "bvh.hpp"
 #include "camera_controller.hpp"
 #include "cuda_pt_integrator.hpp"
-#include "scene.hpp"
+#include "reference_api.hpp"
 
 namespace rt_host
 {
