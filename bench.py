@@ -113,10 +113,23 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def host_threads() -> int:
+    """Threads the CPU arm may really use: the affinity mask, capped by the cgroup CPU quota when one is set."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(np.ceil(int(quota) / int(period)))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def cpu_reference_frame(scene, cam, w, h, mb, budget_s, threads):
     """Times the reference's CPU implementation of the path (oracle/_ref if built, else the oracle port) on a bounded
     sample: rows y % step == 0 of the same frame.  Returns (Mrays/s, kind, cores, sample description, seconds)."""
     os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")        # shared boxes: idle workers sleep instead of spinning
     from oracle import refbind
     from oracle.orcbind import Oracle
     use_ref = refbind.available()
@@ -154,7 +167,7 @@ def run_reference_arm(args, workload):
         return
     name, w, h, mb = workload
     scene, cam = load_workload_scene(name, w, h, args.copies)
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     total_budget = 150.0
     per_step = max(2.0, total_budget / (args.steps + args.warmup))
     vals, info = [], None
@@ -398,7 +411,7 @@ def main():
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:
-            v, kind, cores, sample, _ = cpu_reference_frame(scene, cam, w, h, mb, 15.0, os.cpu_count() or 1)
+            v, kind, cores, sample, _ = cpu_reference_frame(scene, cam, w, h, mb, 15.0, host_threads())
             line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line))
     ctx.destroy()
