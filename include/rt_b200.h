@@ -60,7 +60,7 @@ typedef struct RtSceneDesc {
 /* rt_set_option keys: the Integrator setters (integrator.hpp:45-53) */
 typedef enum RtOption {
     RT_OPT_WHITE_FURNACE = 0,   /* EnableWhiteFurnace(bool)                          */
-    RT_OPT_SAMPLER = 1,         /* SetSamplerType: 0 = kRandom, 1 = kBlueNoise (unsupported yet) */
+    RT_OPT_SAMPLER = 1,         /* SetSamplerType: 0 = kRandom, 1 = kBlueNoise (after rt_upload_sampler_tables) */
     RT_OPT_AOV = 2,             /* SetAOV: 0 shaded colour, 1 albedo, 2 depth, 3 normal, 4 motion vectors (view used by rt_resolve) */
     RT_OPT_DENOISER = 3,        /* EnableDenoiser(bool): temporal accumulation (single-GPU only) */
     RT_OPT_COUNT_TRAVERSAL = 16,/* 1: kernels also count BVH nodes visited / triangles tested (slower; for
@@ -125,6 +125,14 @@ int rt_set_partition(rt_ctx* ctx, uint32_t rank, uint32_t world);
 int rt_upload_scene(rt_ctx* ctx, const RtSceneDesc* scene);     /* UploadGPUData, cl_pt_integrator.cpp:373-456 */
 int rt_set_camera(rt_ctx* ctx, const RtCamera* camera);         /* SetCameraData,  cl_pt_integrator.cpp:365-371 */
 int rt_set_option(rt_ctx* ctx, int key, uint32_t value);
+/* The three tables of the blue-noise sampler (SamplerType::kBlueNoise, kernels/common/sampling.h:40-61).  The OpenCL
+ * backend creates its buffers from the arrays of utils/blue_noise_sampler.hpp (cl_pt_integrator.cpp:222-235); the
+ * caller passes the same arrays here: sobol_256spp_256d[RT_BN_SOBOL_COUNT], scramblingTile[RT_BN_TILE_COUNT],
+ * rankingTile[RT_BN_TILE_COUNT].  Copied; ranking entries must lie in 0..255 (they are XORed into a sobol row index).
+ * One deviation is defined here: the reference indexes rankingTile with the un-wrapped sample dimension
+ * (sampling.h:50), which reads up to 247 entries past the end of the table for the last tile pixels once the dimension
+ * exceeds 7 (undefined in the reference); such reads return 0. */
+int rt_upload_sampler_tables(rt_ctx* ctx, const int32_t* sobol_256spp_256d, const int32_t* scrambling_tile, const int32_t* ranking_tile);
 
 /* ---- Integrator protected steps, one call per virtual (integrator.hpp:55-71), same
  *      order contract as Integrator::Integrate (integrator.cpp:27-59) ----------------- */

@@ -101,6 +101,9 @@ typedef struct RtCamera {
 #define RT_INV_TWO_PI 0.15915494309f
 #define RT_INVALID_ID 0xFFFFFFFFu
 #define RT_INVALID_TEXTURE_IDX 0xFFu
+/* blue-noise sampler tables (kernels/common/sampling.h:40-61; the reference ships them in utils/blue_noise_sampler.hpp) */
+#define RT_BN_SOBOL_COUNT 65536      /* sobol_256spp_256d: 256 samples x 256 dimensions */
+#define RT_BN_TILE_COUNT 131072      /* scramblingTile / rankingTile: 128 x 128 pixels x 8 dimensions */
 
 #ifdef __cplusplus
 }

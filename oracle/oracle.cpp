@@ -70,10 +70,32 @@ inline float GetRandomFloat(uint32_t* seed)
     return (float)s * 2.3283064365386963e-10f;
 }
 
-// kernels/common/sampling.h:64-82 (kRandom sampler).  Result is in [0,1] INCLUSIVE.
+// kernels/common/sampling.h:40-61 (kBlueNoise sampler).  The tables are the caller's (the reference ships them in
+// utils/blue_noise_sampler.hpp); orc_set_sampler_tables selects the sampler for the renders that follow.
+// sampling.h:50 indexes rankingTile with the un-wrapped dimension, which runs past the table's end for the last
+// tile pixels once the dimension exceeds 7 (undefined in the reference): such reads return 0 (include/rt_b200.h).
+static const int32_t* g_bn_sobol = nullptr;
+static const int32_t* g_bn_scrambling = nullptr;
+static const int32_t* g_bn_ranking = nullptr;
+inline float SampleBlueNoise(int pixel_i, int pixel_j, int sample_index, int sample_dimension)
+{
+    pixel_i = pixel_i & 127;
+    pixel_j = pixel_j & 127;
+    sample_index = sample_index & 255;
+    sample_dimension = sample_dimension & 255;
+    int tile = (pixel_i + pixel_j * 128) * 8;
+    int ranking_index = sample_dimension + tile;
+    int ranked_sample_index = sample_index ^ (ranking_index < RT_BN_TILE_COUNT ? g_bn_ranking[ranking_index] : 0);
+    int value = g_bn_sobol[sample_dimension + ranked_sample_index * 256];
+    value = value ^ g_bn_scrambling[(sample_dimension % 8) + tile];
+    return (0.5f + (float)value) / 256.0f;
+}
+
+// kernels/common/sampling.h:64-82.  kRandom results are in [0,1] INCLUSIVE.
 inline float SampleRandom(uint32_t px, uint32_t py, uint32_t sample_index, uint32_t bounce, uint32_t type)
 {
     uint32_t dim = bounce * 5u + type;
+    if (g_bn_sobol) return SampleBlueNoise((int)px, (int)py, (int)sample_index, (int)dim);
     uint32_t seed = WangHash(px);
     seed = WangHash(seed + WangHash(py));
     seed = WangHash(seed + WangHash(sample_index));
@@ -500,6 +522,13 @@ static Scene to_scene(const OrcScene* s)
 }
 
 uint32_t orc_wang_hash(uint32_t x) { return WangHash(x); }
+/* kBlueNoise when all three tables are given (sobol[65536], scrambling[131072], ranking[131072]; not copied — they
+ * must outlive the renders), kRandom when any is NULL. */
+void orc_set_sampler_tables(const int32_t* sobol, const int32_t* scrambling, const int32_t* ranking)
+{
+    bool on = sobol && scrambling && ranking;
+    g_bn_sobol = on ? sobol : nullptr; g_bn_scrambling = on ? scrambling : nullptr; g_bn_ranking = on ? ranking : nullptr;
+}
 float orc_sample_random(uint32_t px, uint32_t py, uint32_t sample, uint32_t bounce, uint32_t type) { return SampleRandom(px, py, sample, bounce, type); }
 
 /* Primary rays for pixels [first, first+count): kernels/cl/raygeneration.cl:65-139 */

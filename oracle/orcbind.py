@@ -43,6 +43,7 @@ class Oracle:
         L = self.lib = C.CDLL(LIB)
         L.orc_wang_hash.restype = C.c_uint32
         L.orc_wang_hash.argtypes = [C.c_uint32]
+        L.orc_set_sampler_tables.argtypes = [C.c_void_p] * 3
         L.orc_sample_random.restype = C.c_float
         L.orc_sample_random.argtypes = [C.c_uint32] * 5
         L.orc_generate_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
@@ -74,6 +75,16 @@ class Oracle:
             s.info[i] = int(info[i])
 
     def wang_hash(self, x): return self.lib.orc_wang_hash(x)
+    def set_sampler_tables(self, tables):
+        """kBlueNoise with (sobol, scrambling, ranking) int32 arrays, kRandom with None.  Process-wide, like the option it mirrors."""
+        if tables is None:
+            self._bn = None
+            self.lib.orc_set_sampler_tables(None, None, None)
+            return
+        self._bn = [np.ascontiguousarray(t, dtype=np.int32) for t in tables]
+        assert [t.size for t in self._bn] == [65536, 131072, 131072]
+        self.lib.orc_set_sampler_tables(*[t.ctypes.data for t in self._bn])
+
     def sample_random(self, px, py, sample, bounce, typ): return self.lib.orc_sample_random(px, py, sample, bounce, typ)
 
     def generate_rays(self, cam, width, height, sample_idx=0, first=0, count=None):

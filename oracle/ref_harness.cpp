@@ -92,6 +92,20 @@ struct Stats
     std::uint32_t n_shadow[kMaxStatBounces], n_cont[kMaxStatBounces], n_unoccluded[kMaxStatBounces];
 };
 
+// sampling.h:50 indexes rankingTile with the un-wrapped dimension and so reads up to 247 ints past its end for the last
+// tile pixels (undefined behaviour; on the host it would pick up whatever the linker placed next).  The kernels get a
+// copy followed by 256 zeros, which is the behaviour include/rt_b200.h defines for those reads.
+static const int* PaddedRankingTile()
+{
+    static std::vector<int> padded = [] {
+        const size_t n = sizeof(rankingTile) / sizeof(rankingTile[0]);
+        std::vector<int> v(n + 256, 0);
+        for (size_t k = 0; k < n; ++k) v[k] = (int)rankingTile[k];
+        return v;
+    }();
+    return padded.data();
+}
+
 class RefCpuIntegrator : public Integrator
 {
 public:
@@ -189,7 +203,7 @@ protected:
         fn(N(), rays_[in].p, ray_counter_[in].p, pixel_indices_[in].p, hits_.p, scene_.triangles.data(),
             scene_.lights.data(), scene_.emissive.data(), scene_.materials.data(), scene_.textures.data(),
             scene_.texture_data.data(), bounce, width_, height_, sample_counter_.p, &scene_.info,
-            (void*)sobol_256spp_256d, (void*)scramblingTile, (void*)rankingTile,
+            (void*)sobol_256spp_256d, (void*)scramblingTile, (void*)PaddedRankingTile(),
             throughputs_.p, rays_[out].p, ray_counter_[out].p, pixel_indices_[out].p,
             shadow_rays_.p, shadow_ray_counter_.p, shadow_pixel_indices_.p, direct_light_samples_.p, radiance_.p);
         if (bounce < (std::uint32_t)kMaxStatBounces)
@@ -339,6 +353,12 @@ int ref_begin(void* handle, std::uint32_t width, std::uint32_t height)
 void ref_set_camera(void* handle, const void* camera) { Camera c; memcpy(&c, camera, sizeof(Camera)); ((RefHandle*)handle)->integrator->SetCameraData(c); }
 void ref_set_max_bounces(void* handle, std::uint32_t b) { ((RefHandle*)handle)->integrator->SetMaxBounces(b); }
 void ref_enable_white_furnace(void* handle, int e) { ((RefHandle*)handle)->integrator->EnableWhiteFurnace(e != 0); }
+// The three sampler tables of utils/blue_noise_sampler.hpp as the reference compiled them in (tests read them from here
+// rather than from a committed copy).
+void ref_sampler_tables(const int** sobol, const int** scrambling, const int** ranking)
+{
+    *sobol = (const int*)sobol_256spp_256d; *scrambling = (const int*)scramblingTile; *ranking = (const int*)rankingTile;
+}
 void ref_set_sampler(void* handle, int blue_noise) { ((RefHandle*)handle)->integrator->SetSamplerType(blue_noise ? Integrator::SamplerType::kBlueNoise : Integrator::SamplerType::kRandom); }
 void ref_enable_denoiser(void* handle, int e) { ((RefHandle*)handle)->integrator->EnableDenoiser(e != 0); }
 void ref_set_aov(void* handle, int aov) { ((RefHandle*)handle)->integrator->SetAOV((Integrator::AOV)aov); }

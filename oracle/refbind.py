@@ -48,6 +48,7 @@ class RefRenderer:
         for name in ("ref_request_reset", "ref_integrate", "ref_close"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.ref_set_row_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.ref_sampler_tables.argtypes = [C.POINTER(C.POINTER(C.c_int))] * 3
         L.ref_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         self.h = None
         self.width = self.height = 0
@@ -95,6 +96,12 @@ class RefRenderer:
     def set_max_bounces(self, b): self.lib.ref_set_max_bounces(self.h, b)
     def enable_white_furnace(self, e): self.lib.ref_enable_white_furnace(self.h, int(e))
     def set_blue_noise(self, e): self.lib.ref_set_sampler(self.h, int(e))
+
+    def sampler_tables(self):
+        """(sobol[65536], scrambling[131072], ranking[131072]) int32 copies of the tables the reference compiled in."""
+        ps = [C.POINTER(C.c_int)() for _ in range(3)]
+        self.lib.ref_sampler_tables(*[C.byref(p) for p in ps])
+        return tuple(np.ctypeslib.as_array(p, shape=(n,)).astype(np.int32) for p, n in zip(ps, (65536, 131072, 131072)))
     def enable_denoiser(self, e): self.lib.ref_enable_denoiser(self.h, int(e))
     def set_aov(self, a): self.lib.ref_set_aov(self.h, int(a))
     def set_row_sample(self, first, step): self.lib.ref_set_row_sample(self.h, first, step)

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("RT_B200_LIB", os.path.join(HERE, "librt_b200.so"))   
 MAX_BOUNCES = 255
 
 OPT_WHITE_FURNACE, OPT_SAMPLER, OPT_AOV, OPT_DENOISER = 0, 1, 2, 3
+BN_SOBOL_COUNT, BN_TILE_COUNT = 65536, 131072
 OPT_COUNT_TRAVERSAL, OPT_KERNEL_TIMING, OPT_TRAVERSAL, OPT_FUSION, OPT_REFILL_MIN = 16, 17, 18, 19, 20
 OPT_AOV_ALWAYS, OPT_SMEM_BVH, OPT_OVERLAP, OPT_GRAPH = 21, 22, 23, 24
 KERNEL_CLASSES = ["raygen", "intersect", "miss", "hit", "intersect_shadow", "accumulate", "extend_shade",
@@ -23,6 +24,7 @@ KERNEL_CLASSES = ["raygen", "intersect", "miss", "hit", "intersect_shadow", "acc
 
 # every symbol include/rt_b200.h declares
 SYMBOLS = ["rt_create", "rt_destroy", "rt_last_error", "rt_set_partition", "rt_upload_scene", "rt_set_camera", "rt_set_option",
+           "rt_upload_sampler_tables",
            "rt_reset", "rt_advance_sample_count", "rt_generate_rays", "rt_intersect", "rt_compute_aovs", "rt_shade_miss",
            "rt_clear_outgoing_counter", "rt_clear_shadow_counter", "rt_shade_hits", "rt_intersect_shadow",
            "rt_accumulate_direct", "rt_denoise", "rt_copy_history", "rt_resolve", "rt_resolve_async", "rt_resolve_wait", "rt_extend_shade", "rt_shadow_accumulate",
@@ -72,6 +74,7 @@ def load_library():
     L.rt_upload_scene.argtypes = [C.c_void_p, C.POINTER(RtSceneDesc)]
     L.rt_set_camera.argtypes = [C.c_void_p, C.c_void_p]
     L.rt_set_option.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    L.rt_upload_sampler_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     for name in ("rt_destroy", "rt_reset", "rt_advance_sample_count", "rt_generate_rays", "rt_compute_aovs", "rt_clear_shadow_counter",
                  "rt_intersect_shadow", "rt_accumulate_direct", "rt_denoise", "rt_copy_history", "rt_sync"):
         getattr(L, name).argtypes = [C.c_void_p]
@@ -158,6 +161,13 @@ class Context:
         self._ck(self.lib.rt_set_camera(self.h, c.ctypes.data))
 
     def set_option(self, key, value): self._ck(self.lib.rt_set_option(self.h, key, int(value)))
+
+    def upload_sampler_tables(self, sobol, scrambling, ranking):
+        """The blue-noise sampler's tables (utils/blue_noise_sampler.hpp in the reference); then set_option(OPT_SAMPLER, 1)."""
+        t = [np.ascontiguousarray(a, dtype=np.int32) for a in (sobol, scrambling, ranking)]
+        if [a.size for a in t] != [BN_SOBOL_COUNT, BN_TILE_COUNT, BN_TILE_COUNT]:
+            raise ValueError("sampler tables must have 65536, 131072 and 131072 entries")
+        self._ck(self.lib.rt_upload_sampler_tables(self.h, *[a.ctypes.data for a in t]))
 
     # ---- Integrator protected steps
     def reset(self): self._ck(self.lib.rt_reset(self.h))

@@ -77,6 +77,22 @@ __device__ __forceinline__ float sample_random(uint32_t pixel_seed, uint32_t bou
 }
 enum { SAMPLE_LAYER = 1, SAMPLE_U = 2, SAMPLE_V = 3, SAMPLE_LIGHT = 4 };
 
+// kernels/common/sampling.h:40-61 (kBlueNoise).  `bn` is the caller's three tables back to back (rt_upload_sampler_tables):
+// sobol_256spp_256d[65536] | scramblingTile[131072] | rankingTile[131072].  The ranking tile is indexed with the
+// UN-wrapped dimension (sampling.h:50), which runs past the table for the last tile pixels once the dimension exceeds 7;
+// those reads return 0 here (include/rt_b200.h).
+__device__ __forceinline__ float sample_blue_noise(const int* __restrict__ bn, uint32_t px, uint32_t py, uint32_t sample_index, uint32_t dim)
+{
+    int pixel_i = (int)px & 127, pixel_j = (int)py & 127;
+    int sample = (int)sample_index & 255, d = (int)dim & 255;
+    int tile = (pixel_i + pixel_j * 128) * 8;
+    int ri = d + tile;
+    int ranked = sample ^ (ri < RT_BN_TILE_COUNT ? __ldg(bn + RT_BN_SOBOL_COUNT + RT_BN_TILE_COUNT + ri) : 0);
+    int value = __ldg(bn + d + ranked * 256);
+    value = value ^ __ldg(bn + RT_BN_SOBOL_COUNT + (d % 8) + tile);
+    return (0.5f + (float)value) / 256.0f;
+}
+
 // ---------------------------------------------------------------------------- ray generation
 struct RayGenConsts
 {

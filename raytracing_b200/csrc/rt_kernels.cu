@@ -95,6 +95,7 @@ struct FrameParams
 {
     uint32_t width, height, rank, world, n_local;
     int white_furnace;
+    const int* bn;                 // blue-noise sampler tables (kBlueNoise) or nullptr (kRandom)
     const FrameDyn* dyn;
 };
 
@@ -431,7 +432,8 @@ __device__ __forceinline__ void shade_hit(const DevScene& sc, const FrameParams&
     }
     uint32_t pixel_seed = sample_seed_pixel(px, py, p.dyn->sample_idx);
     {   // direct lighting (next-event estimation on analytic lights)
-        float s_light = sample_random(pixel_seed, bounce, SAMPLE_LIGHT);
+        float s_light = p.bn ? sample_blue_noise(p.bn, px, py, p.dyn->sample_idx, bounce * 5u + SAMPLE_LIGHT)
+                             : sample_random(pixel_seed, bounce, SAMPLE_LIGHT);
         f3 outgoing; float pdf, distance_to_light;
         f3 light_radiance = light_sample(sc, position, s_light, outgoing, distance_to_light, pdf);
         // light_sample = L * throughput * brdf / pdf * max(n.l, 0); a shadow ray is spawned iff pdf > 0 and
@@ -449,8 +451,19 @@ __device__ __forceinline__ void shade_hit(const DevScene& sc, const FrameParams&
         }
     }
     {   // BSDF sampling
-        f2 s; s.x = sample_random(pixel_seed, bounce, SAMPLE_U); s.y = sample_random(pixel_seed, bounce, SAMPLE_V);
-        float s1 = sample_random(pixel_seed, bounce, SAMPLE_LAYER);
+        f2 s; float s1;
+        if (p.bn)
+        {
+            const uint32_t sample_idx = p.dyn->sample_idx;
+            s.x = sample_blue_noise(p.bn, px, py, sample_idx, bounce * 5u + SAMPLE_U);
+            s.y = sample_blue_noise(p.bn, px, py, sample_idx, bounce * 5u + SAMPLE_V);
+            s1 = sample_blue_noise(p.bn, px, py, sample_idx, bounce * 5u + SAMPLE_LAYER);
+        }
+        else
+        {
+            s.x = sample_random(pixel_seed, bounce, SAMPLE_U); s.y = sample_random(pixel_seed, bounce, SAMPLE_V);
+            s1 = sample_random(pixel_seed, bounce, SAMPLE_LAYER);
+        }
         float pdf = 0.0f, offset = 1.0f;
         f3 outgoing = mk3(0.0f, 0.0f, 0.0f);
         f3 bxdf = sample_bxdf(s1, s, material, normal, incoming, p.white_furnace != 0, outgoing, pdf, offset);
@@ -1110,6 +1123,7 @@ struct rt_ctx
     RtCamera prev_camera = {}, aov_prev_camera = {};
     DevCounters* counters = nullptr;
     FrameDyn* d_dyn = nullptr;
+    int* d_bn = nullptr;           // sobol | scrambling | ranking (rt_upload_sampler_tables)
     void* scratch = nullptr; size_t scratch_bytes = 0;
 
     // scene
@@ -1198,7 +1212,7 @@ FrameParams frame_params(const rt_ctx* c)
 {
     FrameParams p;
     p.width = c->width; p.height = c->height; p.rank = c->rank; p.world = c->world; p.n_local = c->n_local;
-    p.white_furnace = c->white_furnace; p.dyn = c->d_dyn;
+    p.white_furnace = c->white_furnace; p.bn = c->sampler ? c->d_bn : nullptr; p.dyn = c->d_dyn;
     return p;
 }
 
@@ -1353,7 +1367,7 @@ int rt_destroy(rt_ctx* c)
     for (int i = 0; i < 2; ++i) { cudaFree(c->q.A[i]); cudaFree(c->q.B[i]); cudaFree(c->q.C[i]); }
     cudaFree(c->q.sA); cudaFree(c->q.sB); cudaFree(c->q.sC); cudaFree(c->q.hits); cudaFree(c->q.shadow_flags);
     cudaFree(c->q.hitq); cudaFree(c->q.missq);
-    cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->resolved2); cudaFree(c->counters); cudaFree(c->scratch); cudaFree(c->d_dyn);
+    cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->resolved2); cudaFree(c->counters); cudaFree(c->scratch); cudaFree(c->d_dyn); cudaFree(c->d_bn);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->graph) cudaGraphDestroy(c->graph);
     if (c->shadow_stream) { cudaStreamSynchronize(c->shadow_stream); cudaStreamDestroy(c->shadow_stream); }
@@ -1496,8 +1510,10 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
     {
     case RT_OPT_WHITE_FURNACE: c->white_furnace = value != 0; return RT_OK;
     case RT_OPT_SAMPLER:
-        if (value != 0) RT_FAIL(c, RT_ERR_UNSUPPORTED, "blue-noise sampler is not implemented yet (SURVEY 8f rank 3)");
-        c->sampler = 0; return RT_OK;
+        if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "sampler type must be 0 (kRandom) or 1 (kBlueNoise)");
+        if (value == 1 && !c->d_bn)
+            RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "kBlueNoise needs the sampler tables: call rt_upload_sampler_tables first");
+        c->sampler = (int)value; return RT_OK;
     case RT_OPT_AOV:
         if (value > 4) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "AOV index out of range");
         c->aov = (int)value;
@@ -1529,6 +1545,25 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
         c->refill_min = (int)value; return RT_OK;
     }
     RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "unknown option key %d", key);
+}
+
+int rt_upload_sampler_tables(rt_ctx* c, const int32_t* sobol, const int32_t* scrambling, const int32_t* ranking)
+{
+    RT_CHECK_CTX(c);
+    if (!sobol || !scrambling || !ranking) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_sampler_tables: null table");
+    for (int i = 0; i < RT_BN_TILE_COUNT; ++i)
+        if (ranking[i] < 0 || ranking[i] > 255)
+            RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_sampler_tables: ranking entry %d is %d, outside 0..255", i, ranking[i]);
+    RT_CUDA(c, cudaSetDevice(c->device));
+    int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_;
+    RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)RT_BN_SOBOL_COUNT + 2 * (size_t)RT_BN_TILE_COUNT;
+    if (!c->d_bn) RT_CUDA(c, cudaMalloc(&c->d_bn, n * sizeof(int)));
+    RT_CUDA(c, cudaMemcpy(c->d_bn, sobol, RT_BN_SOBOL_COUNT * sizeof(int), cudaMemcpyHostToDevice));
+    RT_CUDA(c, cudaMemcpy(c->d_bn + RT_BN_SOBOL_COUNT, scrambling, RT_BN_TILE_COUNT * sizeof(int), cudaMemcpyHostToDevice));
+    RT_CUDA(c, cudaMemcpy(c->d_bn + RT_BN_SOBOL_COUNT + RT_BN_TILE_COUNT, ranking, RT_BN_TILE_COUNT * sizeof(int), cudaMemcpyHostToDevice));
+    ++c->config_gen;
+    return RT_OK;
 }
 
 int rt_reset(rt_ctx* c)

@@ -68,6 +68,12 @@ void CUDAPathTraceIntegrator::SetSamplerType(SamplerType sampler_type)
     RequestReset();
 }
 
+void CUDAPathTraceIntegrator::SetBlueNoiseTables(const int* sobol_256spp_256d, const int* scrambling_tile, const int* ranking_tile)
+{
+    Check(rt_upload_sampler_tables(ctx_, sobol_256spp_256d, scrambling_tile, ranking_tile), "SetBlueNoiseTables");
+    if (sampler_type_ == SamplerType::kBlueNoise) RequestReset();
+}
+
 void CUDAPathTraceIntegrator::SetAOV(AOV aov)
 {
     if (aov == aov_) return;

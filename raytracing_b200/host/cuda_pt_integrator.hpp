@@ -15,7 +15,8 @@
  *                     the stepwise schedule, bit for bit.
  *   kStepwise         one kernel per virtual, like the OpenCL backend.
  * AOVs (ComputeAOVs) are produced inside the bounce-0 shading pass, and only when SetAOV selected a view other than
- * the shaded colour or the denoiser is on.  SetSamplerType(kBlueNoise) is not supported (throws).
+ * the shaded colour or the denoiser is on.  SetSamplerType(kBlueNoise) needs the sampler's three tables first
+ * (SetBlueNoiseTables; the OpenCL backend reads them from utils/blue_noise_sampler.hpp, cl_pt_integrator.cpp:222-235).
  * The last constructor argument of the OpenCL backend is a GL texture to resolve into
  * (cl_pt_integrator.hpp:33-34); here ResolveRadiance() writes to a host RGBA32F image instead
  * (SetResolveTarget), or only resolves on the device if none is set.
@@ -45,6 +46,8 @@ public:
     void SetAOV(AOV aov) override;
     void EnableDenoiser(bool enable) override;
 
+    // sobol_256spp_256d[256*256], scramblingTile[128*128*8], rankingTile[128*128*8]; copied to the device
+    void SetBlueNoiseTables(const int* sobol_256spp_256d, const int* scrambling_tile, const int* ranking_tile);
     void SetResolveTarget(float* host_rgba) { resolve_target_ = host_rgba; }
     void SetSchedule(Schedule s) { schedule_ = s; }
     rt_ctx* Context() const { return ctx_; }

@@ -125,6 +125,11 @@ int rth_render_set_sampler(void* h, int blue_noise)
     try { ((RenderHandle*)h)->render->GetIntegrator().SetSamplerType(blue_noise ? Integrator::SamplerType::kBlueNoise : Integrator::SamplerType::kRandom); return 0; }
     catch (std::exception& ex) { g_error = ex.what(); return -1; }
 }
+int rth_render_set_sampler_tables(void* h, const int* sobol, const int* scrambling, const int* ranking)
+{
+    try { static_cast<CUDAPathTraceIntegrator&>(((RenderHandle*)h)->render->GetIntegrator()).SetBlueNoiseTables(sobol, scrambling, ranking); return 0; }
+    catch (std::exception& ex) { g_error = ex.what(); return -1; }
+}
 int rth_render_frame(void* h)
 {
     try { ((RenderHandle*)h)->render->RenderFrame(); return 0; } catch (std::exception& e) { g_error = e.what(); return -1; }

@@ -40,6 +40,7 @@ def load_library():
     L.rth_render_set_max_bounces.argtypes = [C.c_void_p, C.c_uint32]
     L.rth_render_enable_white_furnace.argtypes = [C.c_void_p, C.c_int]
     L.rth_render_set_sampler.argtypes = [C.c_void_p, C.c_int]
+    L.rth_render_set_sampler_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.rth_render_frame.argtypes = [C.c_void_p]
     L.rth_render_request_reset.argtypes = [C.c_void_p]
     L.rth_render_nodes.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
@@ -139,6 +140,11 @@ class HostRender:
 
     def set_blue_noise(self, e):
         if self.L.rth_render_set_sampler(self.h, int(e)) != 0:
+            raise _err(self.L)
+
+    def set_blue_noise_tables(self, sobol, scrambling, ranking):
+        t = [np.ascontiguousarray(a, dtype=np.int32) for a in (sobol, scrambling, ranking)]
+        if self.L.rth_render_set_sampler_tables(self.h, *[a.ctypes.data for a in t]) != 0:
             raise _err(self.L)
 
     def render_frame(self):

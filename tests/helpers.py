@@ -40,3 +40,19 @@ def bits(a):
     u = np.ascontiguousarray(a, dtype="<f4").copy().view("<u4")
     u[(u & 0x7FFFFFFF) > 0x7F800000] = 0x7FC00000
     return u
+
+
+def synthetic_sampler_tables(seed=20260923):
+    """Seeded stand-ins for the blue-noise sampler's tables (same shapes and value ranges as the reference's
+    utils/blue_noise_sampler.hpp, which is reference data and not committed here): any tables exercise the same lookups."""
+    rng = np.random.default_rng(seed)
+    return (rng.integers(0, 256, 65536, dtype=np.int32), rng.integers(0, 256, 131072, dtype=np.int32),
+            rng.integers(0, 256, 131072, dtype=np.int32))
+
+
+def reference_sampler_tables():
+    """The reference's own tables, read out of oracle/_ref/libref.so when that library was built; else None."""
+    from oracle import refbind
+    if not refbind.available():
+        return None
+    return refbind.RefRenderer().sampler_tables()

@@ -14,7 +14,7 @@ import pytest
 from oracle.orcbind import Oracle
 from raytracing_b200 import capi
 from raytracing_b200.camera import default_camera
-from tests.helpers import bits, golden_files, load_golden, scene
+from tests.helpers import bits, golden_files, load_golden, reference_sampler_tables, scene, synthetic_sampler_tables
 
 pytestmark = pytest.mark.gpu
 
@@ -288,6 +288,49 @@ def test_textured_materials_match_oracle():
         c.destroy()
 
 
+@pytest.mark.parametrize("tables", ["synthetic", "reference"])
+@pytest.mark.parametrize("name,w,h,mb,wf", [
+    ("CornellBox", 160, 136, 3, False),      # > 128 x 128: all tile pixels, incl. those whose ranking index runs past the table
+    ("ShaderBalls", 272, 144, 8, False),
+    ("CornellBox", 64, 64, 5, True),
+])
+def test_blue_noise_sampler_matches_oracle(name, w, h, mb, wf, tables):
+    """SetSamplerType(kBlueNoise): all three schedules vs the oracle (itself pinned to hit_surface.cl -DBLUE_NOISE_SAMPLER
+    in tests/test_oracle_vs_ref.py), three progressive samples, then back to kRandom."""
+    t = synthetic_sampler_tables() if tables == "synthetic" else reference_sampler_tables()
+    if t is None:
+        pytest.skip("oracle/_ref/libref.so (the carrier of the reference's tables) is not built here")
+    sc = scene(name); cam = default_camera(w, h)
+    o = Oracle(sc)
+    ctxs = {}
+    for mode in ("fused", "monolithic", "stepwise"):
+        c = make_ctx(name, w, h)
+        c.set_option(capi.OPT_FUSION, 1 if mode == "monolithic" else 0)
+        c.set_option(capi.OPT_WHITE_FURNACE, int(wf))
+        c.upload_sampler_tables(*t)
+        c.set_option(capi.OPT_SAMPLER, 1)
+        c.reset()
+        ctxs[mode] = c
+    try:
+        o.set_sampler_tables(t)
+        oacc = np.zeros((h, w, 4), dtype="<f4")
+        for sample in range(3):
+            oacc, _, ost = o.render(cam, w, h, mb, sample_idx=sample, white_furnace=wf, radiance=oacc)
+            for mode, c in ctxs.items():
+                c.integrate_stepwise(mb) if mode == "stepwise" else c.integrate(mb)
+                check_stats(c.frame_stats(), ost, mb)
+                assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(oacc[..., :3])), (mode, sample)
+        o.set_sampler_tables(None)
+        plain, _, _ = o.render(cam, w, h, mb, sample_idx=0, white_furnace=wf)
+        c = ctxs["fused"]
+        c.set_option(capi.OPT_SAMPLER, 0); c.reset(); c.integrate(mb)      # switching back re-captures the frame graph
+        assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(plain[..., :3]))
+    finally:
+        o.set_sampler_tables(None)
+        for c in ctxs.values():
+            c.destroy()
+
+
 @pytest.mark.parametrize("n_tris", [1, 2])
 def test_root_leaf_bvh_and_tiny_images(n_tris):
     """A BVH that is a single leaf, a 1x1 image, and a partition where one rank owns no row at all."""
@@ -322,7 +365,17 @@ def test_error_behaviour():
     with pytest.raises(capi.RtError):
         c.integrate(3)                        # no camera yet
     with pytest.raises(capi.RtError):
-        c.set_option(capi.OPT_SAMPLER, 1)     # blue noise not implemented: loud, not silent
+        c.set_option(capi.OPT_SAMPLER, 1)     # kBlueNoise without its tables: loud, not silent
+    sob, scr, rank = synthetic_sampler_tables()
+    bad_rank = rank.copy(); bad_rank[77] = 256
+    with pytest.raises(capi.RtError):
+        c.upload_sampler_tables(sob, scr, bad_rank)   # would index past the sobol table
+    with pytest.raises(ValueError):
+        c.upload_sampler_tables(sob[:100], scr, rank)
+    c.upload_sampler_tables(sob, scr, rank)
+    c.set_option(capi.OPT_SAMPLER, 1)
+    with pytest.raises(capi.RtError):
+        c.set_option(capi.OPT_SAMPLER, 2)
     c.destroy()
     c = capi.Context(32, 32, rank=1, world=2)
     with pytest.raises(capi.RtError):

@@ -10,7 +10,7 @@ import pytest
 from oracle.orcbind import Oracle
 from raytracing_b200 import hostapi, scene_io
 from raytracing_b200.camera import default_camera
-from tests.helpers import bits, scene
+from tests.helpers import bits, scene, synthetic_sampler_tables
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PROC_OBJ = os.path.join(REPO, "tests", "golden", "scenes", "procedural.obj")
@@ -169,9 +169,21 @@ def test_render_kcuda_backend_matches_oracle(tmp_path, stepwise):
         img = r.image()
         assert np.array_equal(bits(img[..., :3]), bits(expect)), sample
         assert (img[..., 3] == 1.0).all()
-    # option setters keep the reference behaviour: unsupported sampler fails loudly, white furnace re-renders from scratch
+    # option setters keep the reference behaviour: kBlueNoise without its tables fails loudly; with them the next frame
+    # restarts the accumulation with the other sampler; white furnace re-renders from scratch
     with pytest.raises(hostapi.HostError):
         r.set_blue_noise(True)
+    tables = synthetic_sampler_tables()
+    r.set_blue_noise_tables(*tables)
+    r.set_blue_noise(True)
+    r.render_frame()
+    try:
+        o.set_sampler_tables(tables)
+        bn, _, _ = o.render(cam, w, h, mb, sample_idx=0)
+    finally:
+        o.set_sampler_tables(None)
+    assert np.array_equal(bits(r.image()[..., :3]), bits(bn[..., :3] / (bn[..., :3] + np.float32(1.0))))
+    r.set_blue_noise(False)
     r.enable_white_furnace(True)
     r.render_frame()
     wf, _, _ = o.render(cam, w, h, mb, sample_idx=0, white_furnace=True)

@@ -85,6 +85,42 @@ def test_textured_materials_bit_exact_vs_reference_kernels():
     r.close()
 
 
+@pytest.mark.parametrize("name,w,h,mb,wf", [
+    ("CornellBox", 160, 136, 3, False),        # > 128 x 128: every tile pixel, incl. the ones whose ranking index runs past the table
+    ("ShaderBalls", 144, 130, 8, False),
+    ("CornellBox", 64, 64, 4, True),
+])
+def test_blue_noise_sampler_bit_exact_vs_reference_kernels(name, w, h, mb, wf):
+    """SamplerType::kBlueNoise (sampling.h:40-61): the restatement with the reference's own tables against
+    hit_surface.cl built with -DBLUE_NOISE_SAMPLER, three progressive samples."""
+    sc = scene(name)
+    r = refbind.RefRenderer().open_arrays(sc)
+    r.begin(w, h)
+    cam = default_camera(w, h)
+    r.set_camera(cam); r.set_max_bounces(mb); r.enable_white_furnace(wf); r.set_blue_noise(True)
+    o = Oracle(sc)
+    tables = r.sampler_tables()
+    assert 0 <= tables[2].min() and tables[2].max() <= 255
+    try:
+        o.set_sampler_tables(tables)
+        acc = np.zeros((h, w, 4), dtype="<f4")
+        for sample in range(3):
+            r.integrate()
+            acc, hits, st = o.render(cam, w, h, mb, sample_idx=sample, white_furnace=wf, radiance=acc)
+            rs = r.stats()
+            for k in ("n_ext", "n_miss", "n_hit", "n_shadow", "n_cont", "n_unoccluded"):
+                assert np.array_equal(st[k][: mb + 1], rs[k][: mb + 1]), (k, sample)
+            assert np.array_equal(bits(acc[..., :3]), bits(r.radiance()[..., :3]))
+        # and the sampler did change the image
+        o.set_sampler_tables(None)
+        plain, _, _ = o.render(cam, w, h, mb, sample_idx=0, white_furnace=wf)
+        first, _, _ = (o.set_sampler_tables(tables), o.render(cam, w, h, mb, sample_idx=0, white_furnace=wf))[1]
+        assert not np.array_equal(bits(plain), bits(first))
+    finally:
+        o.set_sampler_tables(None)
+        r.close()
+
+
 def test_math_library_sensitivity_is_small():
     """The OpenCL driver's libm is unpinned.  Swapping include/rt_math.h for glibc's libm inside the
     reference kernels must leave all but a small fraction of pixels within 1e-4 relative."""
