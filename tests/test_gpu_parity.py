@@ -353,6 +353,26 @@ def test_root_leaf_bvh_and_tiny_images(n_tris):
     assert np.array_equal(bits(out[..., :3]), bits(orad[..., :3]))
 
 
+def test_scene_reupload_and_camera_change_on_one_context():
+    """UploadGPUData twice and SetCameraData between frames on the same context (the frame graph is re-captured when a
+    launch argument changes, and only its per-frame constants are refreshed when the camera moves)."""
+    w, h, mb = 200, 112, 5
+    c = capi.Context(w, h)
+    cams = [default_camera(w, h), default_camera(w, h, position=(0.3, -1.4, 1.2))]
+    for name in ("CornellBox", "ShaderBalls", "CornellBox"):
+        sc = scene(name); o = Oracle(sc)
+        c.upload_scene(sc)
+        for cam in cams:
+            c.set_camera(cam); c.reset()
+            acc = np.zeros((h, w, 4), dtype="<f4")
+            for sample in range(2):
+                c.integrate(mb)
+                acc, _, ost = o.render(cam, w, h, mb, sample_idx=sample, radiance=acc)
+                check_stats(c.frame_stats(), ost, mb)
+                assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(acc[..., :3])), (name, sample)
+    c.destroy()
+
+
 def test_error_behaviour():
     c = capi.Context(32, 32)
     with pytest.raises(capi.RtError):
