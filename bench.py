@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--traversal", type=int, default=None, help="RT_OPT_TRAVERSAL override (0 literal, 1 fast, 2 per-lane refill)")
     ap.add_argument("--refill-min", type=int, default=None, help="RT_OPT_REFILL_MIN override")
     ap.add_argument("--no-graph", action="store_true", help="RT_OPT_GRAPH=0: launch every kernel of the frame individually")
+    ap.add_argument("--no-pdl", action="store_true", help="RT_OPT_PDL=0: no programmatic dependent launch between the kernels of a frame")
     ap.add_argument("--no-overlap", action="store_true", help="RT_OPT_OVERLAP=0: shadow pass on the render stream (no concurrency with the next traversal)")
     ap.add_argument("--no-smem-bvh", action="store_true", help="RT_OPT_SMEM_BVH=0: fetch BVH records through L1 even for small scenes")
     ap.add_argument("--copies", type=int, default=183, help="Synthetic10M: number of ShaderBalls copies (183 = 10 026 570 triangles)")
@@ -243,6 +244,8 @@ def main():
         ctx.set_option(capi.OPT_GRAPH, 0)
     if args.no_overlap:
         ctx.set_option(capi.OPT_OVERLAP, 0)
+    if args.no_pdl:
+        ctx.set_option(capi.OPT_PDL, 0)
     if args.no_smem_bvh:
         ctx.set_option(capi.OPT_SMEM_BVH, 0)
     if args.refill_min is not None:

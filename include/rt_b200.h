@@ -78,6 +78,8 @@ typedef enum RtOption {
                                    of bounce b+1; 0: everything on one in-order stream */
     RT_OPT_GRAPH = 24,          /* 1 (default): rt_integrate replays the frame as one CUDA graph (captured on first use, re-captured when an
                                    option, the scene or the partition changes; the camera and sample index are a node-parameter update) */
+    RT_OPT_PDL = 25,            /* 1 (default): the traversal and shading kernels of a frame are chained by programmatic dependent launch
+                                   (a kernel's CTAs start and stage the BVH while the previous kernel drains) */
     RT_OPT_REFILL_MIN = 20,     /* traversal mode 2: refill a warp when at least this many lanes are idle (1..32) */
     RT_OPT_FUSION = 19          /* rt_extend_shade: 0 = traversal kernel + hit/miss queue compaction + shading kernel
                                    (default), 1 = one monolithic kernel; results are bit-identical */

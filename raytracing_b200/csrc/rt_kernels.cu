@@ -182,6 +182,14 @@ __device__ __forceinline__ void tma_stage_bvh(float4* dst, const DevScene& sc, u
                      : "=r"(done) : "r"(bar), "r"(0) : "memory");
 }
 
+// Programmatic dependent launch (RT_OPT_PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start (launch its CTAs, stage the BVH) while the previous kernel of the stream is still draining; pdl_wait() blocks
+// until that kernel has completed and its memory is visible, and is a no-op for a normal launch.  Every persistent
+// kernel lets ITS dependent start as early as possible: its CTAs are all resident by then (persistent_grid), so
+// the dependent's CTAs only take the slots that exiting CTAs free.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <bool SMEM>
 __device__ __forceinline__ float4 ld_bvh(const float4* p) { return SMEM ? *p : __ldg(p); }
 
@@ -693,6 +701,7 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameP
     extern __shared__ __align__(128) float4 s_bvh[];
     __shared__ uint64_t s_mbar;
     if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    pdl_wait(); pdl_launch_dependents();
     const uint32_t n = ctr->emit[bounce].shadow;
     const int lane = threadIdx.x & 31;
     uint32_t nv = 0, nt = 0;
@@ -740,6 +749,7 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_closest(FrameParam
     extern __shared__ __align__(128) float4 s_bvh[];
     __shared__ uint64_t s_mbar;
     if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    pdl_wait(); pdl_launch_dependents();
     const uint32_t n = *in_count_ptr(ctr, bounce);
     const int in = bounce & 1;
     const int lane = threadIdx.x & 31;
@@ -980,6 +990,7 @@ __global__ void __launch_bounds__(256) k_trace_refill(FrameParams p, DevScene sc
 // ShadeSurfaceHits over the hit queue, then ShadeMissedRays over the miss queue (independent pixels).
 __global__ void __launch_bounds__(256, RT_MINB_SHADE) k_shade_queues(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce, AovParams aov)
 {
+    pdl_wait(); pdl_launch_dependents();
     const uint32_t n_hit = ctr->hm[bounce].hit, n_miss = ctr->hm[bounce].miss;
     const uint32_t hit_span = (n_hit + 31u) & ~31u;            // warps never mix hits and misses
     const uint32_t total = hit_span + n_miss;
@@ -1123,6 +1134,7 @@ struct rt_ctx
     RtCamera prev_camera = {}, aov_prev_camera = {};
     DevCounters* counters = nullptr;
     FrameDyn* d_dyn = nullptr;
+    bool pdl = true;               // RT_OPT_PDL
     int* d_bn = nullptr;           // sobol | scrambling | ranking (rt_upload_sampler_tables)
     struct Occupancy { const void* kernel; size_t smem; int per_sm; };
     std::vector<Occupancy> occupancy;   // resident CTAs per SM of each persistent kernel (persistent_grid)
@@ -1272,6 +1284,19 @@ int persistent_grid(rt_ctx* c, const void* kernel, size_t dyn_smem)
     return g < need ? g : need;
 }
 #define RT_PGRID(c, kern, smem) persistent_grid(c, (const void*)(kern), smem)
+
+// <<<grid, 256, smem, stream>>> with the programmatic-dependent-launch attribute when RT_OPT_PDL is on
+template <class... KArgs, class... Args>
+cudaError_t launch_chain(rt_ctx* c, void (*kernel)(KArgs...), int grid, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    if (c->pdl && !c->kernel_timing) { cfg.attrs = &attr; cfg.numAttrs = 1; }
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // Bytes of dynamic shared memory for the TMA-staged BVH, or 0 when staging does not apply: only the optimised
 // traversal (mode 1) on a scene whose records fit 40 KB (5 resident CTAs x 40 KB stay under the 227 KB of an SM).
@@ -1552,6 +1577,7 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
     case RT_OPT_COUNT_TRAVERSAL: c->count_traversal = value != 0; return RT_OK;
     case RT_OPT_KERNEL_TIMING: c->kernel_timing = value != 0; return RT_OK;
     case RT_OPT_GRAPH: c->use_graph = value != 0; return RT_OK;
+    case RT_OPT_PDL: c->pdl = value != 0; return RT_OK;
     case RT_OPT_SMEM_BVH: c->smem_bvh = value != 0; return RT_OK;
     case RT_OPT_OVERLAP: { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; c->overlap = value != 0; return RT_OK; }
     case RT_OPT_FUSION:
@@ -1741,13 +1767,13 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
         TimedLaunch t(c, RT_K_TRACE_CLOSEST);
         size_t stage = smem_stage_bytes(c);
         if (c->count_traversal) k_trace_closest<true, false><<<RT_PGRID(c, (k_trace_closest<true, false>), 0), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
-        else if (stage) k_trace_closest<false, true><<<RT_PGRID(c, (k_trace_closest<false, true>), stage), 256, stage, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
-        else k_trace_closest<false, false><<<RT_PGRID(c, (k_trace_closest<false, false>), 0), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
+        else if (stage) launch_chain(c, k_trace_closest<false, true>, RT_PGRID(c, (k_trace_closest<false, true>), stage), stage, c->stream, frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
+        else launch_chain(c, k_trace_closest<false, false>, RT_PGRID(c, (k_trace_closest<false, false>), 0), 0, c->stream, frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
         int rc = post_launch(c, "k_trace_closest"); if (rc) return rc;
     }
     { int rc = join_shadow(c); if (rc) return rc; }     // the shading pass accumulates into radiance and refills the shadow queue
     TimedLaunch t(c, RT_K_SHADE_QUEUES);
-    k_shade_queues<<<RT_PGRID(c, k_shade_queues, 0), 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, aov_params(c));
+    launch_chain(c, k_shade_queues, RT_PGRID(c, k_shade_queues, 0), 0, c->stream, frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, aov_params(c));
     return post_launch(c, "k_shade_queues");
 }
 
