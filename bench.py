@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--refill-min", type=int, default=None, help="RT_OPT_REFILL_MIN override")
     ap.add_argument("--no-graph", action="store_true", help="RT_OPT_GRAPH=0: launch every kernel of the frame individually")
     ap.add_argument("--no-pdl", action="store_true", help="RT_OPT_PDL=0: no programmatic dependent launch between the kernels of a frame")
+    ap.add_argument("--overlap", type=int, default=2, help="RT_OPT_OVERLAP: 2 shadow pass inside the next traversal kernel (default), 1 second stream, 0 none")
     ap.add_argument("--no-overlap", action="store_true", help="RT_OPT_OVERLAP=0: shadow pass on the render stream (no concurrency with the next traversal)")
     ap.add_argument("--no-smem-bvh", action="store_true", help="RT_OPT_SMEM_BVH=0: fetch BVH records through L1 even for small scenes")
     ap.add_argument("--copies", type=int, default=183, help="Synthetic10M: number of ShaderBalls copies (183 = 10 026 570 triangles)")
@@ -242,8 +243,7 @@ def main():
         ctx.set_option(capi.OPT_TRAVERSAL, args.traversal)
     if args.no_graph:
         ctx.set_option(capi.OPT_GRAPH, 0)
-    if args.no_overlap:
-        ctx.set_option(capi.OPT_OVERLAP, 0)
+    ctx.set_option(capi.OPT_OVERLAP, 0 if args.no_overlap else args.overlap)
     if args.no_pdl:
         ctx.set_option(capi.OPT_PDL, 0)
     if args.no_smem_bvh:
@@ -312,8 +312,8 @@ def main():
     launches = ctx.launch_count() - launches0
     sampler.join(timeout=2)
     # Per-kernel durations for the roofline.  In the timed region above the frame is ONE CUDA-graph launch and the shadow
-    # pass overlaps the next traversal on a second stream, so per-launch CUDA events are neither possible (graph) nor clean
-    # (concurrent kernels' durations include each other): the same K steps are run once more, in this same process, with
+    # pass of a bounce runs inside the next bounce's traversal kernel, so per-launch CUDA events are neither possible (graph)
+    # nor would they separate the two passes: the same K steps are run once more, in this same process, with
     # per-launch events on, individual launches and the overlap off.
     ctx.set_option(capi.OPT_KERNEL_TIMING, 1)
     ctx.set_option(capi.OPT_OVERLAP, 0)
@@ -327,7 +327,7 @@ def main():
     ktimes = ctx.kernel_times()
     ctx.set_option(capi.OPT_KERNEL_TIMING, 0)
     if not args.no_overlap:
-        ctx.set_option(capi.OPT_OVERLAP, 1)
+        ctx.set_option(capi.OPT_OVERLAP, args.overlap)
     value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
 
     # ---- end to end through the public API with HOST buffers: camera H2D, frame, gather, resolve, image D2H
@@ -410,7 +410,8 @@ def main():
                          "whole_frame_algorithmic_GBs": alg_total / (ms_per_step * 1e-3) / 1e9},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
             "kernel_timing_note": "kernel_ms_per_step: CUDA events per launch over K extra steps of this run with individual launches and the "
-                                  "two-stream overlap disabled (in the timed region the frame is one CUDA-graph launch with two concurrent streams)",
+                                  "shadow pass as its own kernel (in the timed region the frame is one CUDA-graph launch in which the shadow pass of "
+                                  "bounce b runs inside the traversal kernel of bounce b+1)",
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:

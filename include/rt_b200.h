@@ -74,8 +74,12 @@ typedef enum RtOption {
                                    does; here they are skipped unless a view or the denoiser needs them) */
     RT_OPT_SMEM_BVH = 22,       /* 1 (default): scenes whose traversal records fit 40 KB are staged into shared memory by a TMA
                                    bulk copy at the start of every traversal kernel; 0: always fetch through L1 */
-    RT_OPT_OVERLAP = 23,        /* 1 (default): rt_shadow_accumulate(b) runs on a second stream and overlaps the closest-hit traversal
-                                   of bounce b+1; 0: everything on one in-order stream */
+    RT_OPT_OVERLAP = 23,        /* how the shadow pass of bounce b overlaps the closest-hit traversal of bounce b+1 (they are independent):
+                                   2 (default): rt_shadow_accumulate(b) is deferred and runs inside the traversal kernel of
+                                      rt_extend_shade(b+1) (one persistent kernel drains both queues); any other call that needs
+                                      its result launches it on its own first;
+                                   1: on a second stream, concurrently with the traversal kernel;
+                                   0: everything in call order on one in-order stream */
     RT_OPT_GRAPH = 24,          /* 1 (default): rt_integrate replays the frame as one CUDA graph (captured on first use, re-captured when an
                                    option, the scene or the partition changes; the camera and sample index are a node-parameter update) */
     RT_OPT_PDL = 25,            /* 1 (default): the traversal and shading kernels of a frame are chained by programmatic dependent launch
@@ -105,7 +109,8 @@ typedef struct RtFrameStats {
 typedef enum RtKernelClass {
     RT_K_RAYGEN = 0, RT_K_INTERSECT = 1, RT_K_MISS = 2, RT_K_HIT = 3, RT_K_INTERSECT_SHADOW = 4,
     RT_K_ACCUMULATE = 5, RT_K_EXTEND_SHADE = 6, RT_K_SHADOW_ACCUMULATE = 7, RT_K_RESOLVE = 8,
-    RT_K_AOV = 9, RT_K_MISC = 10, RT_K_TRACE_CLOSEST = 11, RT_K_SHADE_QUEUES = 12, RT_K_CLASS_COUNT = 13
+    RT_K_AOV = 9, RT_K_MISC = 10, RT_K_TRACE_CLOSEST = 11, RT_K_SHADE_QUEUES = 12, RT_K_TRACE_BOTH = 13,
+    RT_K_CLASS_COUNT = 14
 } RtKernelClass;
 
 /* ---- lifetime ------------------------------------------------------------------ */

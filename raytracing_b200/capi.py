@@ -20,7 +20,7 @@ BN_SOBOL_COUNT, BN_TILE_COUNT = 65536, 131072
 OPT_COUNT_TRAVERSAL, OPT_KERNEL_TIMING, OPT_TRAVERSAL, OPT_FUSION, OPT_REFILL_MIN = 16, 17, 18, 19, 20
 OPT_AOV_ALWAYS, OPT_SMEM_BVH, OPT_OVERLAP, OPT_GRAPH, OPT_PDL = 21, 22, 23, 24, 25
 KERNEL_CLASSES = ["raygen", "intersect", "miss", "hit", "intersect_shadow", "accumulate", "extend_shade",
-                  "shadow_accumulate", "resolve", "aov", "misc", "trace_closest", "shade_queues"]
+                  "shadow_accumulate", "resolve", "aov", "misc", "trace_closest", "shade_queues", "trace_both"]
 
 # every symbol include/rt_b200.h declares
 SYMBOLS = ["rt_create", "rt_destroy", "rt_last_error", "rt_set_partition", "rt_upload_scene", "rt_set_camera", "rt_set_option",

@@ -696,12 +696,9 @@ __global__ void __launch_bounds__(256) k_extend_shade(FrameParams p, DevScene sc
 
 // Fused IntersectShadowRays + AccumulateDirectSamples, persistent like k_extend_shade.
 template <bool COUNT, bool SMEM>
-__global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
+__device__ __forceinline__ void shadow_phase(const FrameParams& p, const DevScene& sc, int mode, const Queues& q, DevCounters* ctr, float4* radiance,
+                                             uint32_t bounce, const float4* s_bvh)
 {
-    extern __shared__ __align__(128) float4 s_bvh[];
-    __shared__ uint64_t s_mbar;
-    if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
-    pdl_wait(); pdl_launch_dependents();
     const uint32_t n = ctr->emit[bounce].shadow;
     const int lane = threadIdx.x & 31;
     uint32_t nv = 0, nt = 0;
@@ -736,6 +733,16 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameP
     if (COUNT) { warp_sum64(&ctr->nodes_shadow[bounce], nv); warp_sum64(&ctr->tris_shadow[bounce], nt); }
 }
 
+template <bool COUNT, bool SMEM>
+__global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
+{
+    extern __shared__ __align__(128) float4 s_bvh[];
+    __shared__ uint64_t s_mbar;
+    if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    pdl_wait(); pdl_launch_dependents();
+    shadow_phase<COUNT, SMEM>(p, sc, mode, q, ctr, radiance, bounce, s_bvh);
+}
+
 // ---- queue-split schedule (default): hit/miss stream compaction between traversal and shading --------------
 // Traversal and shading are separate persistent kernels: the traversal kernel stays small in registers
 // (more resident warps to hide the dependent node fetches), and it compacts its results into a HIT queue and a
@@ -744,12 +751,9 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameP
 // mix the two and idle through each other's code.  Both kernels drain their queues through a global atomic
 // cursor, 32 entries per grab.
 template <bool COUNT, bool SMEM>
-__global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_closest(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, uint32_t bounce)
+__device__ __forceinline__ void closest_phase(const FrameParams& p, const DevScene& sc, int mode, const Queues& q, DevCounters* ctr, uint32_t bounce,
+                                              const float4* s_bvh)
 {
-    extern __shared__ __align__(128) float4 s_bvh[];
-    __shared__ uint64_t s_mbar;
-    if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
-    pdl_wait(); pdl_launch_dependents();
     const uint32_t n = *in_count_ptr(ctr, bounce);
     const int in = bounce & 1;
     const int lane = threadIdx.x & 31;
@@ -787,6 +791,32 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_closest(FrameParam
         }
     }
     if (COUNT) { warp_sum64(&ctr->nodes_ext[bounce], nv); warp_sum64(&ctr->tris_ext[bounce], nt); }
+}
+
+template <bool COUNT, bool SMEM>
+__global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_closest(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, uint32_t bounce)
+{
+    extern __shared__ __align__(128) float4 s_bvh[];
+    __shared__ uint64_t s_mbar;
+    if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    pdl_wait(); pdl_launch_dependents();
+    closest_phase<COUNT, SMEM>(p, sc, mode, q, ctr, bounce, s_bvh);
+}
+
+// Closest-hit traversal of bounce b and the shadow pass of bounce b-1 in ONE persistent kernel (RT_OPT_OVERLAP = 2, the
+// default): the two are independent (the shadow pass only shares the radiance buffer with LATER shading passes), every
+// warp drains the extension queue and then the shadow queue, so the short shadow rays fill the tail of the long
+// extension rays without a second launch, a second staging of the BVH or cross-stream events.
+template <bool SMEM>
+__global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_both(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance,
+                                                                   uint32_t bounce, uint32_t shadow_bounce)
+{
+    extern __shared__ __align__(128) float4 s_bvh[];
+    __shared__ uint64_t s_mbar;
+    if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    pdl_wait(); pdl_launch_dependents();
+    closest_phase<false, SMEM>(p, sc, mode, q, ctr, bounce, s_bvh);
+    shadow_phase<false, SMEM>(p, sc, mode, q, ctr, radiance, shadow_bounce, s_bvh);
 }
 
 
@@ -1117,7 +1147,9 @@ struct rt_ctx
     void* graph_set_frame_func = nullptr;
     uint64_t graph_launches = 0;
     // shadow pass on a second stream (RT_OPT_OVERLAP): k_shadow_accumulate(b) runs concurrently with k_trace_closest(b+1)
-    int overlap = 1;
+    int overlap = 2;               // RT_OPT_OVERLAP
+    bool shadow_deferred = false;  // overlap 2: rt_shadow_accumulate(shadow_deferred_bounce) has been requested but not launched yet
+    uint32_t shadow_deferred_bounce = 0;
     cudaStream_t shadow_stream = nullptr;
     cudaEvent_t ev_shaded = nullptr, ev_shadowed = nullptr;
     bool shadow_pending = false;
@@ -1179,6 +1211,9 @@ static std::string g_create_error;
 
 #define RT_CHECK_CTX(ctx) do { if (!(ctx)) return RT_ERR_INVALID_ARGUMENT; } while (0)
 
+struct rt_ctx;
+extern "C" { static int launch_shadow_pass(rt_ctx* c, uint32_t bounce, cudaStream_t st); }   // defined with rt_shadow_accumulate
+
 namespace
 {
 
@@ -1207,6 +1242,11 @@ inline dim3 grid_for(uint32_t n, uint32_t block = 256) { uint32_t g = (n + block
 // buffer, the shadow queue or the counters again.
 int join_shadow(rt_ctx* c)
 {
+    if (c->shadow_deferred)
+    {   // nobody merged the deferred shadow pass into a traversal kernel: it runs on its own, in stream order
+        c->shadow_deferred = false;
+        int rc = launch_shadow_pass(c, c->shadow_deferred_bounce, c->stream); if (rc) return rc;
+    }
     if (c->shadow_pending)
     {
         RT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_shadowed, 0));
@@ -1284,6 +1324,9 @@ int persistent_grid(rt_ctx* c, const void* kernel, size_t dyn_smem)
     return g < need ? g : need;
 }
 #define RT_PGRID(c, kern, smem) persistent_grid(c, (const void*)(kern), smem)
+
+// Can the traversal kernel of the next bounce also run a deferred shadow pass (k_trace_both)?
+bool merged_trace_available(const rt_ctx* c) { return c->fusion == 0 && c->traversal != 2 && !c->count_traversal && !c->kernel_timing; }
 
 // <<<grid, 256, smem, stream>>> with the programmatic-dependent-launch attribute when RT_OPT_PDL is on
 template <class... KArgs, class... Args>
@@ -1579,7 +1622,12 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
     case RT_OPT_GRAPH: c->use_graph = value != 0; return RT_OK;
     case RT_OPT_PDL: c->pdl = value != 0; return RT_OK;
     case RT_OPT_SMEM_BVH: c->smem_bvh = value != 0; return RT_OK;
-    case RT_OPT_OVERLAP: { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; c->overlap = value != 0; return RT_OK; }
+    case RT_OPT_OVERLAP:
+    {
+        if (value > 2) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "overlap mode must be 0, 1 or 2");
+        int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_;
+        c->overlap = (int)value; return RT_OK;
+    }
     case RT_OPT_FUSION:
         if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "fusion mode must be 0 or 1");
         c->fusion = (int)value; return RT_OK;
@@ -1762,6 +1810,15 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
         k_trace_refill<false><<<RT_PGRID(c, k_trace_refill<false>, 0), 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, c->refill_min);
         int rc = post_launch(c, "k_trace_refill<closest>"); if (rc) return rc;
     }
+    else if (c->shadow_deferred && merged_trace_available(c))
+    {   // this bounce's closest-hit traversal + the previous bounce's shadow pass in one kernel
+        c->shadow_deferred = false;
+        TimedLaunch t(c, RT_K_TRACE_BOTH);
+        size_t stage = smem_stage_bytes(c);
+        if (stage) launch_chain(c, k_trace_both<true>, RT_PGRID(c, k_trace_both<true>, stage), stage, c->stream, frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
+        else launch_chain(c, k_trace_both<false>, RT_PGRID(c, k_trace_both<false>, 0), 0, c->stream, frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
+        int rc = post_launch(c, "k_trace_both"); if (rc) return rc;
+    }
     else
     {
         TimedLaunch t(c, RT_K_TRACE_CLOSEST);
@@ -1777,41 +1834,44 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
     return post_launch(c, "k_shade_queues");
 }
 
+static int launch_shadow_pass(rt_ctx* c, uint32_t bounce, cudaStream_t st)
+{
+    TimedLaunch t(c, RT_K_SHADOW_ACCUMULATE, st);
+    size_t stage = smem_stage_bytes(c);
+    if (c->traversal == 2 && !c->count_traversal)
+        k_trace_refill<true><<<RT_PGRID(c, k_trace_refill<true>, 0), 256, 0, st>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, c->refill_min);
+    else if (c->count_traversal) k_shadow_accumulate<true, false><<<RT_PGRID(c, (k_shadow_accumulate<true, false>), 0), 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    else if (stage) k_shadow_accumulate<false, true><<<RT_PGRID(c, (k_shadow_accumulate<false, true>), stage), 256, stage, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    else k_shadow_accumulate<false, false><<<RT_PGRID(c, (k_shadow_accumulate<false, false>), 0), 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    return post_launch(c, "k_shadow_accumulate");
+}
+
 int rt_shadow_accumulate(rt_ctx* c, uint32_t bounce)
 {
     RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
     int rc = join_shadow(c); if (rc) return rc;
-    // The shadow pass of bounce b only shares the radiance buffer with LATER shading passes, so it is submitted to a second
-    // stream and overlaps the closest-hit traversal of bounce b+1 (which touches neither); join_shadow() orders it before
-    // the next kernel that needs its results.  Both kernels are persistent, so the second fills the SMs as the first drains.
-    cudaStream_t st = c->stream;
-    if (c->overlap)
-    {
-        if (!c->shadow_stream)
-        {
-            RT_CUDA(c, cudaStreamCreateWithFlags(&c->shadow_stream, cudaStreamNonBlocking));
-            RT_CUDA(c, cudaEventCreateWithFlags(&c->ev_shaded, cudaEventDisableTiming));
-            RT_CUDA(c, cudaEventCreateWithFlags(&c->ev_shadowed, cudaEventDisableTiming));
-        }
-        st = c->shadow_stream;
-        RT_CUDA(c, cudaEventRecord(c->ev_shaded, c->stream));
-        RT_CUDA(c, cudaStreamWaitEvent(st, c->ev_shaded, 0));
+    // The shadow pass of bounce b only shares the radiance buffer with LATER shading passes, so it may overlap the
+    // closest-hit traversal of bounce b+1 (which touches neither).
+    if (c->overlap == 2 && merged_trace_available(c))
+    {   // deferred: rt_extend_shade(b+1) runs it inside its traversal kernel; join_shadow() launches it for anyone else
+        c->shadow_deferred = true; c->shadow_deferred_bounce = bounce;
+        return RT_OK;
     }
+    if (c->overlap != 1) return launch_shadow_pass(c, bounce, c->stream);
+    // overlap 1: second stream; join_shadow() orders it before the next kernel that needs its results.  Both kernels are
+    // persistent, so the second fills the SMs as the first drains.
+    if (!c->shadow_stream)
     {
-        TimedLaunch t(c, RT_K_SHADOW_ACCUMULATE, st);
-        size_t stage = smem_stage_bytes(c);
-        if (c->traversal == 2 && !c->count_traversal)
-            k_trace_refill<true><<<RT_PGRID(c, k_trace_refill<true>, 0), 256, 0, st>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, c->refill_min);
-        else if (c->count_traversal) k_shadow_accumulate<true, false><<<RT_PGRID(c, (k_shadow_accumulate<true, false>), 0), 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-        else if (stage) k_shadow_accumulate<false, true><<<RT_PGRID(c, (k_shadow_accumulate<false, true>), stage), 256, stage, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-        else k_shadow_accumulate<false, false><<<RT_PGRID(c, (k_shadow_accumulate<false, false>), 0), 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-        rc = post_launch(c, "k_shadow_accumulate"); if (rc) return rc;
+        RT_CUDA(c, cudaStreamCreateWithFlags(&c->shadow_stream, cudaStreamNonBlocking));
+        RT_CUDA(c, cudaEventCreateWithFlags(&c->ev_shaded, cudaEventDisableTiming));
+        RT_CUDA(c, cudaEventCreateWithFlags(&c->ev_shadowed, cudaEventDisableTiming));
     }
-    if (c->overlap)
-    {
-        RT_CUDA(c, cudaEventRecord(c->ev_shadowed, st));
-        c->shadow_pending = true;
-    }
+    cudaStream_t st = c->shadow_stream;
+    RT_CUDA(c, cudaEventRecord(c->ev_shaded, c->stream));
+    RT_CUDA(c, cudaStreamWaitEvent(st, c->ev_shaded, 0));
+    rc = launch_shadow_pass(c, bounce, st); if (rc) return rc;
+    RT_CUDA(c, cudaEventRecord(c->ev_shadowed, st));
+    c->shadow_pending = true;
     return RT_OK;
 }
 
@@ -1838,7 +1898,7 @@ static int capture_frame_graph(rt_ctx* c, uint32_t max_bounces)
 {
     drop_graph(c);
     int rc = join_shadow(c); if (rc) return rc;
-    if (c->overlap && !c->shadow_stream)
+    if (c->overlap == 1 && !c->shadow_stream)
     {   // create the second stream and its events outside the capture
         RT_CUDA(c, cudaStreamCreateWithFlags(&c->shadow_stream, cudaStreamNonBlocking));
         RT_CUDA(c, cudaEventCreateWithFlags(&c->ev_shaded, cudaEventDisableTiming));
@@ -1853,7 +1913,7 @@ static int capture_frame_graph(rt_ctx* c, uint32_t max_bounces)
     cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
     c->graph_launches = c->launches - saved_launches;
     c->sample_count = saved_samples; c->cur_bounce = saved_bounce; c->launches = saved_launches; c->frame_started = saved_started;
-    c->shadow_pending = false;
+    c->shadow_pending = false; c->shadow_deferred = false;
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) RT_FAIL(c, RT_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
     size_t n_nodes = 0;

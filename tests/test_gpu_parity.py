@@ -353,6 +353,40 @@ def test_root_leaf_bvh_and_tiny_images(n_tris):
     assert np.array_equal(bits(out[..., :3]), bits(orad[..., :3]))
 
 
+@pytest.mark.parametrize("name,w,h,mb", [("CornellBox", 320, 180, 8), ("ShaderBalls", 256, 144, 6)])
+def test_shadow_pass_overlap_modes_are_equivalent(name, w, h, mb):
+    """RT_OPT_OVERLAP 0 (in order), 1 (second stream) and 2 (shadow pass deferred into the next traversal kernel), with and
+    without the frame graph / programmatic dependent launch, and with reads in the middle of a frame that force the
+    deferred pass out early: same radiance, same counters."""
+    sc = scene(name); cam = default_camera(w, h)
+    o = Oracle(sc)
+    want, _, ost = o.render(cam, w, h, mb)
+    for overlap in (0, 1, 2):
+        for graph, pdl in ((1, 1), (0, 1), (0, 0)):
+            c = make_ctx(name, w, h)
+            c.set_option(capi.OPT_OVERLAP, overlap); c.set_option(capi.OPT_GRAPH, graph); c.set_option(capi.OPT_PDL, pdl)
+            c.reset(); c.integrate(mb)
+            check_stats(c.frame_stats(), ost, mb)
+            assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(want[..., :3])), (overlap, graph, pdl)
+            c.destroy()
+        # the per-virtual calls of the fused schedule, interrupted by taps
+        c = make_ctx(name, w, h)
+        c.set_option(capi.OPT_OVERLAP, overlap)
+        c.reset(); c.generate_rays()
+        partial, _, _ = o.render(cam, w, h, 2)
+        for b in range(mb + 1):
+            c.extend_shade(b)
+            c.shadow_accumulate(b)
+            if b == 2:                       # radiance after bounce 2 == a 2-bounce render
+                assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(partial[..., :3])), overlap
+            if b == 4:
+                c.sync()
+        c.advance_sample_count()
+        check_stats(c.frame_stats(), ost, mb)
+        assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(want[..., :3])), overlap
+        c.destroy()
+
+
 def test_scene_reupload_and_camera_change_on_one_context():
     """UploadGPUData twice and SetCameraData between frames on the same context (the frame graph is re-captured when a
     launch argument changes, and only its per-frame constants are refreshed when the camera moves)."""
