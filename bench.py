@@ -337,8 +337,11 @@ def main():
 
     def e2e_frame():
         ctx.set_camera(cam_host)                       # per-frame input (render.cpp:188): 64 B host -> device (kernel parameter)
-        frame()
-        ctx.resolve(host_np)                           # resolve + device->host of this rank's rows; blocks
+        frame()                                        # N > 1: ends with the NCCL gather of the radiance slabs to rank 0
+        if world == 1:
+            ctx.resolve(host_np)                       # resolve + device->host of the image; blocks
+        elif rank == 0:                                # rank 0 presents: resolve the WHOLE gathered frame + device->host; blocks
+            ctx.resolve_gathered(gather.recv_ptr, gather.recv_stride_bytes, host_np)
     for _ in range(2):
         e2e_frame()
     barrier()
@@ -359,7 +362,10 @@ def main():
     def e2e_frame_pipelined(i):
         ctx.set_camera(cam_host)
         frame()
-        ctx.resolve_async(host_nps[i & 1])
+        if world == 1:
+            ctx.resolve_async(host_nps[i & 1])
+        elif rank == 0:
+            ctx.resolve_gathered(gather.recv_ptr, gather.recv_stride_bytes, host_nps[i & 1], wait=False)
     for i in range(2):
         e2e_frame_pipelined(i)
     ctx.resolve_wait(); barrier()
@@ -390,12 +396,13 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{name} {w}x{h} 1spp {mb}-bounce, {len(scene['triangles'])} triangles, sample_idx 0, Reset+Integrate per step",
-                       "schedule": "stepwise" if args.stepwise else ("fused-monolithic" if args.monolithic else "fused: trace -> hit/miss queues -> shade, shadow+accumulate"), "partition": f"scanline y%{world}",
+                       "schedule": "stepwise" if args.stepwise else ("fused-monolithic" if args.monolithic else "fused: [closest-hit trace(b) + shadow pass(b-1)] -> hit/miss queues -> shade(b)"), "partition": f"scanline y%{world}",
                        "rays_per_step": rays_per_frame,
                        "l2": "per-step working set (ray/shadow queues + radiance, ~365 MB at 1080p) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_ms[0]), "h2d_bytes_per_step": 64,
-                    "d2h_bytes_per_step": int(ctx.local_pixel_count()) * 16,
-                    "api": "rt_set_camera + rt_reset + rt_integrate + rt_resolve(host image), blocking per frame like ResolveRadiance/Finish()",
+                    "d2h_bytes_per_step": w * h * 16,
+                    "api": ("rt_set_camera + rt_reset + rt_integrate + rt_resolve(host image), blocking per frame like ResolveRadiance/Finish()" if world == 1 else
+                            "every rank: rt_set_camera + rt_reset + rt_integrate + NCCL gather to rank 0; rank 0: rt_resolve_gathered(whole host image), blocking per frame"),
                     "pipelined_value": e2e_pipe_value, "pipelined_ms_per_step": float(e2e_pipe_ms[0]),
                     "pipelined_api": "same, with rt_resolve_async: image D2H of frame i overlaps frame i+1"},
             "gpu_launches": int(launches),

@@ -166,6 +166,16 @@ int rt_resolve(rt_ctx* ctx, float* dst_rgba);
 int rt_resolve_async(rt_ctx* ctx, float* dst_rgba);
 int rt_resolve_wait(rt_ctx* ctx);
 
+/* Multi-GPU presentation on the rank that gathered the frame (new capability; SURVEY 8e: the resolve reads through the
+ * scanline map).  `slabs` is a DEVICE pointer on this context's GPU to `world` radiance slabs, rank r's at
+ * slabs + r * slab_stride_bytes, each holding that rank's rows (its local row k is image row r + k * world) as
+ * width float4 per row — the layout rt_radiance_device_ptr exposes and the NCCL gather delivers.  Resolves the
+ * shaded colour of the WHOLE width x height image (resolve_radiance.cl:80-84: radiance / sample_count, x/(1+x),
+ * alpha 1) on the render stream and copies it to dst_rgba.  rt_resolve_gathered blocks; the _async variant copies on
+ * the read-back stream like rt_resolve_async (rt_resolve_wait).  AOV views and the denoiser are single-GPU only. */
+int rt_resolve_gathered(rt_ctx* ctx, const void* slabs, uint64_t slab_stride_bytes, float* dst_rgba);
+int rt_resolve_gathered_async(rt_ctx* ctx, const void* slabs, uint64_t slab_stride_bytes, float* dst_rgba);
+
 /* ---- fused steps (same per-pixel results, fewer passes over HBM) ------------------ */
 int rt_extend_shade(rt_ctx* ctx, uint32_t bounce);              /* IntersectRays + ShadeMissedRays + ShadeSurfaceHits */
 int rt_shadow_accumulate(rt_ctx* ctx, uint32_t bounce);         /* IntersectShadowRays + AccumulateDirectSamples */

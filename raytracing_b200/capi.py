@@ -27,7 +27,7 @@ SYMBOLS = ["rt_create", "rt_destroy", "rt_last_error", "rt_set_partition", "rt_u
            "rt_upload_sampler_tables",
            "rt_reset", "rt_advance_sample_count", "rt_generate_rays", "rt_intersect", "rt_compute_aovs", "rt_shade_miss",
            "rt_clear_outgoing_counter", "rt_clear_shadow_counter", "rt_shade_hits", "rt_intersect_shadow",
-           "rt_accumulate_direct", "rt_denoise", "rt_copy_history", "rt_resolve", "rt_resolve_async", "rt_resolve_wait", "rt_extend_shade", "rt_shadow_accumulate",
+           "rt_accumulate_direct", "rt_denoise", "rt_copy_history", "rt_resolve", "rt_resolve_async", "rt_resolve_wait", "rt_resolve_gathered", "rt_resolve_gathered_async", "rt_extend_shade", "rt_shadow_accumulate",
            "rt_integrate", "rt_sync", "rt_read_hits", "rt_read_rays", "rt_read_radiance", "rt_read_frame_stats",
            "rt_read_sample_count", "rt_read_aovs", "rt_kernel_times", "rt_launch_count", "rt_local_pixel_count",
            "rt_radiance_device_ptr", "rt_stream_handle"]
@@ -84,6 +84,8 @@ def load_library():
     L.rt_resolve.argtypes = [C.c_void_p, C.c_void_p]
     L.rt_resolve_async.argtypes = [C.c_void_p, C.c_void_p]
     L.rt_resolve_wait.argtypes = [C.c_void_p]
+    L.rt_resolve_gathered.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.rt_resolve_gathered_async.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.rt_read_hits.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
     L.rt_read_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
     L.rt_read_radiance.argtypes = [C.c_void_p, C.c_void_p]
@@ -212,6 +214,14 @@ class Context:
         self._ck(self.lib.rt_resolve_async(self.h, out.ctypes.data))
 
     def resolve_wait(self): self._ck(self.lib.rt_resolve_wait(self.h))
+
+    def resolve_gathered(self, slabs_device_ptr, slab_stride_bytes, out=None, wait=True):
+        """Rank 0 of a multi-GPU frame: resolve the gathered slabs (device pointer, one slab per rank) into the whole host image."""
+        if out is None:
+            out = np.zeros((self.height, self.width, 4), dtype="<f4")
+        fn = self.lib.rt_resolve_gathered if wait else self.lib.rt_resolve_gathered_async
+        self._ck(fn(self.h, C.c_void_p(slabs_device_ptr), int(slab_stride_bytes), out.ctypes.data))
+        return out
 
     # ---- taps
     def local_pixel_count(self):

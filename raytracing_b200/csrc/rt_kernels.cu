@@ -1083,6 +1083,19 @@ __global__ void __launch_bounds__(256) k_resolve(const float4* radiance, float4*
     }
 }
 
+// ResolveRadiance of a gathered multi-GPU frame: pixel (x, y) lives in slab y % world at local row y / world
+__global__ void __launch_bounds__(256) k_resolve_gathered(const float4* slabs, size_t stride_f4, float4* out, uint32_t width, uint32_t height,
+                                                          uint32_t world, uint32_t sample_count)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= width * height) return;
+    uint32_t y = i / width, x = i - y * width;
+    float4 r = slabs[(size_t)(y % world) * stride_f4 + (size_t)(y / world) * width + x];
+    f3 hdr = mk3(r) / (float)sample_count;
+    f3 ldr = hdr / (mk3(hdr.x + 1.0f, hdr.y + 1.0f, hdr.z + 1.0f));
+    out[i] = make_float4(ldr.x, ldr.y, ldr.z, 1.0f);
+}
+
 // TemporalAccumulation, denoiser.cl:27-79 (single-GPU only: the reprojected pixel may be any pixel of the image)
 __global__ void __launch_bounds__(256) k_temporal(uint32_t width, uint32_t height, float4* radiance, const float4* prev_radiance,
                                                   const float* depth, const float* prev_depth, const float2* velocity)
@@ -1155,6 +1168,7 @@ struct rt_ctx
     bool shadow_pending = false;
     // pipelined read-back (rt_resolve_async): second resolve buffer, copy stream, events
     float4* resolved2 = nullptr;
+    float4* resolved_full[2] = { nullptr, nullptr };   // whole-frame resolve targets of rt_resolve_gathered
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t resolve_done[2] = { nullptr, nullptr }, copy_done[2] = { nullptr, nullptr };
     bool copy_pending[2] = { false, false };
@@ -1454,7 +1468,7 @@ int rt_destroy(rt_ctx* c)
     for (int i = 0; i < 2; ++i) { cudaFree(c->q.A[i]); cudaFree(c->q.B[i]); cudaFree(c->q.C[i]); }
     cudaFree(c->q.sA); cudaFree(c->q.sB); cudaFree(c->q.sC); cudaFree(c->q.hits); cudaFree(c->q.shadow_flags);
     cudaFree(c->q.hitq); cudaFree(c->q.missq);
-    cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->resolved2); cudaFree(c->counters); cudaFree(c->scratch); cudaFree(c->d_dyn); cudaFree(c->d_bn);
+    cudaFree(c->radiance); cudaFree(c->resolved); cudaFree(c->resolved2); cudaFree(c->counters); cudaFree(c->scratch); cudaFree(c->d_dyn); cudaFree(c->d_bn); cudaFree(c->resolved_full[0]); cudaFree(c->resolved_full[1]);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->graph) cudaGraphDestroy(c->graph);
     if (c->shadow_stream) { cudaStreamSynchronize(c->shadow_stream); cudaStreamDestroy(c->shadow_stream); }
@@ -2021,6 +2035,55 @@ int rt_resolve_async(rt_ctx* c, float* dst)
     c->copy_pending[k] = true;
     return RT_OK;
 }
+
+static int resolve_gathered_impl(rt_ctx* c, const void* slabs, uint64_t stride_bytes, float* dst, bool async)
+{
+    RT_CHECK_CTX(c);
+    { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
+    if (!slabs || !dst) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_resolve_gathered: null pointer");
+    const size_t rows_max = ((size_t)c->height + c->world - 1) / c->world;
+    if (stride_bytes % 16 != 0 || stride_bytes < rows_max * c->width * 16)
+        RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_resolve_gathered: slab stride must be a multiple of 16 and hold %zu rows", rows_max);
+    if (c->aov != 0 || c->denoiser) RT_FAIL(c, RT_ERR_UNSUPPORTED, "rt_resolve_gathered resolves the shaded colour only (AOV views and the denoiser are single-GPU)");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)c->width * c->height;
+    int k = 0;
+    if (async)
+    {
+        if (!c->copy_stream)
+        {
+            RT_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i)
+            {
+                RT_CUDA(c, cudaEventCreateWithFlags(&c->resolve_done[i], cudaEventDisableTiming));
+                RT_CUDA(c, cudaEventCreateWithFlags(&c->copy_done[i], cudaEventDisableTiming));
+            }
+        }
+        k = (int)(c->async_index++ & 1u);
+        if (c->copy_pending[k]) RT_CUDA(c, cudaStreamWaitEvent(c->stream, c->copy_done[k], 0));
+    }
+    if (!c->resolved_full[k]) RT_CUDA(c, cudaMalloc(&c->resolved_full[k], n * 16));
+    {
+        TimedLaunch t(c, RT_K_RESOLVE);
+        k_resolve_gathered<<<grid_for((uint32_t)n), 256, 0, c->stream>>>((const float4*)slabs, (size_t)(stride_bytes / 16), c->resolved_full[k],
+                                                                            c->width, c->height, c->world, c->sample_count);
+        int rc = post_launch(c, "k_resolve_gathered"); if (rc) return rc;
+    }
+    if (!async)
+    {
+        RT_CUDA(c, cudaMemcpyAsync(dst, c->resolved_full[k], n * 16, cudaMemcpyDeviceToHost, c->stream));
+        RT_CUDA(c, cudaStreamSynchronize(c->stream));
+        return RT_OK;
+    }
+    RT_CUDA(c, cudaEventRecord(c->resolve_done[k], c->stream));
+    RT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->resolve_done[k], 0));
+    RT_CUDA(c, cudaMemcpyAsync(dst, c->resolved_full[k], n * 16, cudaMemcpyDeviceToHost, c->copy_stream));
+    RT_CUDA(c, cudaEventRecord(c->copy_done[k], c->copy_stream));
+    c->copy_pending[k] = true;
+    return RT_OK;
+}
+int rt_resolve_gathered(rt_ctx* c, const void* slabs, uint64_t stride_bytes, float* dst) { return resolve_gathered_impl(c, slabs, stride_bytes, dst, false); }
+int rt_resolve_gathered_async(rt_ctx* c, const void* slabs, uint64_t stride_bytes, float* dst) { return resolve_gathered_impl(c, slabs, stride_bytes, dst, true); }
 
 int rt_resolve_wait(rt_ctx* c)
 {

@@ -29,7 +29,12 @@ class RadianceGather:
         self.n_local = local_rows(height, rank, world) * width
         self.n_pad = rows_max(height, world) * width
         self.send = torch.zeros((self.n_pad, 4), dtype=torch.float32, device=device)
-        self.recv = [torch.zeros_like(self.send) for _ in range(world)] if rank == 0 else None
+        # rank 0 receives into ONE contiguous (world, n_pad, 4) buffer: slab r at recv_all[r], the layout
+        # rt_resolve_gathered reads through (recv_ptr, recv_stride_bytes)
+        self.recv_all = torch.zeros((world, self.n_pad, 4), dtype=torch.float32, device=device) if rank == 0 else None
+        self.recv = list(self.recv_all.unbind(0)) if rank == 0 else None
+        self.recv_ptr = self.recv_all.data_ptr() if rank == 0 and self.recv_all.is_cuda else None
+        self.recv_stride_bytes = self.n_pad * 16
 
     def gather(self, slab: torch.Tensor):
         """The one collective of the frame.  Returns the list of padded slabs on rank 0, None elsewhere."""

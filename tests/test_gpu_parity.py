@@ -172,6 +172,45 @@ def test_scanline_partition_reassembles_bit_exact(world):
     full.destroy()
 
 
+def test_gathered_frame_resolves_like_a_single_gpu_frame():
+    """rt_resolve_gathered on the gathering rank: three partitions rendered by three contexts, their radiance slabs laid
+    out the way the NCCL gather delivers them, resolved through the scanline map — equal to rt_resolve of one context
+    that rendered the whole image.  Height 101 is not a multiple of 3 (ragged last rows, padded slabs)."""
+    import torch
+    from raytracing_b200.distributed import RadianceGather, local_rows
+    w, h, mb, world = 160, 101, 4, 3
+    whole = make_ctx("CornellBox", w, h); whole.reset()
+    parts = [capi.Context(w, h, rank=r, world=world) for r in range(world)]
+    for c in parts:
+        c.upload_scene(scene("CornellBox")); c.set_camera(default_camera(w, h)); c.reset()
+    for _ in range(2):
+        whole.integrate(mb)
+        for c in parts:
+            c.integrate(mb)
+    g = RadianceGather(w, h, 0, world, torch.device("cuda", 0))
+    for r, c in enumerate(parts):
+        c.sync()
+        ptr, nbytes = c.radiance_device_ptr()
+        n = c.local_pixel_count()
+        assert n == local_rows(h, r, world) * w and nbytes >= n * 16
+
+        class _Slab:
+            __cuda_array_interface__ = {"shape": (n, 4), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+        g.recv_all[r, :n].copy_(torch.as_tensor(_Slab(), device="cuda"))
+    torch.cuda.synchronize()
+    want = whole.resolve()
+    got = parts[0].resolve_gathered(g.recv_ptr, g.recv_stride_bytes)
+    assert np.array_equal(bits(got), bits(want))
+    import torch as _t
+    host = _t.zeros((h, w, 4), dtype=_t.float32).pin_memory().numpy()
+    parts[0].resolve_gathered(g.recv_ptr, g.recv_stride_bytes, out=host, wait=False); parts[0].resolve_wait()
+    assert np.array_equal(bits(host), bits(want))
+    with pytest.raises(capi.RtError):
+        parts[0].resolve_gathered(g.recv_ptr, 64)          # stride cannot hold a slab
+    for c in parts + [whole]:
+        c.destroy()
+
+
 def test_full_size_properties_1080p():
     """BASELINE config C2 at full size (CornellBox 1920x1080, 8 bounces): size-independent properties.
     fused == stepwise bit-for-bit; live-ray counters are monotone and consistent; a 64-row band equals the oracle."""
