@@ -179,6 +179,9 @@ int rt_resolve_gathered_async(rt_ctx* ctx, const void* slabs, uint64_t slab_stri
 /* ---- fused steps (same per-pixel results, fewer passes over HBM) ------------------ */
 int rt_extend_shade(rt_ctx* ctx, uint32_t bounce);              /* IntersectRays + ShadeMissedRays + ShadeSurfaceHits */
 int rt_shadow_accumulate(rt_ctx* ctx, uint32_t bounce);         /* IntersectShadowRays + AccumulateDirectSamples */
+/* With RT_OPT_OVERLAP = 2 (default) the work of rt_shadow_accumulate(b) is submitted with the traversal of the next
+ * rt_extend_shade, or by the next call that depends on it: every step / resolve / read / rt_sync /
+ * rt_advance_sample_count does that, so the device state after each call is what in-order execution gives. */
 /* GenerateRays + (max_bounces+1) x {extend_shade, shadow_accumulate} + AdvanceSampleCount, i.e. the body of
  * Integrator::Integrate between Reset() and ResolveRadiance(). */
 int rt_integrate(rt_ctx* ctx, uint32_t max_bounces);
@@ -205,6 +208,8 @@ int rt_launch_count(rt_ctx* ctx, uint64_t* out);
  * the local radiance slab is local_rows x width float4, local row r = image row rank + r*world. */
 int rt_local_pixel_count(rt_ctx* ctx, uint32_t* out);
 int rt_radiance_device_ptr(rt_ctx* ctx, void** out_ptr, uint64_t* out_bytes);
+/* The render stream.  Work a caller enqueues on it sees the complete frame after rt_integrate or
+ * rt_advance_sample_count (which close the frame in stream order). */
 int rt_stream_handle(rt_ctx* ctx, void** out_cuda_stream);
 
 #ifdef __cplusplus

@@ -28,7 +28,7 @@ def fnum(x):
 
 
 traffic = {}
-for k, cls in (("trace", "trace_closest"), ("shade", "shade_queues"), ("shadow", "shadow_accumulate")):
+for k, cls in (("trace", "trace_closest"), ("shade", "shade_queues"), ("shadow", "shadow_accumulate"), ("both", "trace_both")):
     rep = os.path.join(src, f"prof_{k}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -45,7 +45,10 @@ for k, cls in (("trace", "trace_closest"), ("shade", "shade_queues"), ("shadow",
                     "dram_GBs_under_ncu": (sum(rd) + sum(wr)) / sum(du) / 1e9, "duration_us_under_ncu": [round(d * 1e6, 1) for d in du]}
     with open(os.path.join(HERE, f"{tag}_{k}_summary.txt"), "w") as f:
         f.write(f"# ncu --set full --clock-control none, kernel class {cls}, bench.py CornellBox 1920x1080 x 8 bounces, tag {tag}\n")
-        f.write("# one column per launch = bounce 0..8 of one frame (cold-cache, serialised by the profiler: compare shares, not absolutes)\n")
+        f.write("# one column per launch = the launches of this kernel in one frame (cold-cache, serialised by the profiler: compare shares, not absolutes)\n")
+        if k in ("trace", "shadow"):
+            f.write("# captured with bench.py --overlap 0 (each pass its own kernel: the configuration bench.py's roofline region times);\n"
+                    "# in the default schedule the shadow pass of bounce b runs inside the traversal kernel of bounce b+1 (k_trace_both)\n")
         f.write("\n".join(l[:400] for l in s1.splitlines()) + "\n\n")
         f.write(f"DRAM traffic per launch (read+write, mean over {len(rows)} launches): {per_launch / 1e6:.1f} MB; "
                 f"achieved DRAM bandwidth under ncu: {traffic[cls]['dram_GBs_under_ncu']:.0f} GB/s "
