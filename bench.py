@@ -168,7 +168,7 @@ def run_reference_arm(args, workload):
     name, w, h, mb = workload
     scene, cam = load_workload_scene(name, w, h, args.copies)
     cores = host_threads()
-    total_budget = 150.0
+    total_budget = args.cpu_budget
     per_step = max(2.0, total_budget / (args.steps + args.warmup))
     vals, info = [], None
     for i in range(args.warmup + args.steps):
@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--stepwise", action="store_true", help="time the one-kernel-per-reference-step schedule instead of the fused one")
     ap.add_argument("--monolithic", action="store_true", help="fused schedule with ONE extend+shade kernel instead of trace -> queues -> shade")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for the whole run (split over warm-up + steps)")
     ap.add_argument("--traversal", type=int, default=None, help="RT_OPT_TRAVERSAL override (0 literal, 1 fast, 2 per-lane refill)")
     ap.add_argument("--refill-min", type=int, default=None, help="RT_OPT_REFILL_MIN override")
     ap.add_argument("--no-graph", action="store_true", help="RT_OPT_GRAPH=0: launch every kernel of the frame individually")
@@ -421,9 +422,17 @@ def main():
                                   "bounce b runs inside the traversal kernel of bounce b+1)",
             "clocks": sampler.summary(),
         }
-        if not args.no_cpu_baseline:
-            v, kind, cores, sample, _ = cpu_reference_frame(scene, cam, w, h, mb, 15.0, host_threads())
-            line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample}
+        if not args.no_cpu_baseline and world == 1:
+            # The CPU leg runs in a fresh process (the --impl reference arm, one bounded sample): this process has torch's OpenMP
+            # runtime loaded and already configured, which would decide the thread count and wait policy for the oracle too.
+            env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE")}
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                                  "--scene", args.scene, "--copies", str(args.copies), "--cpu-budget", "30"],
+                                 capture_output=True, text=True, env=env, timeout=900)
+            try:
+                line["cpu_baseline"] = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception:
+                line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "error": (out.stderr or out.stdout)[-300:]}
         print(json.dumps(line))
     ctx.destroy()
     if world > 1:
