@@ -74,23 +74,37 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.sm, self.power, self.reason_bits, self.stop_flag, self.err = index, [], [], 0, False, None
         self.sm_max = None
+        self.nv = self.h = None
 
-    def run(self):
+    def prepare(self):
+        """NVML start-up (tens of ms) happens here, before the timed region, so that even a 10 ms region is sampled."""
         try:
             import pynvml as nv
             nv.nvmlInit()
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
-            h = nv.nvmlDeviceGetHandleByIndex(idx)
-            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception as e:           # noqa: BLE001
+            self.err = repr(e)
+        return self
+
+    def sample(self):
+        nv, h = self.nv, self.h
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+        except Exception:
+            pass
+        self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+
+    def run(self):
+        if self.err is not None:
+            return
+        try:
             while not self.stop_flag:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                try:
-                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
-                except Exception:
-                    pass
-                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
-                time.sleep(0.002)
+                self.sample()
+                time.sleep(0.001)
         except Exception as e:           # noqa: BLE001
             self.err = repr(e)
 
@@ -297,13 +311,18 @@ def main():
         frame()
     barrier()
     launches0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler = ClockSampler(local_rank).prepare(); sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
         frame()
     ev1.record(stream)
+    if sampler.h is not None and sampler.err is None:
+        try:
+            sampler.sample()            # the K steps are enqueued and running: at least this sample is taken under load
+        except Exception as e:          # noqa: BLE001
+            sampler.err = repr(e)
     barrier()
     sampler.stop_flag = True
     ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=slab.device)
