@@ -277,12 +277,18 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
         return trace_literal<ANY, COUNT>(sc, o, d, t_min, t_max, bu, bv, bt, nv, nt);
 
     f3 inv = splat(1.0f) / d;
-    bool sx = inv.x < 0, sy = inv.y < 0, sz = inv.z < 0;
+    const bool sx = inv.x < 0, sy = inv.y < 0, sz = inv.z < 0;
+    const uint32_t sign_bits = (sx ? 1u : 0u) | (sy ? 2u : 0u) | (sz ? 4u : 0u);
     uint32_t prim = RT_INVALID_ID;
     int sp = 0;
     int cur = sc.root_ref;
-    int stack_ref[64];
-    float stack_t[64];
+    // Deferred far children: (node reference, entry distance).  Two code shapes, chosen by where the BVH records live
+    // (measured, same results): with the records in shared memory the kernel is purely issue-bound and the packed
+    // 64-bit stack entry + the sign-bit axis test win (CornellBox frame -2.7 %); with the records behind L1/L2 the two
+    // 32-bit arrays (a discarded pop costs one load) and predicate selects are faster (ShaderBalls +1 %, Dragon +3.5 %).
+    int2 stack[SMEM ? 64 : 1];
+    int stack_ref[SMEM ? 1 : 64];
+    float stack_t[SMEM ? 1 : 64];
     if (cur < 0)
     {   // single-leaf tree: the root box is tested like any visited node
         float4 r0 = __ldg(sc.nodes_ref), r1 = __ldg(sc.nodes_ref + 1);
@@ -315,13 +321,18 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
             bool h0 = fminf(hi0, t_max) >= lo0, h1 = fminf(hi1, t_max) >= lo1;
             int r0 = __float_as_int(m.x), r1 = __float_as_int(m.y);
             uint32_t axis = __float_as_uint(m.z);
-            bool swap = axis == 0 ? sx : (axis == 1 ? sy : sz);       // near child = second iff inv_dir[axis] < 0
+            bool swap = SMEM ? ((sign_bits >> axis) & 1u) != 0u : (axis == 0 ? sx : (axis == 1 ? sy : sz));   // near child = second iff inv_dir[axis] < 0
             int near_ref = swap ? r1 : r0, far_ref = swap ? r0 : r1;
             bool near_hit = swap ? h1 : h0, far_hit = swap ? h0 : h1;
             float far_lo = swap ? lo0 : lo1;
             if (near_hit)
             {
-                if (far_hit) { stack_ref[sp] = far_ref; stack_t[sp] = far_lo; ++sp; }
+                if (far_hit)
+                {
+                    if (SMEM) stack[sp] = make_int2(far_ref, __float_as_int(far_lo));
+                    else { stack_ref[sp] = far_ref; stack_t[sp] = far_lo; }
+                    ++sp;
+                }
                 cur = near_ref;
             }
             else if (far_hit) cur = far_ref;
@@ -329,7 +340,12 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
             {   // pop: a pushed far child is re-tested against the (possibly shrunk) t_max, as the
                 // reference does when it pops it; its slab interval was already valid at push time
                 bool found = false;
-                while (sp > 0) { --sp; if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; } }
+                while (sp > 0)
+                {
+                    --sp;
+                    if (SMEM) { int2 e = stack[sp]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
+                    else if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; }
+                }
                 if (!found) return prim;
             }
         }
@@ -367,7 +383,12 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
             ++ti;
         }
         bool found = false;
-        while (sp > 0) { --sp; if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; } }
+        while (sp > 0)
+                {
+                    --sp;
+                    if (SMEM) { int2 e = stack[sp]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
+                    else if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; }
+                }
         if (!found) return prim;
     }
 }
