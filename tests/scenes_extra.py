@@ -53,3 +53,19 @@ def single_leaf_scene(n_tris=1):
     info = np.array(sc["scene_info"], copy=True); info["emissive_count"] = 0
     sc["scene_info"] = info
     return sc
+
+
+def many_lights_scene(name="CornellBox"):
+    """The fixture with five analytic lights — two directional, three point lights inside the box (light.h:30-65: uniform
+    pick, 1/d^2 fall-off, shadow rays that stop at the light)."""
+    sc = dict(scene(name))
+    lights = np.zeros(5, dtype=sc["lights"].dtype)
+    lights[0] = sc["lights"][0]
+    d = np.array([0.3, 0.2, 0.93], dtype=np.float32); d /= np.float32(np.sqrt((d * d).sum(dtype=np.float32)))
+    lights[1]["origin"][:3] = d; lights[1]["radiance"][:3] = (2.0, 3.0, 6.0); lights[1]["type"] = 1
+    for i, (pos, rad) in enumerate([((0.0, 0.0, 1.6), (3.0, 3.0, 3.0)), ((-0.6, 0.3, 0.4), (5.0, 1.0, 0.5)), ((0.7, -0.4, 1.0), (0.5, 2.0, 6.0))]):
+        lights[2 + i]["origin"][:3] = pos; lights[2 + i]["radiance"][:3] = rad; lights[2 + i]["type"] = 0
+    sc["lights"] = lights
+    info = np.array(sc["scene_info"], copy=True); info["analytic_light_count"] = len(lights)
+    sc["scene_info"] = info
+    return sc

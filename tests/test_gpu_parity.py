@@ -426,6 +426,53 @@ def test_shadow_pass_overlap_modes_are_equivalent(name, w, h, mb):
         c.destroy()
 
 
+@pytest.mark.parametrize("name,w,h,mb", [("CornellBox", 300, 170, 6), ("ShaderBalls", 256, 144, 5)])
+def test_point_lights_and_thin_lens_match_oracle(name, w, h, mb):
+    """Five analytic lights (point + directional) and a thin-lens camera off the default pose: fused and stepwise vs the
+    oracle (pinned on the same configuration in tests/test_oracle_vs_ref.py)."""
+    from tests.scenes_extra import many_lights_scene
+    sc = many_lights_scene(name)
+    cam = default_camera(w, h, position=(0.15, -1.3, 0.9), aperture=0.04, focus_distance=1.7)
+    o = Oracle(sc)
+    oacc = np.zeros((h, w, 4), dtype="<f4")
+    ctxs = []
+    for stepwise in (False, True):
+        c = capi.Context(w, h); c.upload_scene(sc); c.set_camera(cam); c.reset()
+        ctxs.append((stepwise, c))
+    for sample in range(2):
+        oacc, ohits, ost = o.render(cam, w, h, mb, sample_idx=sample, radiance=oacc)
+        for stepwise, c in ctxs:
+            c.integrate_stepwise(mb) if stepwise else c.integrate(mb)
+            check_stats(c.frame_stats(), ost, mb)
+            assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(oacc[..., :3])), (stepwise, sample)
+    for _, c in ctxs:
+        c.destroy()
+
+
+@pytest.mark.parametrize("case", ["zero_bounces", "all_miss", "inside_geometry"])
+def test_degenerate_frames_match_oracle(case):
+    """max_bounces = 0; a frame whose every primary ray misses (all later queues empty: persistent kernels with nothing to
+    drain, merged traversal kernels with two empty queues); a camera inside closed geometry."""
+    name, w, h, mb, kw = {"zero_bounces": ("CornellBox", 192, 128, 0, {}),
+                          "all_miss": ("ShaderBalls", 160, 96, 4, {"position": (0.0, -30.0, 40.0), "pitch": 0.3}),
+                          "inside_geometry": ("ShaderBalls", 160, 96, 4, {"position": (0.0, 0.0, 0.35), "pitch": 1.9})}[case]
+    sc = scene(name); cam = default_camera(w, h, **kw)
+    o = Oracle(sc)
+    oacc = np.zeros((h, w, 4), dtype="<f4")
+    ctxs = []
+    for stepwise in (False, True):
+        c = capi.Context(w, h); c.upload_scene(sc); c.set_camera(cam); c.reset()
+        ctxs.append((stepwise, c))
+    for sample in range(2):
+        oacc, _, ost = o.render(cam, w, h, mb, sample_idx=sample, radiance=oacc)
+        for stepwise, c in ctxs:
+            c.integrate_stepwise(mb) if stepwise else c.integrate(mb)
+            check_stats(c.frame_stats(), ost, mb)
+            assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(oacc[..., :3])), (case, stepwise, sample)
+    for _, c in ctxs:
+        c.destroy()
+
+
 def test_scene_reupload_and_camera_change_on_one_context():
     """UploadGPUData twice and SetCameraData between frames on the same context (the frame graph is re-captured when a
     launch argument changes, and only its per-frame constants are refreshed when the camera moves)."""

@@ -121,6 +121,54 @@ def test_blue_noise_sampler_bit_exact_vs_reference_kernels(name, w, h, mb, wf):
         r.close()
 
 
+@pytest.mark.parametrize("name,w,h,mb", [("CornellBox", 150, 90, 5), ("ShaderBalls", 128, 72, 4)])
+def test_point_lights_and_thin_lens_bit_exact_vs_reference_kernels(name, w, h, mb):
+    """Five analytic lights (point + directional, light.h:30-65) and a thin-lens camera (aperture > 0: the hexagonal
+    aperture sampling of raygeneration.cl:40-49,108-124), moved off the default pose."""
+    from tests.scenes_extra import many_lights_scene
+    sc = many_lights_scene(name)
+    cam = default_camera(w, h, position=(0.15, -1.3, 0.9), aperture=0.04, focus_distance=1.7)
+    r = refbind.RefRenderer().open_arrays(sc)
+    r.begin(w, h); r.set_camera(cam); r.set_max_bounces(mb)
+    o = Oracle(sc)
+    acc = np.zeros((h, w, 4), dtype="<f4")
+    for sample in range(2):
+        r.integrate()
+        acc, hits, st = o.render(cam, w, h, mb, sample_idx=sample, radiance=acc)
+        rs = r.stats()
+        for k in ("n_ext", "n_miss", "n_hit", "n_shadow", "n_cont", "n_unoccluded"):
+            assert np.array_equal(st[k][: mb + 1], rs[k][: mb + 1]), (k, sample)
+        assert np.array_equal(hits["primitive_id"], r.primary_hits()["primitive_id"])
+        assert np.array_equal(bits(acc[..., :3]), bits(r.radiance()[..., :3]))
+    assert st["n_shadow"][:mb].min() > 0 and st["n_unoccluded"][:mb].min() > 0
+    r.close()
+
+
+@pytest.mark.parametrize("case", ["zero_bounces", "all_miss", "inside_geometry"])
+def test_degenerate_frames_bit_exact_vs_reference_kernels(case):
+    """max_bounces = 0 (one extension pass, one shadow pass); a camera that only sees the sky (every queue after bounce 0
+    is empty); a camera placed inside a ShaderBall (rays start inside closed geometry: back faces are culled)."""
+    name, w, h, mb, kw = {"zero_bounces": ("CornellBox", 96, 64, 0, {}),
+                          "all_miss": ("ShaderBalls", 80, 48, 4, {"position": (0.0, -30.0, 40.0), "pitch": 0.3}),
+                          "inside_geometry": ("ShaderBalls", 80, 48, 4, {"position": (0.0, 0.0, 0.35), "pitch": 1.9})}[case]
+    sc = scene(name); cam = default_camera(w, h, **kw)
+    r = refbind.RefRenderer().open_arrays(sc)
+    r.begin(w, h); r.set_camera(cam); r.set_max_bounces(mb)
+    o = Oracle(sc)
+    acc = np.zeros((h, w, 4), dtype="<f4")
+    for sample in range(2):
+        r.integrate()
+        acc, hits, st = o.render(cam, w, h, mb, sample_idx=sample, radiance=acc)
+        rs = r.stats()
+        for k in ("n_ext", "n_miss", "n_hit", "n_shadow", "n_cont", "n_unoccluded"):
+            assert np.array_equal(st[k][: mb + 1], rs[k][: mb + 1]), (k, sample)
+        assert np.array_equal(hits["primitive_id"], r.primary_hits()["primitive_id"])
+        assert np.array_equal(bits(acc[..., :3]), bits(r.radiance()[..., :3]))
+    if case == "all_miss":
+        assert st["n_hit"][0] == 0 and st["n_ext"][1] == 0
+    r.close()
+
+
 def test_math_library_sensitivity_is_small():
     """The OpenCL driver's libm is unpinned.  Swapping include/rt_math.h for glibc's libm inside the
     reference kernels must leave all but a small fraction of pixels within 1e-4 relative."""
