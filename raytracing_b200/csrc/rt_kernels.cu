@@ -1318,7 +1318,7 @@ int alloc_frame_buffers(rt_ctx* c)
 {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->shadow_stream) cudaStreamSynchronize(c->shadow_stream);
-    c->shadow_pending = false;
+    c->shadow_pending = false; c->shadow_deferred = false;     // the frame in flight (if any) is abandoned with its buffers
     ++c->config_gen;
     auto freep = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     for (int i = 0; i < 2; ++i) { freep(c->q.A[i]); freep(c->q.B[i]); freep(c->q.C[i]); }
