@@ -21,6 +21,9 @@ def load_library():
         return _lib
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    # The BVH builder's OpenMP tasks leave workers idle at the top of the tree; spinning idle workers (libgomp's default) cost
+    # 3x on shared hosts.  Only effective if this is the process's first OpenMP user (the policy is read when libgomp starts).
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
     L = C.CDLL(LIB_PATH)
     L.rth_last_error.restype = C.c_char_p
     L.rth_scene_load.restype = C.c_void_p
