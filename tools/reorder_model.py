@@ -2,7 +2,7 @@
 A warp costs max over its 32 rays of (nodes visited + c * triangles tested); SIMD efficiency = sum(work) / (32 * sum(warp max)).
 Compares queue order with a few orderings that a GPU could produce cheaply."""
 import ctypes as C, sys, numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from oracle.orcbind import Oracle
 from raytracing_b200 import scene_io
 from raytracing_b200.camera import default_camera
