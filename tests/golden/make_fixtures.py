@@ -28,13 +28,18 @@ from raytracing_b200 import scene_io  # noqa: E402
 REFERENCE = "/root/reference"
 OUT = os.path.join(REPO, "tests", "golden")
 
-# (scene, width, height, max_bounces, white_furnace, full dump of rays/hits/AOVs?)
+# (scene, width, height, max_bounces, white_furnace, full dump of rays/hits/AOVs?[, extras])
+# extras: "samples" = progressive samples accumulated (sample_idx 0..n-1), "camera" = default_camera keyword arguments,
+# "tag" = file-name suffix.  Primary hits and counters of a multi-sample fixture are those of its LAST sample.
 GOLDEN = [
     ("CornellBox", 128, 128, 2, False, True),
     ("CornellBox", 256, 256, 2, False, False),       # BASELINE config C1
     ("CornellBox", 128, 128, 4, True, False),        # white furnace
     ("ShaderBalls", 320, 180, 8, False, False),      # C3 at reduced resolution
     ("CornellBox_Dragon", 240, 135, 16, False, False),  # C4 at reduced resolution
+    ("CornellBox", 160, 96, 3, False, False, {"samples": 3, "tag": "lens3spp",
+                                              "camera": {"position": (0.15, -1.3, 0.9), "aperture": 0.04, "focus_distance": 1.7}}),
+    ("ShaderBalls", 200, 112, 5, False, False, {"samples": 2, "tag": "moved2spp", "camera": {"position": (0.6, -1.6, 0.8), "yaw": 1.9, "pitch": 1.4}}),
 ]
 
 
@@ -52,14 +57,20 @@ def main():
         renderers[name] = r
         print(name, len(sc["triangles"]), "triangles", len(sc["nodes"]), "nodes")
 
-    for (name, w, h, mb, wf, full) in GOLDEN:
+    only_new = "--only-new" in sys.argv
+    for entry in GOLDEN:
+        (name, w, h, mb, wf, full), extra = entry[:6], (entry[6] if len(entry) > 6 else {})
+        fn = f"golden_{name}_{w}x{h}_b{mb}{'_wf' if wf else ''}{'_' + extra['tag'] if extra.get('tag') else ''}.npz.xz"
+        if only_new and os.path.exists(os.path.join(OUT, fn)):
+            continue
         r = renderers[name]
         r.begin(w, h)
-        cam = default_camera(w, h)
+        cam = default_camera(w, h, **extra.get("camera", {}))
         r.set_camera(cam)
         r.set_max_bounces(mb)
         r.enable_white_furnace(wf)
-        r.integrate()
+        for _ in range(extra.get("samples", 1)):
+            r.integrate()
         hits = r.primary_hits()
         st = r.stats()
         out = {
@@ -81,7 +92,6 @@ def main():
             out["aov_depth"] = r.aov_depth().copy()
             out["aov_normal"] = r.aov_normal()[..., :3].copy()
             out["aov_velocity"] = r.aov_velocity().copy()
-        fn = f"golden_{name}_{w}x{h}_b{mb}{'_wf' if wf else ''}.npz.xz"
         scene_io.save_npz_xz(os.path.join(OUT, fn), out)
         print(fn, os.path.getsize(os.path.join(OUT, fn)), "bytes")
 

@@ -25,12 +25,11 @@ def golden_files():
 def load_golden(path):
     g = scene_io.load_npz_xz(path)
     base = os.path.basename(path)[len("golden_"):]
-    # file name: golden_<scene>_<w>x<h>_b<mb>[_wf].npz.xz
+    # file name: golden_<scene>_<w>x<h>_b<mb>[_wf][_<tag>].npz.xz
     stem = base.replace(".npz.xz", "")
     parts = stem.split("_")
-    if parts[-1] == "wf":
-        parts = parts[:-1]
-    g["scene_name"] = "_".join(parts[:-2])
+    size = max(i for i, p in enumerate(parts) if "x" in p and p.replace("x", "").isdigit())
+    g["scene_name"] = "_".join(parts[:size])
     return g
 
 

@@ -44,6 +44,8 @@ def test_matches_reference_golden(path, fused):
     ctx.set_camera(g["camera"])
     ctx.set_option(capi.OPT_WHITE_FURNACE, int(g["white_furnace"]))
     ctx.reset()
+    for _ in range(int(g["sample_count"]) - 1):               # progressive fixtures: the earlier samples
+        ctx.integrate(mb) if fused else ctx.integrate_stepwise(mb)
     if fused:
         ctx.integrate(mb)
     else:

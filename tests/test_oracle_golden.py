@@ -16,7 +16,9 @@ def test_oracle_matches_reference_golden(path):
     g = load_golden(path)
     o = Oracle(scene(g["scene_name"]))
     w, h, mb = int(g["width"]), int(g["height"]), int(g["max_bounces"])
-    rad, hits, st = o.render(g["camera"], w, h, mb, sample_idx=0, white_furnace=bool(g["white_furnace"]))
+    rad = np.zeros((h, w, 4), dtype="<f4")
+    for sample in range(int(g["sample_count"])):          # progressive fixtures: hits and counters are the last sample's
+        rad, hits, st = o.render(g["camera"], w, h, mb, sample_idx=sample, white_furnace=bool(g["white_furnace"]), radiance=rad)
     assert np.array_equal(hits["primitive_id"], g["primitive_id"])
     for k in ("n_ext", "n_miss", "n_hit", "n_shadow", "n_cont", "n_unoccluded"):
         assert np.array_equal(st[k][: mb + 1], g[k]), k
