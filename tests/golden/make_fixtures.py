@@ -50,8 +50,10 @@ def main():
     for name in ("CornellBox", "ShaderBalls", "CornellBox_Dragon"):
         r = RefRenderer().open_obj(REFERENCE, f"assets/{name}.obj")
         sc = r.scene()
-        scene_io.save_scene(os.path.join(scene_io.SCENE_DIR, name + ".npz.xz"), sc)
-        if not env_saved:
+        keep = "--only-new" in sys.argv and os.path.exists(os.path.join(scene_io.SCENE_DIR, name + ".npz.xz"))
+        if not keep:       # (struct padding bytes are uninitialised in the reference: a re-saved scene differs in those bytes only)
+            scene_io.save_scene(os.path.join(scene_io.SCENE_DIR, name + ".npz.xz"), sc)
+        if not env_saved and not keep:
             scene_io.save_env(os.path.join(scene_io.SCENE_DIR, scene_io.ENV_NAME + ".npz.xz"), sc["env"], sc["env_width"], sc["env_height"])
             env_saved = True
         renderers[name] = r
