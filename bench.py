@@ -414,6 +414,19 @@ def main():
         except Exception:
             pass
         achieved = (dom_bytes_frame * args.steps / (dom_ms * 1e-3) / 1e9) if dom_ms > 0 else None
+        others = []                                             # the same figures for the other kernels of the step
+        for k in alg_of:
+            if k == dom or not ktimes[k][1] or ktimes[k][0] <= 0:
+                continue
+            a = alg_of[k] / world * args.steps / (ktimes[k][0] * 1e-3) / 1e9
+            t = None
+            try:
+                if tj["workload"].split()[0] == name and world == 1:
+                    t = tj["kernels"][k]["dram_bytes_per_launch"]
+            except Exception:
+                pass
+            others.append({"kernel": k, "achieved": a, "frac": a / peak, "traffic": t, "ms_per_step": ktimes[k][0] / args.steps,
+                           "algorithmic_bytes_per_launch": alg_of[k] / world / max(ktimes[k][1] / args.steps, 1)})
         line = {
             "metric": "Mrays/sec @1920x1080x8-bounce", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -438,7 +451,7 @@ def main():
                          "kernel_algorithmic_bytes_per_launch": dom_bytes_frame / max(dom_n / args.steps, 1),
                          "algorithmic_bytes_per_step": alg_total, "kernel_algorithmic_bytes_per_step": dom_bytes_frame,
                          "kernel_ms_per_step": dom_ms / args.steps, "kernel_launches_per_step": dom_n / args.steps,
-                         "whole_frame_algorithmic_GBs": alg_total / (ms_per_step * 1e-3) / 1e9},
+                         "whole_frame_algorithmic_GBs": alg_total / (ms_per_step * 1e-3) / 1e9, "other_kernels": others},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
             "kernel_timing_note": "kernel_ms_per_step: CUDA events per launch over K extra steps of this run with individual launches and the "
                                   "shadow pass as its own kernel (in the timed region the frame is one CUDA-graph launch in which the shadow pass of "
