@@ -55,3 +55,24 @@ def reference_sampler_tables():
     if not refbind.available():
         return None
     return refbind.RefRenderer().sampler_tables()
+
+
+def fuzz_configs(n=12, seed=77):
+    """Seeded random frame configurations (scene, size, bounces, camera pose / lens, white furnace) shared by the
+    oracle-vs-reference fuzz on the CPU and the CUDA-vs-oracle fuzz on the GPU."""
+    rng = np.random.default_rng(seed)
+    names = ["CornellBox", "ShaderBalls", "CornellBox_Dragon"]
+    out = []
+    for i in range(n):
+        name = names[i % 3]
+        w, h = int(rng.integers(33, 97)), int(rng.integers(17, 65))
+        mb = int(rng.integers(0, 7))
+        pos = (float(rng.uniform(-0.8, 0.8)), float(rng.uniform(-1.8, -0.2)), float(rng.uniform(0.2, 1.8)))
+        kw = {"position": pos, "yaw": float(rng.uniform(0.9, 2.2)), "pitch": float(rng.uniform(1.0, 2.1))}
+        if rng.random() < 0.4:
+            kw.update(aperture=float(rng.uniform(0.0, 0.1)), focus_distance=float(rng.uniform(0.5, 4.0)))
+        out.append((name, w, h, mb, kw, bool(rng.random() < 0.2)))
+    # axis-aligned views: rays with exactly-zero direction components (inv_dir = +-inf in the slab test)
+    out.append(("CornellBox", 65, 33, 3, {"position": (0.0, -1.0, 1.0), "yaw": 1.5707963267948966, "pitch": 1.5707963267948966}, False))
+    out.append(("ShaderBalls", 64, 48, 4, {"position": (0.0, 0.0, 3.0), "yaw": 0.0, "pitch": 3.14159265}, False))
+    return out

@@ -14,7 +14,7 @@ import pytest
 from oracle.orcbind import Oracle
 from raytracing_b200 import capi
 from raytracing_b200.camera import default_camera
-from tests.helpers import bits, golden_files, load_golden, reference_sampler_tables, scene, synthetic_sampler_tables
+from tests.helpers import bits, fuzz_configs, golden_files, load_golden, reference_sampler_tables, scene, synthetic_sampler_tables
 
 pytestmark = pytest.mark.gpu
 
@@ -472,6 +472,22 @@ def test_degenerate_frames_match_oracle(case):
             check_stats(c.frame_stats(), ost, mb)
             assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(oacc[..., :3])), (case, stepwise, sample)
     for _, c in ctxs:
+        c.destroy()
+
+
+def test_fuzzed_frames_match_oracle():
+    """The seeded random configurations of tests/test_oracle_vs_ref.py (scenes, sizes, bounce counts, camera poses and lenses,
+    axis-aligned views): fused schedule vs the oracle, two progressive samples each."""
+    for name, w, h, mb, kw, wf in fuzz_configs():
+        sc = scene(name); cam = default_camera(w, h, **kw)
+        o = Oracle(sc)
+        c = capi.Context(w, h); c.upload_scene(sc); c.set_camera(cam); c.set_option(capi.OPT_WHITE_FURNACE, int(wf)); c.reset()
+        oacc = np.zeros((h, w, 4), dtype="<f4")
+        for sample in range(2):
+            oacc, _, ost = o.render(cam, w, h, mb, sample_idx=sample, white_furnace=wf, radiance=oacc)
+            c.integrate(mb)
+            check_stats(c.frame_stats(), ost, mb)
+            assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(oacc[..., :3])), (name, w, h, mb, kw, wf, sample)
         c.destroy()
 
 

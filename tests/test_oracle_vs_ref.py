@@ -10,7 +10,7 @@ import pytest
 from oracle import refbind
 from oracle.orcbind import Oracle
 from raytracing_b200.camera import default_camera
-from tests.helpers import bits, scene
+from tests.helpers import bits, fuzz_configs, scene
 
 pytestmark = pytest.mark.skipif(not refbind.available(), reason="oracle/_ref not built (no /root/reference here)")
 
@@ -166,6 +166,26 @@ def test_degenerate_frames_bit_exact_vs_reference_kernels(case):
         assert np.array_equal(bits(acc[..., :3]), bits(r.radiance()[..., :3]))
     if case == "all_miss":
         assert st["n_hit"][0] == 0 and st["n_ext"][1] == 0
+    r.close()
+
+
+@pytest.mark.parametrize("cfg", fuzz_configs(), ids=lambda c: f"{c[0]}_{c[1]}x{c[2]}_b{c[3]}")
+def test_fuzzed_frames_bit_exact_vs_reference_kernels(cfg):
+    """Seeded random scenes / sizes / bounce counts / camera poses and lenses, two progressive samples each."""
+    name, w, h, mb, kw, wf = cfg
+    sc = scene(name); cam = default_camera(w, h, **kw)
+    r = refbind.RefRenderer().open_arrays(sc)
+    r.begin(w, h); r.set_camera(cam); r.set_max_bounces(mb); r.enable_white_furnace(wf)
+    o = Oracle(sc)
+    acc = np.zeros((h, w, 4), dtype="<f4")
+    for sample in range(2):
+        r.integrate()
+        acc, hits, st = o.render(cam, w, h, mb, sample_idx=sample, white_furnace=wf, radiance=acc)
+        rs = r.stats()
+        for k in ("n_ext", "n_miss", "n_hit", "n_shadow", "n_cont", "n_unoccluded"):
+            assert np.array_equal(st[k][: mb + 1], rs[k][: mb + 1]), (k, sample)
+        assert np.array_equal(hits["primitive_id"], r.primary_hits()["primitive_id"])
+        assert np.array_equal(bits(acc[..., :3]), bits(r.radiance()[..., :3]))
     r.close()
 
 
