@@ -355,27 +355,51 @@ def main():
     host_np = host_img.numpy()
     cam_host = np.ascontiguousarray(cam)
 
-    def e2e_frame():
+    # N > 1 has two presentation paths: "parallel" — every rank resolves and reads back ITS rows into one shared, page-locked
+    # host image (N PCIe links), one barrier completes the frame; "gathered" — rank 0 resolves the NCCL-gathered frame and
+    # reads the whole image back over its one link.  Both are measured; the parallel one is the headline when available.
+    shared = None
+    if world > 1:
+        try:
+            from raytracing_b200.distributed import SharedHostImage
+            shared = SharedHostImage(w, h, rank, world)
+        except Exception as e:                         # collectively consistent: raised on every rank or on none
+            print(f"[bench] parallel read-back unavailable: {e}", file=sys.stderr)
+            shared = None
+
+    def e2e_frame(parallel=False):
         ctx.set_camera(cam_host)                       # per-frame input (render.cpp:188): 64 B host -> device (kernel parameter)
         frame()                                        # N > 1: ends with the NCCL gather of the radiance slabs to rank 0
         if world == 1:
             ctx.resolve(host_np)                       # resolve + device->host of the image; blocks
+        elif parallel:
+            ctx.resolve(shared.image)                  # this rank's rows -> the shared host image; blocks on this rank's stream
+            shared.complete()                          # one barrier: the image is whole on the host
         elif rank == 0:                                # rank 0 presents: resolve the WHOLE gathered frame + device->host; blocks
             ctx.resolve_gathered(gather.recv_ptr, gather.recv_stride_bytes, host_np)
-    for _ in range(3):
-        e2e_frame()
     e2e_steps = max(3, min(args.steps, 20))
-    e2e_reps = []
-    for _ in range(2):                                 # host-side hiccups (this loop is paced by the CPU) are not the path: best of two repetitions
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_frame()
-        barrier()
-        e2e_reps.append((time.perf_counter() - t0) * 1e3 / e2e_steps)
-    e2e_ms = torch.tensor([min(e2e_reps)], dtype=torch.float64, device=slab.device)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+
+    def time_e2e(parallel):
+        for _ in range(3):
+            e2e_frame(parallel)
+        reps = []
+        for _ in range(2):                             # host-side hiccups (this loop is paced by the CPU) are not the path: best of two repetitions
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_frame(parallel)
+            barrier()
+            reps.append((time.perf_counter() - t0) * 1e3 / e2e_steps)
+        ms = torch.tensor([min(reps)], dtype=torch.float64, device=slab.device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms, reps
+
+    e2e_ms, e2e_reps = time_e2e(False)
+    e2e_gathered_ms = None
+    if shared is not None:                             # N > 1: the figure above is the gathered path; the parallel path is the headline
+        e2e_gathered_ms = float(e2e_ms[0])
+        e2e_ms, e2e_reps = time_e2e(True)
     e2e_value = rays_per_frame / (float(e2e_ms[0]) * 1e-3) / 1e6
 
     # same end-to-end work with the read-back pipelined (rt_resolve_async): the D2H of frame i overlaps frame i+1
@@ -437,9 +461,14 @@ def main():
                        "l2": "per-step working set (ray/shadow queues + radiance, ~365 MB at 1080p) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_ms[0]), "steps": e2e_steps,
                     "repetitions_ms_per_step": [round(x, 4) for x in e2e_reps], "h2d_bytes_per_step": 64,
-                    "d2h_bytes_per_step": w * h * 16,
+                    "d2h_bytes_per_step": w * h * 16,          # the whole image reaches the host every step (N > 1: split over the ranks' links)
                     "api": ("rt_set_camera + rt_reset + rt_integrate + rt_resolve(host image), blocking per frame like ResolveRadiance/Finish()" if world == 1 else
-                            "every rank: rt_set_camera + rt_reset + rt_integrate + NCCL gather to rank 0; rank 0: rt_resolve_gathered(whole host image), blocking per frame"),
+                            ("every rank: rt_set_camera + rt_reset + rt_integrate + NCCL gather to rank 0 + rt_resolve of its rows into ONE shared page-locked host "
+                             "image (N PCIe links) + barrier; blocking per frame" if shared is not None else
+                             "every rank: rt_set_camera + rt_reset + rt_integrate + NCCL gather to rank 0; rank 0: rt_resolve_gathered(whole host image), blocking per frame")),
+                    "gathered_value": (rays_per_frame / (e2e_gathered_ms * 1e-3) / 1e6) if e2e_gathered_ms else None,
+                    "gathered_api": "rank 0: rt_resolve_gathered(whole host image) after the NCCL gather (one PCIe link)" if e2e_gathered_ms else None,
+                    "host_image_page_locked": (shared.pinned if shared is not None else True),
                     "pipelined_value": e2e_pipe_value, "pipelined_ms_per_step": float(e2e_pipe_ms[0]),
                     "pipelined_api": "same, with rt_resolve_async: image D2H of frame i overlaps frame i+1"},
             "gpu_launches": int(launches),
@@ -470,6 +499,8 @@ def main():
             except Exception:
                 line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "error": (out.stderr or out.stdout)[-300:]}
         print(json.dumps(line))
+    if shared is not None:
+        shared.close()
     ctx.destroy()
     if world > 1:
         dist.destroy_process_group()

@@ -54,3 +54,73 @@ class RadianceGather:
             n = local_rows(self.height, r, self.world)
             img[r::self.world] = s[: n * self.width].reshape(n, self.width, 4).cpu().numpy()
         return img
+
+
+class SharedHostImage:
+    """One width x height RGBA32F image in POSIX shared memory, mapped by every rank of the node and (on a GPU box)
+    page-locked in every process, so that each rank's rt_resolve writes ITS rows straight into the final image over its own
+    PCIe link (rt_resolve leaves the rows of other ranks untouched).  After `complete()` — one barrier — rank 0 holds the
+    whole frame on the host.  This is the parallel read-back path; the alternative is rt_resolve_gathered on rank 0 after
+    the NCCL gather (one PCIe link).  Collective: construct and close on all ranks."""
+
+    def __init__(self, width: int, height: int, rank: int, world: int, register_cuda: bool = True):
+        from multiprocessing import shared_memory
+        self.rank, self.world = rank, world
+        self.shm, self.image, self.pinned = None, None, False
+        nbytes = width * height * 16
+        name = [None]
+        if rank == 0:
+            try:
+                self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+                name[0] = self.shm.name
+            except Exception:
+                name[0] = None
+        if world > 1:
+            dist.broadcast_object_list(name, src=0)
+        ok = name[0] is not None
+        if ok and rank != 0:
+            try:
+                self.shm = shared_memory.SharedMemory(name=name[0])
+                try:    # the creating rank owns the segment; keep this process's resource tracker from unlinking it at exit
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(self.shm._name, "shared_memory")
+                except Exception:
+                    pass
+            except Exception:
+                ok = False
+        if world > 1:   # every rank learns whether every rank mapped the segment (no rank is left waiting in a later barrier)
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(int(flag[0]))
+        if not ok:
+            self._release()
+            raise RuntimeError("SharedHostImage: the shared-memory image could not be created / mapped on every rank")
+        self.image = np.ndarray((height, width, 4), dtype=np.float32, buffer=self.shm.buf)
+        if register_cuda and torch.cuda.is_available():
+            err = torch.cuda.cudart().cudaHostRegister(self.image.ctypes.data, nbytes, 0)
+            self.pinned = int(err) == 0         # not fatal: an unregistered mapping is read back through a staging copy
+
+    def _release(self):
+        self.image = None
+        if self.shm is not None:
+            self.shm.close()
+            if self.rank == 0:
+                try:
+                    self.shm.unlink()
+                except Exception:
+                    pass
+            self.shm = None
+
+    def complete(self):
+        """Every rank has finished writing its rows (each rank calls this after its blocking rt_resolve)."""
+        if self.world > 1:
+            dist.barrier()
+
+    def close(self):
+        if self.world > 1:
+            dist.barrier()
+        if self.pinned:
+            torch.cuda.cudart().cudaHostUnregister(self.image.ctypes.data)
+            self.pinned = False
+        self._release()

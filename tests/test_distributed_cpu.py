@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from raytracing_b200.distributed import RadianceGather, local_rows, rows_max
+from raytracing_b200.distributed import RadianceGather, SharedHostImage, local_rows, rows_max
 
 
 def _free_port():
@@ -51,3 +51,28 @@ def test_partition_gather_reassemble(tmp_path, world):
     ref, _, _ = Oracle(scene_io.load_scene("CornellBox")).render(default_camera(w, h), w, h, mb, want_hits=False)
     got = np.load(out)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def _shared_worker(rank, world, port, w, h, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    img = SharedHostImage(w, h, rank, world, register_cuda=False)
+    # what rt_resolve does with a full-image destination: this rank's rows only (row y belongs to rank y % world)
+    rows = np.arange(rank, h, world)
+    img.image[rows] = (rows[:, None, None] * 1000 + np.arange(w)[None, :, None] + np.arange(4)[None, None, :] * 0.25).astype(np.float32)
+    img.complete()
+    if rank == 0:
+        np.save(out_path, np.array(img.image))
+    img.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shared_host_image_collects_every_ranks_rows(tmp_path, world):
+    """The parallel read-back path: every rank writes its scanlines into one shared host image; after one barrier rank 0 sees the whole frame."""
+    w, h = 48, 29
+    out = str(tmp_path / "shared.npy")
+    mp.spawn(_shared_worker, args=(world, _free_port(), w, h, out), nprocs=world, join=True)
+    y = np.arange(h)
+    want = (y[:, None, None] * 1000 + np.arange(w)[None, :, None] + np.arange(4)[None, None, :] * 0.25).astype(np.float32)
+    assert np.array_equal(np.load(out), want)
