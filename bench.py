@@ -215,7 +215,7 @@ def main():
     ap.add_argument("--monolithic", action="store_true", help="fused schedule with ONE extend+shade kernel instead of trace -> queues -> shade")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for the whole run (split over warm-up + steps)")
-    ap.add_argument("--traversal", type=int, default=None, help="RT_OPT_TRAVERSAL override (0 literal, 1 fast, 2 per-lane refill)")
+    ap.add_argument("--traversal", type=int, default=None, help="RT_OPT_TRAVERSAL override (0 literal, 1 fast, 2 per-lane refill, 3 experimental 4-wide layout)")
     ap.add_argument("--refill-min", type=int, default=None, help="RT_OPT_REFILL_MIN override")
     ap.add_argument("--no-graph", action="store_true", help="RT_OPT_GRAPH=0: launch every kernel of the frame individually")
     ap.add_argument("--no-pdl", action="store_true", help="RT_OPT_PDL=0: no programmatic dependent launch between the kernels of a frame")
@@ -250,12 +250,12 @@ def main():
     name, w, h, mb = workload
     scene, cam = load_workload_scene(name, w, h, args.copies)
     ctx = capi.Context(w, h, device=local_rank, rank=rank, world=world)
+    if args.traversal is not None:
+        ctx.set_option(capi.OPT_TRAVERSAL, args.traversal)      # before the upload: mode 3 builds its layout there
     ctx.upload_scene(scene)
     ctx.set_camera(cam)
     if args.monolithic:
         ctx.set_option(capi.OPT_FUSION, 1)
-    if args.traversal is not None:
-        ctx.set_option(capi.OPT_TRAVERSAL, args.traversal)
     if args.no_graph:
         ctx.set_option(capi.OPT_GRAPH, 0)
     ctx.set_option(capi.OPT_OVERLAP, 0 if args.no_overlap else args.overlap)

@@ -69,6 +69,9 @@ typedef enum RtOption {
     RT_OPT_TRAVERSAL = 18,      /* 0: literal reference-order traversal on the reference node layout,
                                    1: child-box node layout, one ray per lane per grab (default),
                                    2: same traversal with per-lane ray refill (experiment, measured slower: DESIGN.md);
+                                   3: EXPERIMENTAL 4-wide collapse of the BVH traversed in the reference's order
+                                      (raytracing_b200/csrc/rt_wide4.h; pinned on the CPU by tools/wide4_check.py, not yet
+                                      measured on the GPU); must be selected before rt_upload_scene, which builds its layout;
                                    results are bit-identical */
     RT_OPT_AOV_ALWAYS = 21,     /* 1: produce the AOV buffers every frame even with the shaded-colour view (the reference always
                                    does; here they are skipped unless a view or the denoiser needs them) */

@@ -36,6 +36,7 @@
 #include "rt_b200.h"
 #include "rt_bvh_layout.h"
 #include "rt_device.cuh"
+#include "rt_wide4.h"
 
 using namespace rt;
 
@@ -841,6 +842,133 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_both(FrameParams p
 }
 
 
+// ---- EXPERIMENTAL 4-wide traversal layout (RT_OPT_TRAVERSAL = 3, rt_wide4.h) ---------------------------------
+// Separate kernels, so that the default kernels' code is untouched.  One persistent kernel covers the three uses of a
+// frame: closest-hit pass only (bounce 0), closest-hit pass + the previous bounce's shadow pass, shadow pass only.
+struct Wide4 { const float4* nodes; uint32_t n_f4; int root_ref; };
+struct W4OpsGlobal
+{
+    static __device__ __forceinline__ float4 ld(const float4* p) { return __ldg(p); }
+    static __device__ __forceinline__ float fmin(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float fmax(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ uint32_t bits(float f) { return __float_as_uint(f); }
+};
+struct W4OpsShared : W4OpsGlobal
+{
+    static __device__ __forceinline__ float4 ld(const float4* p) { return *p; }
+};
+
+template <bool ANY, bool SMEM>
+__device__ __forceinline__ uint32_t trace_w4(const DevScene& sc, const float4* w4, const float4* wtris, int root_ref, f3 o, f3 d, float t_min, float t_max,
+                                             float& bu, float& bv, float& bt)
+{
+    float fin = ((o.x + o.y) + o.z) + ((d.x + d.y) + d.z);
+    if (!(fabsf(fin) <= 3.0e38f) || d.x == 0.0f || d.y == 0.0f || d.z == 0.0f)
+    {   // non-finite rays, and rays whose slab test can produce 0 * inf: literal reference traversal
+        uint32_t nv = 0, nt = 0;
+        return trace_literal<ANY, false>(sc, o, d, t_min, t_max, bu, bv, bt, nv, nt);
+    }
+    const float4 rmin = __ldg(sc.nodes_ref), rmax = __ldg(sc.nodes_ref + 1);
+    if (SMEM) return trace_wide4<ANY, float4, W4OpsShared>(w4, wtris, root_ref, rmin, rmax, o.x, o.y, o.z, d.x, d.y, d.z, t_min, t_max, bu, bv, bt);
+    return trace_wide4<ANY, float4, W4OpsGlobal>(w4, wtris, root_ref, rmin, rmax, o.x, o.y, o.z, d.x, d.y, d.z, t_min, t_max, bu, bv, bt);
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_both_w4(FrameParams p, DevScene sc, Wide4 w, Queues q, DevCounters* ctr, float4* radiance,
+                                                                      uint32_t bounce, uint32_t shadow_bounce, int do_closest, int do_shadow)
+{
+    extern __shared__ __align__(128) float4 s_bvh[];
+    __shared__ uint64_t s_mbar;
+    const float4* nodes = w.nodes;
+    const float4* tris = sc.wtris;
+    if (SMEM)
+    {   // the same TMA bulk-copy staging as tma_stage_bvh, of the wide nodes + the triangle records
+        const uint32_t bar = smem_u32(&s_mbar);
+        const uint32_t nodes_bytes = w.n_f4 * 16u, tris_bytes = sc.wtris_f4 * 16u;
+        if (threadIdx.x == 0)
+        {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nodes_bytes + tris_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(s_bvh)), "l"(w.nodes), "r"(nodes_bytes), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(s_bvh + w.n_f4)), "l"(sc.wtris), "r"(tris_bytes), "r"(bar) : "memory");
+        }
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar), "r"(0) : "memory");
+        nodes = s_bvh; tris = s_bvh + w.n_f4;
+    }
+    pdl_wait(); pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    if (do_closest)
+    {
+        const uint32_t n = *in_count_ptr(ctr, bounce);
+        const int in = bounce & 1;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        for (;;)
+        {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&ctr->work_ext[bounce], 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n) break;
+            uint32_t i = base + lane;
+            bool live = i < n, hit = false;
+            float bu = 0.0f, bv = 0.0f, bt = 0.0f;
+            uint32_t prim = RT_INVALID_ID;
+            if (live)
+            {
+                float4 a = q.A[in][i], b = q.B[in][i];
+                prim = trace_w4<false, SMEM>(sc, nodes, tris, w.root_ref, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt);
+                hit = prim != RT_INVALID_ID;
+            }
+            const unsigned hmask = __ballot_sync(0xffffffffu, hit);
+            const unsigned mmask = __ballot_sync(0xffffffffu, live && !hit);
+            unsigned long long slot = 0ull;
+            if (lane == 0)
+                slot = atomicAdd((unsigned long long*)&ctr->hm[bounce], (unsigned long long)__popc(hmask) | ((unsigned long long)__popc(mmask) << 32));
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (hit) q.hitq[(uint32_t)slot + __popc(hmask & lt_mask)] = make_float4(bu, bv, __uint_as_float(prim), __uint_as_float(i));
+            else if (live) q.missq[(uint32_t)(slot >> 32) + __popc(mmask & lt_mask)] = i;
+        }
+    }
+    if (do_shadow)
+    {
+        const uint32_t n = ctr->emit[shadow_bounce].shadow;
+        for (;;)
+        {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&ctr->work_shadow[shadow_bounce], 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n) break;
+            uint32_t i = base + lane;
+            bool un = false;
+            if (i < n)
+            {
+                float4 a = q.sA[i], b = q.sB[i];
+                float bu, bv, bt;
+                un = trace_w4<true, SMEM>(sc, nodes, tris, w.root_ref, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt) == RT_INVALID_ID;
+                if (un)
+                {
+                    float4 c = q.sC[i];
+                    uint32_t li = local_index(p, __float_as_uint(a.w));
+                    float4 r = radiance[li];
+                    r.x += c.x; r.y += c.y; r.z += c.z;
+                    radiance[li] = r;
+                }
+            }
+            warp_count(&ctr->n_unoccluded[shadow_bounce], un);
+        }
+    }
+}
+
 // ---- traversal with per-lane ray refill ------------------------------------------------------------------
 // After the first diffuse bounce the rays of a warp are incoherent: their traversals have very different lengths and
 // a warp that waits for its slowest ray runs at ~13 of 32 lanes (ncu, profiles/r01b_trace_summary.txt).  Here a warp is
@@ -1202,6 +1330,7 @@ struct rt_ctx
     DevCounters* counters = nullptr;
     FrameDyn* d_dyn = nullptr;
     bool pdl = true;               // RT_OPT_PDL
+    float4* d_w4 = nullptr; uint32_t w4_f4 = 0; int w4_root = 0;   // RT_OPT_TRAVERSAL = 3 (rt_wide4.h), built by rt_upload_scene when selected
     int* d_bn = nullptr;           // sobol | scrambling | ranking (rt_upload_sampler_tables)
     struct Occupancy { const void* kernel; size_t smem; int per_sm; };
     std::vector<Occupancy> occupancy;   // resident CTAs per SM of each persistent kernel (persistent_grid)
@@ -1247,7 +1376,10 @@ static std::string g_create_error;
 #define RT_CHECK_CTX(ctx) do { if (!(ctx)) return RT_ERR_INVALID_ARGUMENT; } while (0)
 
 struct rt_ctx;
-extern "C" { static int launch_shadow_pass(rt_ctx* c, uint32_t bounce, cudaStream_t st); }   // defined with rt_shadow_accumulate
+extern "C" {   // defined with rt_shadow_accumulate
+static int launch_shadow_pass(rt_ctx* c, uint32_t bounce, cudaStream_t st);
+static int launch_wide4(rt_ctx* c, uint32_t bounce, uint32_t shadow_bounce, int do_closest, int do_shadow, cudaStream_t st);
+}
 
 namespace
 {
@@ -1361,7 +1493,9 @@ int persistent_grid(rt_ctx* c, const void* kernel, size_t dyn_smem)
 #define RT_PGRID(c, kern, smem) persistent_grid(c, (const void*)(kern), smem)
 
 // Can the traversal kernel of the next bounce also run a deferred shadow pass (k_trace_both)?
-bool merged_trace_available(const rt_ctx* c) { return c->fusion == 0 && c->traversal != 2 && !c->count_traversal && !c->kernel_timing; }
+bool merged_trace_available(const rt_ctx* c) { return c->fusion == 0 && c->traversal != 2 && c->traversal != 3 && !c->count_traversal && !c->kernel_timing; }
+// experimental 4-wide layout: its own merged kernel (closest-hit pass and / or shadow pass)
+bool wide4_active(const rt_ctx* c) { return c->traversal == 3 && c->d_w4 && c->fusion == 0 && !c->count_traversal; }
 
 // <<<grid, 256, smem, stream>>> with the programmatic-dependent-launch attribute when RT_OPT_PDL is on
 template <class... KArgs, class... Args>
@@ -1598,6 +1732,14 @@ int rt_upload_scene(rt_ctx* c, const RtSceneDesc* s)
         ds.root_ref = wl.root_ref;
         ds.wnodes_f4 = (uint32_t)wl.nodes.size(); ds.wtris_f4 = (uint32_t)wl.tris.size();
     }
+    c->d_w4 = nullptr; c->w4_f4 = 0; c->w4_root = 0;
+    if (c->traversal == 3)
+    {   // experimental 4-wide layout (rt_wide4.h), only built when selected before the upload
+        std::vector<rtw4::F4> w4;
+        c->w4_root = rtw4::build_wide4(s->nodes, s->n_nodes, w4);
+        c->w4_f4 = (uint32_t)w4.size();
+        if ((rc = upload(w4.data(), w4.size() * 16, (const void**)&c->d_w4))) return rc;
+    }
     c->scene_ready = true;
     ++c->config_gen;
     return RT_OK;
@@ -1667,7 +1809,10 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
         if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "fusion mode must be 0 or 1");
         c->fusion = (int)value; return RT_OK;
     case RT_OPT_TRAVERSAL:
-        if (value > 2) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "traversal mode must be 0, 1 or 2");
+        if (value > 3) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "traversal mode must be 0, 1, 2 or 3");
+        if (value == 3 && c->scene_ready && !c->d_w4)
+            RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "traversal mode 3 builds its layout in rt_upload_scene: select it before the upload");
+        { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
         c->traversal = (int)value; return RT_OK;
     case RT_OPT_REFILL_MIN:
         if (value < 1 || value > 32) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "refill threshold must be 1..32 lanes");
@@ -1839,7 +1984,13 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
         else k_extend_shade<false><<<RT_PGRID(c, k_extend_shade<false>, 0), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce, aov_params(c));
         return post_launch(c, "k_extend_shade");
     }
-    if (c->traversal == 2 && !c->count_traversal)
+    if (wide4_active(c))
+    {   // experimental 4-wide layout: this bounce's closest-hit pass (+ a deferred shadow pass of the previous bounce)
+        int with_shadow = c->shadow_deferred ? 1 : 0;
+        c->shadow_deferred = false;
+        int rc = launch_wide4(c, bounce, c->shadow_deferred_bounce, 1, with_shadow, c->stream); if (rc) return rc;
+    }
+    else if (c->traversal == 2 && !c->count_traversal)
     {
         TimedLaunch t(c, RT_K_TRACE_CLOSEST);
         k_trace_refill<false><<<RT_PGRID(c, k_trace_refill<false>, 0), 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, c->refill_min);
@@ -1869,8 +2020,21 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
     return post_launch(c, "k_shade_queues");
 }
 
+// experimental 4-wide layout: closest-hit pass of `bounce` and / or shadow pass of `shadow_bounce` in one kernel
+static int launch_wide4(rt_ctx* c, uint32_t bounce, uint32_t shadow_bounce, int do_closest, int do_shadow, cudaStream_t st)
+{
+    TimedLaunch t(c, do_closest ? RT_K_TRACE_BOTH : RT_K_SHADOW_ACCUMULATE, st);
+    Wide4 w = { c->d_w4, c->w4_f4, c->w4_root };
+    size_t stage = ((size_t)c->w4_f4 + c->scene.wtris_f4) * 16;
+    if (!c->smem_bvh || stage > 40 * 1024) stage = 0;
+    if (stage) launch_chain(c, k_trace_both_w4<true>, RT_PGRID(c, k_trace_both_w4<true>, stage), stage, st, frame_params(c), c->scene, w, c->q, c->counters, c->radiance, bounce, shadow_bounce, do_closest, do_shadow);
+    else launch_chain(c, k_trace_both_w4<false>, RT_PGRID(c, k_trace_both_w4<false>, 0), 0, st, frame_params(c), c->scene, w, c->q, c->counters, c->radiance, bounce, shadow_bounce, do_closest, do_shadow);
+    return post_launch(c, "k_trace_both_w4");
+}
+
 static int launch_shadow_pass(rt_ctx* c, uint32_t bounce, cudaStream_t st)
 {
+    if (wide4_active(c)) return launch_wide4(c, 0, bounce, 0, 1, st);
     TimedLaunch t(c, RT_K_SHADOW_ACCUMULATE, st);
     size_t stage = smem_stage_bytes(c);
     if (c->traversal == 2 && !c->count_traversal)
@@ -1887,7 +2051,7 @@ int rt_shadow_accumulate(rt_ctx* c, uint32_t bounce)
     int rc = join_shadow(c); if (rc) return rc;
     // The shadow pass of bounce b only shares the radiance buffer with LATER shading passes, so it may overlap the
     // closest-hit traversal of bounce b+1 (which touches neither).
-    if (c->overlap == 2 && merged_trace_available(c))
+    if (c->overlap == 2 && (merged_trace_available(c) || (wide4_active(c) && !c->kernel_timing)))
     {   // deferred: rt_extend_shade(b+1) runs it inside its traversal kernel; join_shadow() launches it for anyone else
         c->shadow_deferred = true; c->shadow_deferred_bounce = bounce;
         return RT_OK;

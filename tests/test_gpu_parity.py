@@ -8,6 +8,8 @@ radiance within 1e-4 relative"): this implementation is held to the stricter BIT
 for everything — hit indices, barycentrics, per-bounce ray counters and every radiance
 float — because oracle and kernels share one arithmetic policy.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -488,6 +490,28 @@ def test_fuzzed_frames_match_oracle():
             c.integrate(mb)
             check_stats(c.frame_stats(), ost, mb)
             assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(oacc[..., :3])), (name, w, h, mb, kw, wf, sample)
+        c.destroy()
+
+
+@pytest.mark.skipif(not os.environ.get("RT_TEST_EXPERIMENTAL"), reason="RT_OPT_TRAVERSAL=3 (4-wide layout) is pinned on the CPU by tools/wide4_check.py "
+                    "and has not run on a GPU yet: opt in with RT_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("name,w,h,mb", [("CornellBox", 256, 256, 4), ("ShaderBalls", 320, 180, 6), ("CornellBox_Dragon", 240, 135, 8)])
+def test_experimental_wide4_traversal_matches_oracle(name, w, h, mb):
+    """RT_OPT_TRAVERSAL = 3: the 4-wide collapse of the BVH traversed in the reference's order (rt_wide4.h)."""
+    sc = scene(name); cam = default_camera(w, h)
+    o = Oracle(sc)
+    oacc = np.zeros((h, w, 4), dtype="<f4")
+    for smem in (1, 0):
+        c = capi.Context(w, h)
+        c.set_option(capi.OPT_TRAVERSAL, 3)                 # before the upload: the layout is built there
+        c.set_option(capi.OPT_SMEM_BVH, smem)
+        c.upload_scene(sc); c.set_camera(cam); c.reset()
+        oacc[:] = 0
+        for sample in range(2):
+            oacc, _, ost = o.render(cam, w, h, mb, sample_idx=sample, radiance=oacc)
+            c.integrate(mb)
+            check_stats(c.frame_stats(), ost, mb)
+            assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(oacc[..., :3])), (smem, sample)
         c.destroy()
 
 
