@@ -212,11 +212,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="CornellBox", choices=sorted(WORKLOADS))
     ap.add_argument("--stepwise", action="store_true", help="time the one-kernel-per-reference-step schedule instead of the fused one")
-    ap.add_argument("--monolithic", action="store_true", help="fused schedule with ONE extend+shade kernel instead of trace -> queues -> shade")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for the whole run (split over warm-up + steps)")
-    ap.add_argument("--traversal", type=int, default=None, help="RT_OPT_TRAVERSAL override (0 literal, 1 fast, 2 per-lane refill, 3 experimental 4-wide layout)")
-    ap.add_argument("--refill-min", type=int, default=None, help="RT_OPT_REFILL_MIN override")
+    ap.add_argument("--traversal", type=int, default=None, help="RT_OPT_TRAVERSAL override (0 literal reference-order traversal, 1 child-box layout)")
     ap.add_argument("--no-graph", action="store_true", help="RT_OPT_GRAPH=0: launch every kernel of the frame individually")
     ap.add_argument("--no-pdl", action="store_true", help="RT_OPT_PDL=0: no programmatic dependent launch between the kernels of a frame")
     ap.add_argument("--overlap", type=int, default=2, help="RT_OPT_OVERLAP: 2 shadow pass inside the next traversal kernel (default), 1 second stream, 0 none")
@@ -251,11 +249,9 @@ def main():
     scene, cam = load_workload_scene(name, w, h, args.copies)
     ctx = capi.Context(w, h, device=local_rank, rank=rank, world=world)
     if args.traversal is not None:
-        ctx.set_option(capi.OPT_TRAVERSAL, args.traversal)      # before the upload: mode 3 builds its layout there
+        ctx.set_option(capi.OPT_TRAVERSAL, args.traversal)
     ctx.upload_scene(scene)
     ctx.set_camera(cam)
-    if args.monolithic:
-        ctx.set_option(capi.OPT_FUSION, 1)
     if args.no_graph:
         ctx.set_option(capi.OPT_GRAPH, 0)
     ctx.set_option(capi.OPT_OVERLAP, 0 if args.no_overlap else args.overlap)
@@ -263,8 +259,6 @@ def main():
         ctx.set_option(capi.OPT_PDL, 0)
     if args.no_smem_bvh:
         ctx.set_option(capi.OPT_SMEM_BVH, 0)
-    if args.refill_min is not None:
-        ctx.set_option(capi.OPT_REFILL_MIN, args.refill_min)
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
 
     # the local radiance slab as a torch tensor (zero copy) for the NCCL gather
@@ -456,7 +450,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{name} {w}x{h} 1spp {mb}-bounce, {len(scene['triangles'])} triangles, sample_idx 0, Reset+Integrate per step",
-                       "schedule": "stepwise" if args.stepwise else ("fused-monolithic" if args.monolithic else "fused: [closest-hit trace(b) + shadow pass(b-1)] -> hit/miss queues -> shade(b)"), "partition": f"scanline y%{world}",
+                       "schedule": "stepwise" if args.stepwise else "fused: [closest-hit trace(b) + shadow pass(b-1)] -> hit/miss queues -> shade(b)", "partition": f"scanline y%{world}",
                        "rays_per_step": rays_per_frame,
                        "l2": "per-step working set (ray/shadow queues + radiance, ~365 MB at 1080p) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_ms[0]), "steps": e2e_steps,

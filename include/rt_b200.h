@@ -67,12 +67,7 @@ typedef enum RtOption {
                                    the algorithmic-bytes figure of the roofline)     */
     RT_OPT_KERNEL_TIMING = 17,  /* 1: bracket every launch with CUDA events on the context's stream */
     RT_OPT_TRAVERSAL = 18,      /* 0: literal reference-order traversal on the reference node layout,
-                                   1: child-box node layout, one ray per lane per grab (default),
-                                   2: same traversal with per-lane ray refill (experiment, measured slower: DESIGN.md);
-                                   3: EXPERIMENTAL 4-wide collapse of the BVH traversed in the reference's order
-                                      (raytracing_b200/csrc/rt_wide4.h; pinned on the CPU by tools/wide4_check.py, not yet
-                                      measured on the GPU); must be selected before rt_upload_scene, which builds its layout;
-                                   results are bit-identical */
+                                   1: child-box node layout (default); results are bit-identical */
     RT_OPT_AOV_ALWAYS = 21,     /* 1: produce the AOV buffers every frame even with the shaded-colour view (the reference always
                                    does; here they are skipped unless a view or the denoiser needs them) */
     RT_OPT_SMEM_BVH = 22,       /* 1 (default): scenes whose traversal records fit 40 KB are staged into shared memory by a TMA
@@ -87,9 +82,6 @@ typedef enum RtOption {
                                    option, the scene or the partition changes; the camera and sample index are a node-parameter update) */
     RT_OPT_PDL = 25,            /* 1 (default): the traversal and shading kernels of a frame are chained by programmatic dependent launch
                                    (a kernel's CTAs start and stage the BVH while the previous kernel drains) */
-    RT_OPT_REFILL_MIN = 20,     /* traversal mode 2: refill a warp when at least this many lanes are idle (1..32) */
-    RT_OPT_FUSION = 19          /* rt_extend_shade: 0 = traversal kernel + hit/miss queue compaction + shading kernel
-                                   (default), 1 = one monolithic kernel; results are bit-identical */
 } RtOption;
 
 #define RT_MAX_BOUNCES 255u     /* bounce index range supported per frame (reference GUI: 0..5) */

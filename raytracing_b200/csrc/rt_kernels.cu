@@ -36,7 +36,6 @@
 #include "rt_b200.h"
 #include "rt_bvh_layout.h"
 #include "rt_device.cuh"
-#include "rt_wide4.h"
 
 using namespace rt;
 
@@ -677,46 +676,8 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams p, Queues q, Dev
     warp_count(&ctr->n_unoccluded[bounce], un);
 }
 
-// Fused IntersectRays + ShadeMissedRays + ShadeSurfaceHits: the ray is read once, the hit never
-// goes to memory.  Persistent warps drain the bounce's ray queue through a global atomic cursor
-// (work_ext[bounce]), 32 consecutive rays per grab, so the launch is sized by the machine
-// (SMs x resident CTAs), not by the image.
-template <bool COUNT>
-__global__ void __launch_bounds__(256) k_extend_shade(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce, AovParams aov)
-{
-    const uint32_t n = *in_count_ptr(ctr, bounce);
-    const int in = bounce & 1;
-    const int lane = threadIdx.x & 31;
-    uint32_t nv = 0, nt = 0;
-    for (;;)
-    {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctr->work_ext[bounce], 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + lane;
-        bool live = i < n, hit = false, miss = false;
-        uint32_t pixel = 0;
-        ShadeOut so;
-        so.emissive = so.spawn_next = so.spawn_shadow = false;
-        if (live)
-        {
-            float4 a = q.A[in][i], b = q.B[in][i], c = q.C[in][i];
-            pixel = __float_as_uint(a.w);
-            float bu = 0.0f, bv = 0.0f, bt = 0.0f;
-            uint32_t prim = trace<false, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
-            hit = prim != RT_INVALID_ID;
-            miss = !hit;
-            if (miss) shade_miss(sc, p, radiance, pixel, mk3(b), mk3(c));
-            else shade_hit(sc, p, aov, bounce, pixel, mk3(a), mk3(b), mk3(c), prim, bu, bv, so);
-        }
-        warp_count(&ctr->hm[bounce].miss, miss);
-        emit_rays(p, q, ctr, radiance, bounce, pixel, hit, so);
-    }
-    if (COUNT) { warp_sum64(&ctr->nodes_ext[bounce], nv); warp_sum64(&ctr->tris_ext[bounce], nt); }
-}
-
-// Fused IntersectShadowRays + AccumulateDirectSamples, persistent like k_extend_shade.
+// Fused IntersectShadowRays + AccumulateDirectSamples: persistent warps drain the bounce's shadow-ray queue through a
+// global atomic cursor (work_shadow[bounce]), 32 consecutive rays per grab.
 template <bool COUNT, bool SMEM>
 __device__ __forceinline__ void shadow_phase(const FrameParams& p, const DevScene& sc, int mode, const Queues& q, DevCounters* ctr, float4* radiance,
                                              uint32_t bounce, const float4* s_bvh)
@@ -841,330 +802,6 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_both(FrameParams p
     shadow_phase<false, SMEM>(p, sc, mode, q, ctr, radiance, shadow_bounce, s_bvh);
 }
 
-
-// ---- EXPERIMENTAL 4-wide traversal layout (RT_OPT_TRAVERSAL = 3, rt_wide4.h) ---------------------------------
-// Separate kernels, so that the default kernels' code is untouched.  One persistent kernel covers the three uses of a
-// frame: closest-hit pass only (bounce 0), closest-hit pass + the previous bounce's shadow pass, shadow pass only.
-struct Wide4 { const float4* nodes; uint32_t n_f4; int root_ref; };
-struct W4OpsGlobal
-{
-    static __device__ __forceinline__ float4 ld(const float4* p) { return __ldg(p); }
-    static __device__ __forceinline__ float fmin(float a, float b) { return fminf(a, b); }
-    static __device__ __forceinline__ float fmax(float a, float b) { return fmaxf(a, b); }
-    static __device__ __forceinline__ uint32_t bits(float f) { return __float_as_uint(f); }
-};
-struct W4OpsShared : W4OpsGlobal
-{
-    static __device__ __forceinline__ float4 ld(const float4* p) { return *p; }
-};
-
-template <bool ANY, bool SMEM>
-__device__ __forceinline__ uint32_t trace_w4(const DevScene& sc, const float4* w4, const float4* wtris, int root_ref, f3 o, f3 d, float t_min, float t_max,
-                                             float& bu, float& bv, float& bt)
-{
-    float fin = ((o.x + o.y) + o.z) + ((d.x + d.y) + d.z);
-    if (!(fabsf(fin) <= 3.0e38f) || d.x == 0.0f || d.y == 0.0f || d.z == 0.0f)
-    {   // non-finite rays, and rays whose slab test can produce 0 * inf: literal reference traversal
-        uint32_t nv = 0, nt = 0;
-        return trace_literal<ANY, false>(sc, o, d, t_min, t_max, bu, bv, bt, nv, nt);
-    }
-    const float4 rmin = __ldg(sc.nodes_ref), rmax = __ldg(sc.nodes_ref + 1);
-    if (SMEM) return trace_wide4<ANY, float4, W4OpsShared>(w4, wtris, root_ref, rmin, rmax, o.x, o.y, o.z, d.x, d.y, d.z, t_min, t_max, bu, bv, bt);
-    return trace_wide4<ANY, float4, W4OpsGlobal>(w4, wtris, root_ref, rmin, rmax, o.x, o.y, o.z, d.x, d.y, d.z, t_min, t_max, bu, bv, bt);
-}
-
-template <bool SMEM>
-__global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_both_w4(FrameParams p, DevScene sc, Wide4 w, Queues q, DevCounters* ctr, float4* radiance,
-                                                                      uint32_t bounce, uint32_t shadow_bounce, int do_closest, int do_shadow)
-{
-    extern __shared__ __align__(128) float4 s_bvh[];
-    __shared__ uint64_t s_mbar;
-    const float4* nodes = w.nodes;
-    const float4* tris = sc.wtris;
-    if (SMEM)
-    {   // the same TMA bulk-copy staging as tma_stage_bvh, of the wide nodes + the triangle records
-        const uint32_t bar = smem_u32(&s_mbar);
-        const uint32_t nodes_bytes = w.n_f4 * 16u, tris_bytes = sc.wtris_f4 * 16u;
-        if (threadIdx.x == 0)
-        {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nodes_bytes + tris_bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(s_bvh)), "l"(w.nodes), "r"(nodes_bytes), "r"(bar) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(s_bvh + w.n_f4)), "l"(sc.wtris), "r"(tris_bytes), "r"(bar) : "memory");
-        }
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done) : "r"(bar), "r"(0) : "memory");
-        nodes = s_bvh; tris = s_bvh + w.n_f4;
-    }
-    pdl_wait(); pdl_launch_dependents();
-    const int lane = threadIdx.x & 31;
-    if (do_closest)
-    {
-        const uint32_t n = *in_count_ptr(ctr, bounce);
-        const int in = bounce & 1;
-        const unsigned lt_mask = (1u << lane) - 1u;
-        for (;;)
-        {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&ctr->work_ext[bounce], 32u);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= n) break;
-            uint32_t i = base + lane;
-            bool live = i < n, hit = false;
-            float bu = 0.0f, bv = 0.0f, bt = 0.0f;
-            uint32_t prim = RT_INVALID_ID;
-            if (live)
-            {
-                float4 a = q.A[in][i], b = q.B[in][i];
-                prim = trace_w4<false, SMEM>(sc, nodes, tris, w.root_ref, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt);
-                hit = prim != RT_INVALID_ID;
-            }
-            const unsigned hmask = __ballot_sync(0xffffffffu, hit);
-            const unsigned mmask = __ballot_sync(0xffffffffu, live && !hit);
-            unsigned long long slot = 0ull;
-            if (lane == 0)
-                slot = atomicAdd((unsigned long long*)&ctr->hm[bounce], (unsigned long long)__popc(hmask) | ((unsigned long long)__popc(mmask) << 32));
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (hit) q.hitq[(uint32_t)slot + __popc(hmask & lt_mask)] = make_float4(bu, bv, __uint_as_float(prim), __uint_as_float(i));
-            else if (live) q.missq[(uint32_t)(slot >> 32) + __popc(mmask & lt_mask)] = i;
-        }
-    }
-    if (do_shadow)
-    {
-        const uint32_t n = ctr->emit[shadow_bounce].shadow;
-        for (;;)
-        {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&ctr->work_shadow[shadow_bounce], 32u);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= n) break;
-            uint32_t i = base + lane;
-            bool un = false;
-            if (i < n)
-            {
-                float4 a = q.sA[i], b = q.sB[i];
-                float bu, bv, bt;
-                un = trace_w4<true, SMEM>(sc, nodes, tris, w.root_ref, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt) == RT_INVALID_ID;
-                if (un)
-                {
-                    float4 c = q.sC[i];
-                    uint32_t li = local_index(p, __float_as_uint(a.w));
-                    float4 r = radiance[li];
-                    r.x += c.x; r.y += c.y; r.z += c.z;
-                    radiance[li] = r;
-                }
-            }
-            warp_count(&ctr->n_unoccluded[shadow_bounce], un);
-        }
-    }
-}
-
-// ---- traversal with per-lane ray refill ------------------------------------------------------------------
-// After the first diffuse bounce the rays of a warp are incoherent: their traversals have very different lengths and
-// a warp that waits for its slowest ray runs at ~13 of 32 lanes (ncu, profiles/r01b_trace_summary.txt).  Here a warp is
-// a pool of 32 traversal slots: a lane whose ray terminates parks its result, and as soon as `refill_min` lanes are
-// idle the warp (1) compacts the parked results into the hit / miss queues with ONE 64-bit atomic (hits in the low
-// word, misses in the high word; __ballot + __popc give every lane its slot), and (2) hands the idle lanes new rays
-// from a warp-level reservation of the global queue (one atomic per 128 rays).  The traversal itself is the same
-// while-while loop in the same order with the same arithmetic as trace_fast, so results are bit-identical.
-// ANY = shadow rays: first hit terminates; an unoccluded ray adds its light sample to the radiance (fused
-// AccumulateDirectSamples) instead of producing queue entries.
-template <bool ANY>
-__global__ void __launch_bounds__(256) k_trace_refill(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance,
-                                                      uint32_t bounce, int refill_min)
-{
-    const uint32_t n = ANY ? ctr->emit[bounce].shadow : *in_count_ptr(ctr, bounce);
-    uint32_t* cursor = ANY ? &ctr->work_shadow[bounce] : &ctr->work_ext[bounce];
-    const float4* __restrict__ A = ANY ? q.sA : q.A[bounce & 1];
-    const float4* __restrict__ B = ANY ? q.sB : q.B[bounce & 1];
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const uint32_t kReserve = 128;
-
-    uint32_t res_next = 0, res_end = 0;          // warp-uniform reservation [res_next, res_end) of queue slots
-    bool exhausted = false;                      // warp-uniform: the global queue has no more rays
-    bool has = false, parked = false, finish_now = false;
-    uint32_t ray_i = 0, prim = RT_INVALID_ID;
-    float bu = 0.0f, bv = 0.0f, t_max = 0.0f;
-    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), inv = mk3(0, 0, 0);
-    bool sx = false, sy = false, sz = false;
-    int cur = 0, sp = 0;
-    int stack_ref[64];
-    float stack_t[64];
-
-    for (;;)
-    {
-        const unsigned idle = __ballot_sync(0xffffffffu, !has);
-        if (idle != 0u && (__popc(idle) >= refill_min || idle == 0xffffffffu))
-        {
-            // (1) emit parked results
-            if (!ANY)
-            {
-                const unsigned hmask = __ballot_sync(0xffffffffu, parked && prim != RT_INVALID_ID);
-                const unsigned mmask = __ballot_sync(0xffffffffu, parked && prim == RT_INVALID_ID);
-                if ((hmask | mmask) != 0u)
-                {
-                    unsigned long long base = 0ull;
-                    if (lane == 0)
-                        base = atomicAdd((unsigned long long*)&ctr->hm[bounce], (unsigned long long)__popc(hmask) | ((unsigned long long)__popc(mmask) << 32));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (parked)
-                    {
-                        if (prim != RT_INVALID_ID)
-                            q.hitq[(uint32_t)base + __popc(hmask & lt_mask)] = make_float4(bu, bv, __uint_as_float(prim), __uint_as_float(ray_i));
-                        else
-                            q.missq[(uint32_t)(base >> 32) + __popc(mmask & lt_mask)] = ray_i;
-                    }
-                }
-            }
-            else
-            {
-                const bool un = parked && prim == RT_INVALID_ID;
-                if (un)
-                {   // accumulate_direct_samples.cl:27-53
-                    float4 a = A[ray_i], c = q.sC[ray_i];
-                    uint32_t li = local_index(p, __float_as_uint(a.w));
-                    float4 r = radiance[li];
-                    r.x += c.x; r.y += c.y; r.z += c.z;
-                    radiance[li] = r;
-                }
-                warp_count(&ctr->n_unoccluded[bounce], un);
-            }
-            parked = false;
-
-            // (2) refill idle lanes from the warp's reservation
-            unsigned need = idle;
-            while (need != 0u)
-            {
-                if (res_next == res_end)
-                {
-                    if (exhausted) break;
-                    uint32_t b = 0;
-                    if (lane == 0) b = atomicAdd(cursor, kReserve);
-                    b = __shfl_sync(0xffffffffu, b, 0);
-                    if (b >= n) { exhausted = true; break; }
-                    res_next = b; res_end = (b + kReserve < n) ? b + kReserve : n;
-                }
-                const uint32_t avail = res_end - res_next;
-                const uint32_t rank = (uint32_t)__popc(need & lt_mask);
-                const bool take = ((need >> lane) & 1u) && rank < avail;
-                if (take)
-                {
-                    ray_i = res_next + rank;
-                    float4 a = A[ray_i], b = B[ray_i];
-                    o = mk3(a); d = mk3(b); t_max = b.w;
-                    prim = RT_INVALID_ID; bu = 0.0f; bv = 0.0f;
-                    has = true; finish_now = false;
-                    float fin = ((o.x + o.y) + o.z) + ((d.x + d.y) + d.z);
-                    if (!(fabsf(fin) <= 3.0e38f))
-                    {   // non-finite ray: literal reference-order traversal (see trace_fast), result ready at once
-                        float bt = 0.0f; uint32_t nv = 0, nt = 0;
-                        prim = trace_literal<ANY, false>(sc, o, d, 0.0f, t_max, bu, bv, bt, nv, nt);
-                        finish_now = true;
-                    }
-                    else
-                    {
-                        inv = splat(1.0f) / d;
-                        sx = inv.x < 0; sy = inv.y < 0; sz = inv.z < 0;
-                        sp = 0; cur = sc.root_ref;
-                        // the reference tests every node it visits, including the root (trace_bvh.cl:144-148)
-                        float4 r0 = __ldg(sc.nodes_ref), r1 = __ldg(sc.nodes_ref + 1);
-                        f3 t0 = (mk3(r0) - o) * inv, t1 = (mk3(r1) - o) * inv;
-                        float lo = fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z));
-                        float hi = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
-                        if (!(fminf(hi, t_max) >= fmaxf(lo, 0.0f))) finish_now = true;
-                    }
-                }
-                const uint32_t wanted = (uint32_t)__popc(need);
-                res_next += wanted < avail ? wanted : avail;
-                need = __ballot_sync(0xffffffffu, ((need >> lane) & 1u) && !take);
-            }
-            if (__ballot_sync(0xffffffffu, has) == 0u) break;      // nothing in flight and nothing left to fetch
-        }
-
-        // One traversal ROUND ("if-if"): every lane that holds a ray performs at most one interior-record step and then at
-        // most one triangle test.  No lane ever waits for another lane's loop to finish: a lane inside a 4-triangle leaf
-        // shares its four rounds with other lanes' interior steps, and a lane whose ray terminates becomes refillable
-        // at the next round.  Order of node visits, triangle tests and t_max updates per ray is unchanged.
-        bool finished = has && finish_now;
-        if (has && !finish_now && cur >= 0)
-        {
-            const float4* np = sc.wnodes + (size_t)cur * 4;
-            float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2), m = __ldg(np + 3);
-            f3 t00 = (mk3(a.x, a.y, a.z) - o) * inv, t01 = (mk3(a.w, b.x, b.y) - o) * inv;
-            f3 t10 = (mk3(b.z, b.w, c.x) - o) * inv, t11 = (mk3(c.y, c.z, c.w) - o) * inv;
-            float lo0 = fmaxf(fmaxf(fmaxf(fminf(t00.x, t01.x), fminf(t00.y, t01.y)), fminf(t00.z, t01.z)), 0.0f);
-            float hi0 = fminf(fminf(fmaxf(t00.x, t01.x), fmaxf(t00.y, t01.y)), fmaxf(t00.z, t01.z));
-            float lo1 = fmaxf(fmaxf(fmaxf(fminf(t10.x, t11.x), fminf(t10.y, t11.y)), fminf(t10.z, t11.z)), 0.0f);
-            float hi1 = fminf(fminf(fmaxf(t10.x, t11.x), fmaxf(t10.y, t11.y)), fmaxf(t10.z, t11.z));
-            bool h0 = fminf(hi0, t_max) >= lo0, h1 = fminf(hi1, t_max) >= lo1;
-            int r0 = __float_as_int(m.x), r1 = __float_as_int(m.y);
-            uint32_t axis = __float_as_uint(m.z);
-            bool swap = axis == 0 ? sx : (axis == 1 ? sy : sz);
-            int near_ref = swap ? r1 : r0, far_ref = swap ? r0 : r1;
-            bool near_hit = swap ? h1 : h0, far_hit = swap ? h0 : h1;
-            float far_lo = swap ? lo0 : lo1;
-            if (near_hit)
-            {
-                if (far_hit) { stack_ref[sp] = far_ref; stack_t[sp] = far_lo; ++sp; }
-                cur = near_ref;
-            }
-            else if (far_hit) cur = far_ref;
-            else
-            {
-                bool found = false;
-                while (sp > 0) { --sp; if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; } }
-                if (!found) finished = true;
-            }
-        }
-        else if (has && !finish_now)
-        {   // cur < 0: the next triangle of the current leaf is ~cur
-            const uint32_t ti = (uint32_t)(~cur);
-            const float4* tp = sc.wtris + (size_t)ti * 3;
-            float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-            f3 p1 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
-            const bool last = __float_as_uint(q2.y) != 0u;
-            f3 pvec = cross(d, e2);
-            float det = dot(e1, pvec);
-            bool hit_tri = false;
-            if (!(det < 1e-8f || -det > 1e-8f))
-            {
-                float inv_det = 1.0f / det;
-                f3 tvec = o - p1;
-                float u = dot(tvec, pvec) * inv_det;
-                if (!(u < 0.0f || u > 1.0f))
-                {
-                    f3 qvec = cross(tvec, e1);
-                    float v = dot(d, qvec) * inv_det;
-                    if (!(v < 0.0f || u + v > 1.0f))
-                    {
-                        float t = dot(e2, qvec) * inv_det;
-                        if (!(t < 0.0f || t > t_max)) { bu = u; bv = v; prim = ANY ? 0u : ti; t_max = t; hit_tri = true; }
-                    }
-                }
-            }
-            if (ANY && hit_tri) finished = true;
-            else if (!last) cur = ~(int)(ti + 1u);
-            else
-            {
-                bool found = false;
-                while (sp > 0) { --sp; if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; } }
-                if (!found) finished = true;
-            }
-        }
-        if (finished) { has = false; parked = true; }
-    }
-}
 
 // ShadeSurfaceHits over the hit queue, then ShadeMissedRays over the miss queue (independent pixels).
 __global__ void __launch_bounds__(256, RT_MINB_SHADE) k_shade_queues(FrameParams p, DevScene sc, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce, AovParams aov)
@@ -1292,7 +929,7 @@ struct rt_ctx
     std::string error;
 
     // options
-    int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 1, fusion = 0, refill_min = 8, smem_bvh = 1;
+    int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 1, smem_bvh = 1;
 
     // per-pixel buffers
     Queues q = {};
@@ -1330,7 +967,6 @@ struct rt_ctx
     DevCounters* counters = nullptr;
     FrameDyn* d_dyn = nullptr;
     bool pdl = true;               // RT_OPT_PDL
-    float4* d_w4 = nullptr; uint32_t w4_f4 = 0; int w4_root = 0;   // RT_OPT_TRAVERSAL = 3 (rt_wide4.h), built by rt_upload_scene when selected
     int* d_bn = nullptr;           // sobol | scrambling | ranking (rt_upload_sampler_tables)
     struct Occupancy { const void* kernel; size_t smem; int per_sm; };
     std::vector<Occupancy> occupancy;   // resident CTAs per SM of each persistent kernel (persistent_grid)
@@ -1378,7 +1014,6 @@ static std::string g_create_error;
 struct rt_ctx;
 extern "C" {   // defined with rt_shadow_accumulate
 static int launch_shadow_pass(rt_ctx* c, uint32_t bounce, cudaStream_t st);
-static int launch_wide4(rt_ctx* c, uint32_t bounce, uint32_t shadow_bounce, int do_closest, int do_shadow, cudaStream_t st);
 }
 
 namespace
@@ -1493,9 +1128,7 @@ int persistent_grid(rt_ctx* c, const void* kernel, size_t dyn_smem)
 #define RT_PGRID(c, kern, smem) persistent_grid(c, (const void*)(kern), smem)
 
 // Can the traversal kernel of the next bounce also run a deferred shadow pass (k_trace_both)?
-bool merged_trace_available(const rt_ctx* c) { return c->fusion == 0 && c->traversal != 2 && c->traversal != 3 && !c->count_traversal && !c->kernel_timing; }
-// experimental 4-wide layout: its own merged kernel (closest-hit pass and / or shadow pass)
-bool wide4_active(const rt_ctx* c) { return c->traversal == 3 && c->d_w4 && c->fusion == 0 && !c->count_traversal; }
+bool merged_trace_available(const rt_ctx* c) { return !c->count_traversal && !c->kernel_timing; }
 
 // <<<grid, 256, smem, stream>>> with the programmatic-dependent-launch attribute when RT_OPT_PDL is on
 template <class... KArgs, class... Args>
@@ -1732,14 +1365,6 @@ int rt_upload_scene(rt_ctx* c, const RtSceneDesc* s)
         ds.root_ref = wl.root_ref;
         ds.wnodes_f4 = (uint32_t)wl.nodes.size(); ds.wtris_f4 = (uint32_t)wl.tris.size();
     }
-    c->d_w4 = nullptr; c->w4_f4 = 0; c->w4_root = 0;
-    if (c->traversal == 3)
-    {   // experimental 4-wide layout (rt_wide4.h), only built when selected before the upload
-        std::vector<rtw4::F4> w4;
-        c->w4_root = rtw4::build_wide4(s->nodes, s->n_nodes, w4);
-        c->w4_f4 = (uint32_t)w4.size();
-        if ((rc = upload(w4.data(), w4.size() * 16, (const void**)&c->d_w4))) return rc;
-    }
     c->scene_ready = true;
     ++c->config_gen;
     return RT_OK;
@@ -1805,18 +1430,10 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
         int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_;
         c->overlap = (int)value; return RT_OK;
     }
-    case RT_OPT_FUSION:
-        if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "fusion mode must be 0 or 1");
-        c->fusion = (int)value; return RT_OK;
     case RT_OPT_TRAVERSAL:
-        if (value > 3) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "traversal mode must be 0, 1, 2 or 3");
-        if (value == 3 && c->scene_ready && !c->d_w4)
-            RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "traversal mode 3 builds its layout in rt_upload_scene: select it before the upload");
+        if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "traversal mode must be 0 (literal) or 1 (child-box layout)");
         { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
         c->traversal = (int)value; return RT_OK;
-    case RT_OPT_REFILL_MIN:
-        if (value < 1 || value > 32) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "refill threshold must be 1..32 lanes");
-        c->refill_min = (int)value; return RT_OK;
     }
     RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "unknown option key %d", key);
 }
@@ -1976,27 +1593,7 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
 {
     RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
     c->cur_bounce = bounce;
-    if (c->fusion == 1)
-    {   // monolithic variant: trace + miss + shade in one kernel
-        { int rc = join_shadow(c); if (rc) return rc; }
-        TimedLaunch t(c, RT_K_EXTEND_SHADE);
-        if (c->count_traversal) k_extend_shade<true><<<RT_PGRID(c, k_extend_shade<true>, 0), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce, aov_params(c));
-        else k_extend_shade<false><<<RT_PGRID(c, k_extend_shade<false>, 0), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce, aov_params(c));
-        return post_launch(c, "k_extend_shade");
-    }
-    if (wide4_active(c))
-    {   // experimental 4-wide layout: this bounce's closest-hit pass (+ a deferred shadow pass of the previous bounce)
-        int with_shadow = c->shadow_deferred ? 1 : 0;
-        c->shadow_deferred = false;
-        int rc = launch_wide4(c, bounce, c->shadow_deferred_bounce, 1, with_shadow, c->stream); if (rc) return rc;
-    }
-    else if (c->traversal == 2 && !c->count_traversal)
-    {
-        TimedLaunch t(c, RT_K_TRACE_CLOSEST);
-        k_trace_refill<false><<<RT_PGRID(c, k_trace_refill<false>, 0), 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, c->refill_min);
-        int rc = post_launch(c, "k_trace_refill<closest>"); if (rc) return rc;
-    }
-    else if (c->shadow_deferred && merged_trace_available(c))
+    if (c->shadow_deferred && merged_trace_available(c))
     {   // this bounce's closest-hit traversal + the previous bounce's shadow pass in one kernel
         c->shadow_deferred = false;
         TimedLaunch t(c, RT_K_TRACE_BOTH);
@@ -2020,26 +1617,11 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
     return post_launch(c, "k_shade_queues");
 }
 
-// experimental 4-wide layout: closest-hit pass of `bounce` and / or shadow pass of `shadow_bounce` in one kernel
-static int launch_wide4(rt_ctx* c, uint32_t bounce, uint32_t shadow_bounce, int do_closest, int do_shadow, cudaStream_t st)
-{
-    TimedLaunch t(c, do_closest ? RT_K_TRACE_BOTH : RT_K_SHADOW_ACCUMULATE, st);
-    Wide4 w = { c->d_w4, c->w4_f4, c->w4_root };
-    size_t stage = ((size_t)c->w4_f4 + c->scene.wtris_f4) * 16;
-    if (!c->smem_bvh || stage > 40 * 1024) stage = 0;
-    if (stage) launch_chain(c, k_trace_both_w4<true>, RT_PGRID(c, k_trace_both_w4<true>, stage), stage, st, frame_params(c), c->scene, w, c->q, c->counters, c->radiance, bounce, shadow_bounce, do_closest, do_shadow);
-    else launch_chain(c, k_trace_both_w4<false>, RT_PGRID(c, k_trace_both_w4<false>, 0), 0, st, frame_params(c), c->scene, w, c->q, c->counters, c->radiance, bounce, shadow_bounce, do_closest, do_shadow);
-    return post_launch(c, "k_trace_both_w4");
-}
-
 static int launch_shadow_pass(rt_ctx* c, uint32_t bounce, cudaStream_t st)
 {
-    if (wide4_active(c)) return launch_wide4(c, 0, bounce, 0, 1, st);
     TimedLaunch t(c, RT_K_SHADOW_ACCUMULATE, st);
     size_t stage = smem_stage_bytes(c);
-    if (c->traversal == 2 && !c->count_traversal)
-        k_trace_refill<true><<<RT_PGRID(c, k_trace_refill<true>, 0), 256, 0, st>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce, c->refill_min);
-    else if (c->count_traversal) k_shadow_accumulate<true, false><<<RT_PGRID(c, (k_shadow_accumulate<true, false>), 0), 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    if (c->count_traversal) k_shadow_accumulate<true, false><<<RT_PGRID(c, (k_shadow_accumulate<true, false>), 0), 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
     else if (stage) k_shadow_accumulate<false, true><<<RT_PGRID(c, (k_shadow_accumulate<false, true>), stage), 256, stage, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
     else k_shadow_accumulate<false, false><<<RT_PGRID(c, (k_shadow_accumulate<false, false>), 0), 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
     return post_launch(c, "k_shadow_accumulate");
@@ -2051,7 +1633,7 @@ int rt_shadow_accumulate(rt_ctx* c, uint32_t bounce)
     int rc = join_shadow(c); if (rc) return rc;
     // The shadow pass of bounce b only shares the radiance buffer with LATER shading passes, so it may overlap the
     // closest-hit traversal of bounce b+1 (which touches neither).
-    if (c->overlap == 2 && (merged_trace_available(c) || (wide4_active(c) && !c->kernel_timing)))
+    if (c->overlap == 2 && merged_trace_available(c))
     {   // deferred: rt_extend_shade(b+1) runs it inside its traversal kernel; join_shadow() launches it for anyone else
         c->shadow_deferred = true; c->shadow_deferred_bounce = bounce;
         return RT_OK;

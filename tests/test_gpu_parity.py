@@ -87,7 +87,7 @@ def test_matches_reference_golden(path, fused):
     ("ShaderBalls", 480, 270, 8),
     ("CornellBox_Dragon", 384, 216, 16),
 ])
-@pytest.mark.parametrize("traversal", [0, 1, 2], ids=["literal", "fast", "refill"])
+@pytest.mark.parametrize("traversal", [0, 1], ids=["literal", "fast"])
 def test_fused_and_stepwise_match_oracle(name, w, h, mb, traversal):
     """CUDA (both schedules, both traversal kernels) vs the CPU oracle, live, two accumulated samples."""
     sc = scene(name)
@@ -95,37 +95,20 @@ def test_fused_and_stepwise_match_oracle(name, w, h, mb, traversal):
     o = Oracle(sc)
     oacc = np.zeros((h, w, 4), dtype="<f4")
     ctxs = {}
-    for mode in ("fused", "monolithic", "stepwise"):
+    for mode in ("fused", "stepwise"):
         c = make_ctx(name, w, h)
         c.set_option(capi.OPT_TRAVERSAL, traversal)
-        c.set_option(capi.OPT_FUSION, 1 if mode == "monolithic" else 0)
         c.reset()
         ctxs[mode] = c
     for sample in range(2):
         oacc, ohits, ost = o.render(cam, w, h, mb, sample_idx=sample, radiance=oacc)
         ctxs["fused"].integrate(mb)
-        ctxs["monolithic"].integrate(mb)
         ctxs["stepwise"].integrate_stepwise(mb)
         for mode, c in ctxs.items():
             check_stats(c.frame_stats(), ost, mb)
             assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(oacc[..., :3])), (mode, sample)
     for c in ctxs.values():
         c.destroy()
-
-
-@pytest.mark.parametrize("refill_min", [1, 5, 32])
-def test_refill_threshold_does_not_change_results(refill_min):
-    """Per-lane ray refill (traversal mode 2) with extreme thresholds: compaction order changes, per-pixel results must not."""
-    name, w, h, mb = "ShaderBalls", 257, 131, 6
-    cam = default_camera(w, h)
-    orad, _, ost = Oracle(scene(name)).render(cam, w, h, mb)
-    c = make_ctx(name, w, h)
-    c.set_option(capi.OPT_TRAVERSAL, 2)
-    c.set_option(capi.OPT_REFILL_MIN, refill_min)
-    c.reset(); c.integrate(mb)
-    check_stats(c.frame_stats(), ost, mb)
-    assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(orad[..., :3]))
-    c.destroy()
 
 
 def test_traversal_work_counters_match_oracle():
@@ -346,9 +329,8 @@ def test_blue_noise_sampler_matches_oracle(name, w, h, mb, wf, tables):
     sc = scene(name); cam = default_camera(w, h)
     o = Oracle(sc)
     ctxs = {}
-    for mode in ("fused", "monolithic", "stepwise"):
+    for mode in ("fused", "stepwise"):
         c = make_ctx(name, w, h)
-        c.set_option(capi.OPT_FUSION, 1 if mode == "monolithic" else 0)
         c.set_option(capi.OPT_WHITE_FURNACE, int(wf))
         c.upload_sampler_tables(*t)
         c.set_option(capi.OPT_SAMPLER, 1)
@@ -382,7 +364,7 @@ def test_root_leaf_bvh_and_tiny_images(n_tris):
     for (w, h) in [(1, 1), (33, 3)]:
         cam = default_camera(w, h)
         orad, _, ost = Oracle(sc).render(cam, w, h, 3)
-        for traversal in (0, 1, 2):
+        for traversal in (0, 1):
             c = capi.Context(w, h); c.upload_scene(sc); c.set_camera(cam); c.set_option(capi.OPT_TRAVERSAL, traversal)
             c.reset(); c.integrate(3)
             check_stats(c.frame_stats(), ost, 3)
@@ -490,28 +472,6 @@ def test_fuzzed_frames_match_oracle():
             c.integrate(mb)
             check_stats(c.frame_stats(), ost, mb)
             assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(oacc[..., :3])), (name, w, h, mb, kw, wf, sample)
-        c.destroy()
-
-
-@pytest.mark.skipif(not os.environ.get("RT_TEST_EXPERIMENTAL"), reason="RT_OPT_TRAVERSAL=3 (4-wide layout) is pinned on the CPU by tools/wide4_check.py "
-                    "and has not run on a GPU yet: opt in with RT_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("name,w,h,mb", [("CornellBox", 256, 256, 4), ("ShaderBalls", 320, 180, 6), ("CornellBox_Dragon", 240, 135, 8)])
-def test_experimental_wide4_traversal_matches_oracle(name, w, h, mb):
-    """RT_OPT_TRAVERSAL = 3: the 4-wide collapse of the BVH traversed in the reference's order (rt_wide4.h)."""
-    sc = scene(name); cam = default_camera(w, h)
-    o = Oracle(sc)
-    oacc = np.zeros((h, w, 4), dtype="<f4")
-    for smem in (1, 0):
-        c = capi.Context(w, h)
-        c.set_option(capi.OPT_TRAVERSAL, 3)                 # before the upload: the layout is built there
-        c.set_option(capi.OPT_SMEM_BVH, smem)
-        c.upload_scene(sc); c.set_camera(cam); c.reset()
-        oacc[:] = 0
-        for sample in range(2):
-            oacc, _, ost = o.render(cam, w, h, mb, sample_idx=sample, radiance=oacc)
-            c.integrate(mb)
-            check_stats(c.frame_stats(), ost, mb)
-            assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(oacc[..., :3])), (smem, sample)
         c.destroy()
 
 
