@@ -51,6 +51,11 @@ def load_workload_scene(name, w, h, copies=183):
     return scene_io.load_scene(name), default_camera(w, h)
 
 
+def workload_string(name, w, h, mb):
+    """config.workload — the same text in both arms (the driver compares the two strings)."""
+    return f"{name} {w}x{h} 1spp {mb}-bounce, default camera of the workload, sample_idx 0, Reset+Integrate per step"
+
+
 def algorithmic_bytes(st, mb, n_pix):
     """compulsory traffic of the reference layout, from per-bounce counters.
     Returns (total bytes per frame, bytes attributable to the fused extend+shade kernel)."""
@@ -127,6 +132,61 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def issue_roofline(name, world, ktimes, steps, sm_mhz, n_sms, peak_hbm, alg_of):
+    """Roofline of the step's dominant kernel class from MEASURED quantities: CUDA-event time of this run (ktimes) and the
+    per-frame instruction / DRAM counters of the committed ncu capture of the same workload (profiles/traffic.json, written
+    by profiles/make_summaries.py from `ncu --set full`).  Two ceilings are evaluated and the binding one is reported:
+      issue: warp instructions per second / (SMs x 4 schedulers x SM clock)   [one warp instruction per scheduler and clock]
+      hbm:   DRAM bytes per second / MEASURED_PEAKS.json hbm_gbs
+    plus the lane occupancy (thread instructions / 32 x warp instructions): the share of the issued lanes that did work."""
+    try:
+        tj = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+        wk = tj["workloads"][name]["kernels"]
+        tag = tj["workloads"][name].get("tag")
+    except Exception:
+        wk, tag = {}, None
+    issue_peak = n_sms * 4 * sm_mhz * 1e6                      # warp instructions per second
+    rows = {}
+    for k, (ms, n) in ktimes.items():
+        if not n or ms <= 0 or k not in alg_of:
+            continue
+        sec = ms * 1e-3 / steps                                # seconds per frame spent in this kernel class
+        row = {"kernel": k, "ms_per_step": ms / steps, "launches_per_step": n / steps,
+               "algorithmic_GBs": alg_of[k] / world / sec / 1e9}
+        c = wk.get(k)
+        if c:
+            scale = 1.0 / world                                # counters were captured on the whole frame; a rank owns 1/world of it
+            inst, tinst, dram = c["inst_per_frame"] * scale, c["thread_inst_per_frame"] * scale, c["dram_bytes_per_frame"] * scale
+            row.update({"issue_achieved_Ginst_s": inst / sec / 1e9, "issue_frac": inst / sec / issue_peak,
+                        "lane_occupancy": tinst / (32.0 * inst), "hbm_achieved_GBs": dram / sec / 1e9, "hbm_frac": dram / sec / 1e9 / peak_hbm,
+                        "traffic_bytes_per_launch": dram / max(n / steps, 1), "warp_inst_per_frame": inst})
+        rows[k] = row
+    if not rows:
+        return {"bound": None, "frac": None, "note": "no per-kernel times"}
+    dom = max(rows, key=lambda k: rows[k]["ms_per_step"])
+    d = rows[dom]
+    out = {"kernel": dom, "kernel_ms_per_step": d["ms_per_step"], "kernel_launches_per_step": d["launches_per_step"],
+           "peak_issue_Ginst_s": issue_peak / 1e9, "sm_mhz_used": sm_mhz, "n_sms": n_sms, "counter_source": f"profiles/traffic.json ({tag})" if tag else None,
+           "other_kernels": [v for k, v in rows.items() if k != dom]}
+    if "issue_frac" in d:
+        issue_bound = d["issue_frac"] >= d["hbm_frac"]
+        out.update({"bound": "issue" if issue_bound else "hbm",
+                    "achieved": d["issue_achieved_Ginst_s"] if issue_bound else d["hbm_achieved_GBs"],
+                    "peak": issue_peak / 1e9 if issue_bound else peak_hbm,
+                    "unit": "Gwarp-inst/s" if issue_bound else "GB/s",
+                    "frac": d["issue_frac"] if issue_bound else d["hbm_frac"],
+                    "issue": {"achieved": d["issue_achieved_Ginst_s"], "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s", "frac": d["issue_frac"],
+                              "lane_occupancy": d["lane_occupancy"], "effective_frac": d["issue_frac"] * d["lane_occupancy"]},
+                    "hbm": {"achieved": d["hbm_achieved_GBs"], "peak": peak_hbm, "unit": "GB/s", "frac": d["hbm_frac"]},
+                    "traffic": d["traffic_bytes_per_launch"]})
+    else:
+        out.update({"bound": None, "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                    "note": f"no committed ncu counters for workload {name} in profiles/traffic.json"})
+    out["algorithmic"] = {"achieved_GBs": d["algorithmic_GBs"], "note": "SURVEY 8(d) byte model (48 B per BVH node visit / triangle test); "
+                          "secondary figure, not a bound: node and triangle fetches are L1/L2 hits"}
+    return out
+
+
 def host_threads() -> int:
     """Threads the CPU arm may really use: the affinity mask, capped by the cgroup CPU quota when one is set."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -196,7 +256,7 @@ def run_reference_arm(args, workload):
         "impl": "reference", "metric": "Mrays/sec @1920x1080x8-bounce", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name} {w}x{h} 1spp {mb}-bounce, default camera, sample_idx 0", "device": "host CPU"},
+        "config": {"workload": workload_string(name, w, h, mb), "device": "host CPU"},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": info[1], "kind": info[0], "sample": info[2]},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -215,6 +275,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for the whole run (split over warm-up + steps)")
     ap.add_argument("--traversal", type=int, default=None, help="RT_OPT_TRAVERSAL override (0 literal reference-order traversal, 1 child-box layout)")
+    ap.add_argument("--frame-kernel", type=int, default=2, help="RT_OPT_FRAME_KERNEL: 2 by partition size (default), 1 one persistent kernel per frame, 0 one kernel per phase")
+    ap.add_argument("--secondary", default="Synthetic10M", help="second north_star scene measured (device-timed, same N) and reported under 'secondary'; 'none' to skip")
+    ap.add_argument("--secondary-steps", type=int, default=8)
     ap.add_argument("--no-graph", action="store_true", help="RT_OPT_GRAPH=0: launch every kernel of the frame individually")
     ap.add_argument("--no-pdl", action="store_true", help="RT_OPT_PDL=0: no programmatic dependent launch between the kernels of a frame")
     ap.add_argument("--overlap", type=int, default=2, help="RT_OPT_OVERLAP: 2 shadow pass inside the next traversal kernel (default), 1 second stream, 0 none")
@@ -245,104 +308,143 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL logs to stdout by default; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    import types
+
+    def device_run(workload, n_steps):
+        """Scene upload, one counter frame, warm-up, n_steps device-timed frames (CUDA events on the context's stream, barrier +
+        synchronize on both sides, max over ranks), then the same frames once more with per-launch events for the per-kernel
+        split.  Returns everything the JSON line and the end-to-end legs need."""
+        name, w, h, mb = workload
+        steps = n_steps
+        scene, cam = load_workload_scene(name, w, h, args.copies)
+        ctx = capi.Context(w, h, device=local_rank, rank=rank, world=world)
+        if args.traversal is not None:
+            ctx.set_option(capi.OPT_TRAVERSAL, args.traversal)
+        ctx.upload_scene(scene)
+        ctx.set_camera(cam)
+        ctx.set_option(capi.OPT_FRAME_KERNEL, args.frame_kernel)
+        if args.no_graph:
+            ctx.set_option(capi.OPT_GRAPH, 0)
+        ctx.set_option(capi.OPT_OVERLAP, 0 if args.no_overlap else args.overlap)
+        if args.no_pdl:
+            ctx.set_option(capi.OPT_PDL, 0)
+        if args.no_smem_bvh:
+            ctx.set_option(capi.OPT_SMEM_BVH, 0)
+        stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
+
+        # the local radiance slab as a torch tensor (zero copy) for the NCCL gather
+        ptr, nbytes = ctx.radiance_device_ptr()
+        n_local = ctx.local_pixel_count()
+
+        class _Slab:
+            __cuda_array_interface__ = {"shape": (n_local, 4), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+        slab = torch.as_tensor(_Slab(), device=torch.device("cuda", local_rank))
+        from raytracing_b200.distributed import RadianceGather
+        gather = RadianceGather(w, h, rank, world, slab.device)
+
+        def frame():
+            ctx.reset()
+            if args.stepwise:
+                ctx.integrate_stepwise(mb)
+            else:
+                ctx.integrate(mb)
+            if world > 1:
+                with torch.cuda.stream(stream):
+                    gather.gather(slab)                         # the ONE collective of the frame (NCCL, NVLink/NVSwitch)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- one instrumented frame (untimed): per-bounce counters incl. traversal work -> rays/frame, algorithmic bytes
+        ctx.set_option(capi.OPT_COUNT_TRAVERSAL, 1)
+        ctx.reset(); ctx.integrate(mb); ctx.sync()
+        st = ctx.frame_stats()
+        ctx.set_option(capi.OPT_COUNT_TRAVERSAL, 0)
+        counters = torch.tensor([float(st[k][: mb + 1].sum()) for k in ("n_ext", "n_shadow")] +
+                                list(algorithmic_bytes(st, mb, n_local)), dtype=torch.float64, device=slab.device)
+        if world > 1:
+            dist.all_reduce(counters)
+        rays_per_frame = float(counters[0] + counters[1])
+        alg_total, alg_trace, alg_shade, alg_shadow = (float(counters[i]) for i in (2, 3, 4, 5))
+        alg_of = {"trace_closest": alg_trace, "shade_queues": alg_shade, "shadow_accumulate": alg_shadow, "extend_shade": alg_trace + alg_shade,
+                  "intersect": alg_trace, "hit": alg_shade, "intersect_shadow": alg_shadow}
+
+        # ---- warm-up, then K timed steps: barrier + synchronize on both sides, CUDA events on the launching stream
+        for _ in range(args.warmup):
+            frame()
+        barrier()
+        launches0 = ctx.launch_count()
+        sampler = ClockSampler(local_rank).prepare(); sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(steps):
+            frame()
+        ev1.record(stream)
+        if sampler.h is not None and sampler.err is None:
+            try:
+                sampler.sample()            # the K steps are enqueued and running: at least this sample is taken under load
+            except Exception as e:          # noqa: BLE001
+                sampler.err = repr(e)
+        barrier()
+        sampler.stop_flag = True
+        ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=slab.device)
+        if world > 1:
+            dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+        ms_per_step = float(ms_total[0]) / steps
+        launches = ctx.launch_count() - launches0
+        sampler.join(timeout=2)
+        # Per-kernel durations for the roofline.  In the timed region above the frame is ONE CUDA-graph launch and the shadow
+        # pass of a bounce runs inside the next bounce's traversal kernel, so per-launch CUDA events are neither possible (graph)
+        # nor would they separate the two passes: the same K steps are run once more, in this same process, with
+        # per-launch events on, individual launches and the overlap off.
+        ctx.set_option(capi.OPT_KERNEL_TIMING, 1)
+        ctx.set_option(capi.OPT_OVERLAP, 0)
+        for _ in range(2):
+            frame()
+        barrier()
+        ctx.kernel_times()
+        for _ in range(steps):
+            frame()
+        barrier()
+        ktimes = ctx.kernel_times()
+        ctx.set_option(capi.OPT_KERNEL_TIMING, 0)
+        if not args.no_overlap:
+            ctx.set_option(capi.OPT_OVERLAP, args.overlap)
+        value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
+        n_prim = torch.tensor([float(st["n_ext"][0]), float(st["n_miss"][0])], dtype=torch.float64, device=slab.device)
+        if world > 1:
+            dist.all_reduce(n_prim)
+        primary_hit_fraction = 1.0 - float(n_prim[1]) / max(float(n_prim[0]), 1.0)
+        # the collective alone (the NCCL gather of the radiance slabs to rank 0), device-timed on the render stream, max over ranks
+        collective_ms = None
+        if world > 1:
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            for _ in range(steps):
+                with torch.cuda.stream(stream):
+                    gather.gather(slab)
+            c1.record(stream)
+            barrier()
+            cm = torch.tensor([c0.elapsed_time(c1) / steps], dtype=torch.float64, device=slab.device)
+            dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+            collective_ms = float(cm[0])
+        n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        fk_used = args.frame_kernel == 1 or (args.frame_kernel == 2 and n_local <= n_sms * 4096)
+        schedule = ("stepwise: one kernel per reference kernel" if args.stepwise else
+                    ("one persistent kernel per frame, CTA-private wavefronts: T(b) [closest-hit trace(b) + shadow pass(b-1)] -> S(b) [shade hit/miss queues]" if fk_used else
+                     "per-phase kernels: [closest-hit trace(b) + shadow pass(b-1)] -> hit/miss queues -> shade(b), one CUDA graph per frame"))
+
+        return types.SimpleNamespace(**{k: v for k, v in locals().items() if k not in ("workload",)})
+
+    R = device_run(workload, args.steps)
     name, w, h, mb = workload
-    scene, cam = load_workload_scene(name, w, h, args.copies)
-    ctx = capi.Context(w, h, device=local_rank, rank=rank, world=world)
-    if args.traversal is not None:
-        ctx.set_option(capi.OPT_TRAVERSAL, args.traversal)
-    ctx.upload_scene(scene)
-    ctx.set_camera(cam)
-    if args.no_graph:
-        ctx.set_option(capi.OPT_GRAPH, 0)
-    ctx.set_option(capi.OPT_OVERLAP, 0 if args.no_overlap else args.overlap)
-    if args.no_pdl:
-        ctx.set_option(capi.OPT_PDL, 0)
-    if args.no_smem_bvh:
-        ctx.set_option(capi.OPT_SMEM_BVH, 0)
-    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
-
-    # the local radiance slab as a torch tensor (zero copy) for the NCCL gather
-    ptr, nbytes = ctx.radiance_device_ptr()
-    n_local = ctx.local_pixel_count()
-
-    class _Slab:
-        __cuda_array_interface__ = {"shape": (n_local, 4), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
-    slab = torch.as_tensor(_Slab(), device=torch.device("cuda", local_rank))
-    from raytracing_b200.distributed import RadianceGather
-    gather = RadianceGather(w, h, rank, world, slab.device)
-
-    def frame():
-        ctx.reset()
-        if args.stepwise:
-            ctx.integrate_stepwise(mb)
-        else:
-            ctx.integrate(mb)
-        if world > 1:
-            with torch.cuda.stream(stream):
-                gather.gather(slab)                         # the ONE collective of the frame (NCCL, NVLink/NVSwitch)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- one instrumented frame (untimed): per-bounce counters incl. traversal work -> rays/frame, algorithmic bytes
-    ctx.set_option(capi.OPT_COUNT_TRAVERSAL, 1)
-    ctx.reset(); ctx.integrate(mb); ctx.sync()
-    st = ctx.frame_stats()
-    ctx.set_option(capi.OPT_COUNT_TRAVERSAL, 0)
-    counters = torch.tensor([float(st[k][: mb + 1].sum()) for k in ("n_ext", "n_shadow")] +
-                            list(algorithmic_bytes(st, mb, n_local)), dtype=torch.float64, device=slab.device)
-    if world > 1:
-        dist.all_reduce(counters)
-    rays_per_frame = float(counters[0] + counters[1])
-    alg_total, alg_trace, alg_shade, alg_shadow = (float(counters[i]) for i in (2, 3, 4, 5))
-    alg_of = {"trace_closest": alg_trace, "shade_queues": alg_shade, "shadow_accumulate": alg_shadow, "extend_shade": alg_trace + alg_shade,
-              "intersect": alg_trace, "hit": alg_shade, "intersect_shadow": alg_shadow}
-
-    # ---- warm-up, then K timed steps: barrier + synchronize on both sides, CUDA events on the launching stream
-    for _ in range(args.warmup):
-        frame()
-    barrier()
-    launches0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank).prepare(); sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        frame()
-    ev1.record(stream)
-    if sampler.h is not None and sampler.err is None:
-        try:
-            sampler.sample()            # the K steps are enqueued and running: at least this sample is taken under load
-        except Exception as e:          # noqa: BLE001
-            sampler.err = repr(e)
-    barrier()
-    sampler.stop_flag = True
-    ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=slab.device)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms_total[0]) / args.steps
-    launches = ctx.launch_count() - launches0
-    sampler.join(timeout=2)
-    # Per-kernel durations for the roofline.  In the timed region above the frame is ONE CUDA-graph launch and the shadow
-    # pass of a bounce runs inside the next bounce's traversal kernel, so per-launch CUDA events are neither possible (graph)
-    # nor would they separate the two passes: the same K steps are run once more, in this same process, with
-    # per-launch events on, individual launches and the overlap off.
-    ctx.set_option(capi.OPT_KERNEL_TIMING, 1)
-    ctx.set_option(capi.OPT_OVERLAP, 0)
-    for _ in range(2):
-        frame()
-    barrier()
-    ctx.kernel_times()
-    for _ in range(args.steps):
-        frame()
-    barrier()
-    ktimes = ctx.kernel_times()
-    ctx.set_option(capi.OPT_KERNEL_TIMING, 0)
-    if not args.no_overlap:
-        ctx.set_option(capi.OPT_OVERLAP, args.overlap)
-    value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
+    ctx, frame, barrier, gather, slab, stream, scene, cam = R.ctx, R.frame, R.barrier, R.gather, R.slab, R.stream, R.scene, R.cam
+    rays_per_frame, ms_per_step, value, ktimes, alg_of, launches, sampler = R.rays_per_frame, R.ms_per_step, R.value, R.ktimes, R.alg_of, R.launches, R.sampler
+    alg_total = R.alg_total
 
     # ---- end to end through the public API with HOST buffers: camera H2D, frame, gather, resolve, image D2H
     host_img = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory()
@@ -419,44 +521,49 @@ def main():
         dist.all_reduce(e2e_pipe_ms, op=dist.ReduceOp.MAX)
     e2e_pipe_value = rays_per_frame / (float(e2e_pipe_ms[0]) * 1e-3) / 1e6
 
+    # ---- second north_star scene (BASELINE configs[4]): device-timed on the same N GPUs, reported under "secondary"
+    secondary = None
+    sec_name = args.secondary if args.secondary in WORKLOADS and args.secondary != args.scene else None
+    if sec_name:
+        ctx.destroy()                                    # the primary context is finished: free its queues before the 3 GB scene
+        ctx = None
+        S = device_run(WORKLOADS[sec_name], args.secondary_steps)
+        sclk = S.sampler.summary()
+        if rank == 0:
+            s_peak, _ = measured_peak_hbm()
+            s_mhz = float(sclk.get("sm_mhz") or sclk.get("sm_max_mhz") or 1965.0)
+            _, sw, sh, smb = WORKLOADS[sec_name]
+            secondary = {"metric": "Mrays/sec @1920x1080x8-bounce", "value": S.value, "unit": "Mrays/s", "n_gpus": world, "steps": args.secondary_steps,
+                         "ms_per_step": S.ms_per_step, "config": {"workload": workload_string(sec_name, sw, sh, smb), "triangles": int(len(S.scene["triangles"])),
+                                                                  "bvh_depth": int(S.scene.get("bvh_depth", 0)), "schedule": S.schedule, "partition": f"scanline y%{world}",
+                                                                  "rays_per_step": S.rays_per_frame, "primary_hit_fraction": S.primary_hit_fraction},
+                         "collective_ms": S.collective_ms, "gpu_launches": int(S.launches),
+                         "roofline": issue_roofline(sec_name, world, S.ktimes, args.secondary_steps, s_mhz, S.n_sms, s_peak, S.alg_of),
+                         "kernel_ms_per_step": {k: v[0] / args.secondary_steps for k, v in S.ktimes.items() if v[1]}, "clocks": sclk}
+        S.ctx.destroy()
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        dom = max(alg_of, key=lambda k: ktimes[k][0])          # the kernel class with the largest share of the step
-        dom_ms, dom_n = ktimes[dom]
-        dom_bytes_frame = alg_of[dom] / world
-        traffic = None
-        try:        # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)
-            tj = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
-            if tj["workload"].split()[0] == name and world == 1:
-                traffic = tj["kernels"][dom]["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        achieved = (dom_bytes_frame * args.steps / (dom_ms * 1e-3) / 1e9) if dom_ms > 0 else None
-        others = []                                             # the same figures for the other kernels of the step
-        for k in alg_of:
-            if k == dom or not ktimes[k][1] or ktimes[k][0] <= 0:
-                continue
-            a = alg_of[k] / world * args.steps / (ktimes[k][0] * 1e-3) / 1e9
-            t = None
-            try:
-                if tj["workload"].split()[0] == name and world == 1:
-                    t = tj["kernels"][k]["dram_bytes_per_launch"]
-            except Exception:
-                pass
-            others.append({"kernel": k, "achieved": a, "frac": a / peak, "traffic": t, "ms_per_step": ktimes[k][0] / args.steps,
-                           "algorithmic_bytes_per_launch": alg_of[k] / world / max(ktimes[k][1] / args.steps, 1)})
+        clk = sampler.summary()
+        sm_mhz = float(clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0)
+        roof = issue_roofline(name, world, ktimes, args.steps, sm_mhz, R.n_sms, peak, alg_of)
+        roof["peak_source"] = peak_src
+        roof["algorithmic_bytes_per_step"] = alg_total
+        roof["whole_frame_algorithmic_GBs"] = alg_total / (ms_per_step * 1e-3) / 1e9
+        roof["how"] = ("kernel time: CUDA events of THIS run (per-launch, per-phase kernels, shadow pass as its own kernel); instruction and DRAM "
+                       "counters: committed ncu --set full capture of the same workload and kernels (profiles/); issue peak = SMs x 4 x SM clock")
         line = {
             "metric": "Mrays/sec @1920x1080x8-bounce", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{name} {w}x{h} 1spp {mb}-bounce, {len(scene['triangles'])} triangles, sample_idx 0, Reset+Integrate per step",
-                       "schedule": "stepwise" if args.stepwise else "fused: [closest-hit trace(b) + shadow pass(b-1)] -> hit/miss queues -> shade(b)", "partition": f"scanline y%{world}",
-                       "rays_per_step": rays_per_frame,
+            "config": {"workload": workload_string(name, w, h, mb), "triangles": int(len(scene['triangles'])),
+                       "schedule": R.schedule, "partition": f"scanline y%{world}",
+                       "rays_per_step": rays_per_frame, "primary_hit_fraction": R.primary_hit_fraction,
                        "l2": "per-step working set (ray/shadow queues + radiance, ~365 MB at 1080p) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": float(e2e_ms[0]), "steps": e2e_steps,
                     "repetitions_ms_per_step": [round(x, 4) for x in e2e_reps], "h2d_bytes_per_step": 64,
                     "d2h_bytes_per_step": w * h * 16,          # the whole image reaches the host every step (N > 1: split over the ranks' links)
-                    "api": ("rt_set_camera + rt_reset + rt_integrate + rt_resolve(host image), blocking per frame like ResolveRadiance/Finish()" if world == 1 else
+                    "api": ("rt_set_camera + rt_reset + rt_integrate + rt_resolve(host image), blocking per frame like ResolveRadiance/Finish(); best of 2 repetitions" if world == 1 else
                             ("every rank: rt_set_camera + rt_reset + rt_integrate + NCCL gather to rank 0 + rt_resolve of its rows into ONE shared page-locked host "
                              "image (N PCIe links) + barrier; blocking per frame" if shared is not None else
                              "every rank: rt_set_camera + rt_reset + rt_integrate + NCCL gather to rank 0; rank 0: rt_resolve_gathered(whole host image), blocking per frame")),
@@ -466,21 +573,16 @@ def main():
                     "pipelined_value": e2e_pipe_value, "pipelined_ms_per_step": float(e2e_pipe_ms[0]),
                     "pipelined_api": "same, with rt_resolve_async: image D2H of frame i overlaps frame i+1"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                         "note": "achieved = SURVEY 8(d) algorithmic bytes (48 B per BVH node visit / triangle test included) / CUDA-event time; "
-                                 "the scene is L1/L2 resident, so DRAM traffic (ncu, profiles/) is far below the algorithmic bytes and the kernel is "
-                                 "issue-bound, not HBM-bound: frac > 1 is expected here and is not a bandwidth claim",
-                         "kernel_algorithmic_bytes_per_launch": dom_bytes_frame / max(dom_n / args.steps, 1),
-                         "algorithmic_bytes_per_step": alg_total, "kernel_algorithmic_bytes_per_step": dom_bytes_frame,
-                         "kernel_ms_per_step": dom_ms / args.steps, "kernel_launches_per_step": dom_n / args.steps,
-                         "whole_frame_algorithmic_GBs": alg_total / (ms_per_step * 1e-3) / 1e9, "other_kernels": others},
+            "roofline": roof,
+            "collective_ms": R.collective_ms,
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
             "kernel_timing_note": "kernel_ms_per_step: CUDA events per launch over K extra steps of this run with individual launches and the "
                                   "shadow pass as its own kernel (in the timed region the frame is one CUDA-graph launch in which the shadow pass of "
                                   "bounce b runs inside the traversal kernel of bounce b+1)",
-            "clocks": sampler.summary(),
+            "clocks": clk,
         }
+        if secondary is not None:
+            line["secondary"] = secondary
         if not args.no_cpu_baseline and world == 1:
             # The CPU leg runs in a fresh process (the --impl reference arm, one bounded sample): this process has torch's OpenMP
             # runtime loaded and already configured, which would decide the thread count and wait policy for the oracle too.
@@ -495,7 +597,8 @@ def main():
         print(json.dumps(line))
     if shared is not None:
         shared.close()
-    ctx.destroy()
+    if ctx is not None:
+        ctx.destroy()
     if world > 1:
         dist.destroy_process_group()
 

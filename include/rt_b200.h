@@ -82,6 +82,14 @@ typedef enum RtOption {
                                    option, the scene or the partition changes; the camera and sample index are a node-parameter update) */
     RT_OPT_PDL = 25,            /* 1 (default): the traversal and shading kernels of a frame are chained by programmatic dependent launch
                                    (a kernel's CTAs start and stage the BVH while the previous kernel drains) */
+    RT_OPT_FRAME_KERNEL = 26,   /* how rt_integrate runs a frame.  1: ONE persistent kernel in which every CTA is an independent
+                                   wavefront over its own pixels (queue cursors in shared memory, no global atomics, no launch
+                                   boundaries); 0: one kernel per phase (graph replay / PDL chain as configured above);
+                                   2 (default): the one-kernel frame for small partitions (<= 4096 pixels per SM, e.g. a 1/4 or
+                                   smaller share of a 1080p frame), per-phase kernels otherwise.  Results are bit-identical */
+    RT_OPT_PRESENT = 27,        /* multi-device contexts, rt_resolve: 0 (default) parallel read-back of every device's rows,
+                                   1 gather to devices[0] over NVLink, resolve and read back there */
+    RT_OPT_FRAME_THREADS = 28   /* threads per CTA of the one-kernel frame: 0 (default) by partition size, else a multiple of 32 <= 1024 */
 } RtOption;
 
 #define RT_MAX_BOUNCES 255u     /* bounce index range supported per frame (reference GUI: 0..5) */
@@ -113,6 +121,17 @@ typedef enum RtKernelClass {
  * cl_pt_integrator.cpp:188-259): binds CUDA device `device`, allocates every per-pixel
  * buffer for a width x height render.  Fails with RT_ERR_NO_DEVICE if there is no GPU. */
 int rt_create(uint32_t width, uint32_t height, int device, rt_ctx** out_ctx);
+/* One context over several devices of the node — replaces CLContext's device enumeration
+ * (gpu_wrappers/cl_context.cpp:64-89, where the reference lists every device and uses one): devices[i] renders
+ * rank i of an n-way scanline partition (row y -> device y % n), scene replicated.  The caller stays
+ * single-threaded; every call below fans out to the devices, which work concurrently (all steps are
+ * asynchronous enqueues).  rt_resolve presents the WHOLE image: by default every device copies its rows
+ * into the caller's image over its own PCIe link (page-lock it with rt_host_register); with
+ * RT_OPT_PRESENT = 1 the radiance slabs are first gathered to devices[0] over NVLink (rt_gather_radiance,
+ * the frame's one collective) and resolved there.  The stepwise taps (rt_read_hits, rt_read_rays), raw device
+ * pointers and the temporal denoiser are single-device only.  n_devices == 1 is rt_create. */
+int rt_create_multi(uint32_t width, uint32_t height, const int* devices, uint32_t n_devices, rt_ctx** out_ctx);
+int rt_device_count(int* out_count);
 int rt_destroy(rt_ctx* ctx);
 /* Last error text of this context (ctx == NULL: of the last failed rt_create). */
 const char* rt_last_error(const rt_ctx* ctx);
@@ -155,6 +174,18 @@ int rt_copy_history(rt_ctx* ctx);                               /* CopyHistoryBu
  * rows; rows of other ranks are left untouched); dst may be NULL to resolve on the device only.  Blocks
  * (the reference's only Finish(), cl_pt_integrator.cpp:677-684). */
 int rt_resolve(rt_ctx* ctx, float* dst_rgba);
+/* Multi-device contexts: copies every device's radiance slab to devices[0] over NVLink (peer copies on the
+ * devices' own streams; devices[0]'s stream waits for them) — the single collective of the frame. */
+int rt_gather_radiance(rt_ctx* ctx);
+/* Page-lock / release a caller-owned host buffer (the image given to rt_resolve) so that device->host copies into
+ * it are asynchronous and the devices of a multi-device context read back in parallel. */
+int rt_host_register(void* ptr, uint64_t bytes);
+int rt_host_unregister(void* ptr);
+
+/* Parity tap for include/rt_math.h (the elementary functions shared with the oracle): out[i] = f(a[i], b[i]) evaluated on
+ * `device`; host pointers, blocking.  fn: 0 sin, 1 cos, 2 tan, 3 atan2(a, b), 4 acos, 5 pow(a, b), 6 fmin, 7 fmax,
+ * 8 1 / sqrt(a), 9 a / b. */
+int rt_math_eval(int device, int fn, const float* a, const float* b, float* out, uint64_t n);
 
 /* Pipelined read-back for frame loops: resolve on the render stream, device->host copy on a second stream (overlaps the
  * next frame's kernels).  dst must stay untouched until rt_resolve_wait() returns. */

@@ -136,14 +136,17 @@ RT_HD float rt_tanf(float x) { double s, c; rt_sincos_d((double)x, &s, &c); retu
  * alternating Taylor series on |t| <= 1/8 (truncation error < 1e-23). */
 RT_HD double rt_atan_pos_d(double a)
 {
-    double base, t;
+    double base, c;
     int inverted = 0;
     if (a > 1.0) { a = 1.0 / a; inverted = 1; }
-    if (a < 0.125)      { base = 0.0;                 t = a; }
-    else if (a < 0.375) { base = 0.24497866312686414; t = (a - 0.25) / (1.0 + a * 0.25); }
-    else if (a < 0.625) { base = 0.4636476090008061;  t = (a - 0.5)  / (1.0 + a * 0.5); }
-    else if (a < 0.875) { base = 0.6435011087932844;  t = (a - 0.75) / (1.0 + a * 0.75); }
-    else                { base = 0.7853981633974483;  t = (a - 1.0)  / (1.0 + a); }
+    /* one division for all five breakpoints (same operations per breakpoint as the five-way branch: c = 0 gives
+     * (a - 0) / (1 + a * 0) = a exactly, c = 1 gives (a - 1) / (1 + a)), so the compiled code holds one divide */
+    if (a < 0.125)      { base = 0.0;                 c = 0.0; }
+    else if (a < 0.375) { base = 0.24497866312686414; c = 0.25; }
+    else if (a < 0.625) { base = 0.4636476090008061;  c = 0.5; }
+    else if (a < 0.875) { base = 0.6435011087932844;  c = 0.75; }
+    else                { base = 0.7853981633974483;  c = 1.0; }
+    double t = (a - c) / (1.0 + a * c);
     double t2 = t * t;
     double p = 0.04;
     p = p * t2 + -0.043478260869565216;
@@ -170,8 +173,13 @@ RT_HD double rt_atan2_d(double y, double x, int y_negative, int x_negative)
     if (ax != ax || ay != ay) return ax + ay;             /* NaN in, NaN out */
     if (ay == 0.0)            r = 0.0;
     else if (ax == 0.0)       r = 1.5707963267948966;
-    else if (ay <= ax)        r = rt_atan_pos_d(ay / ax);
-    else                      r = 1.5707963267948966 - rt_atan_pos_d(ax / ay);
+    else
+    {   /* one quotient <= 1 and one polynomial for both octants (same operations as two separate calls) */
+        const int steep = !(ay <= ax);
+        const double q = steep ? ax / ay : ay / ax;
+        r = rt_atan_pos_d(q);
+        if (steep) r = 1.5707963267948966 - r;
+    }
     if (x_negative) r = 3.141592653589793 - r;
     return y_negative ? -r : r;
 }

@@ -4,8 +4,11 @@ import csv
 import subprocess
 import sys
 
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
+if sys.argv[1].endswith(".csv"):       # raw page already exported (ncu -i report --page raw --csv)
+    out = open(sys.argv[1]).read()
+else:
+    out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = [r for r in csv.reader(out.splitlines()) if r and not r[0].startswith("==")]
 hdr, units = rows[0], rows[1]
 want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",

@@ -18,7 +18,7 @@ MAX_BOUNCES = 255
 OPT_WHITE_FURNACE, OPT_SAMPLER, OPT_AOV, OPT_DENOISER = 0, 1, 2, 3
 BN_SOBOL_COUNT, BN_TILE_COUNT = 65536, 131072
 OPT_COUNT_TRAVERSAL, OPT_KERNEL_TIMING, OPT_TRAVERSAL = 16, 17, 18
-OPT_AOV_ALWAYS, OPT_SMEM_BVH, OPT_OVERLAP, OPT_GRAPH, OPT_PDL = 21, 22, 23, 24, 25
+OPT_AOV_ALWAYS, OPT_SMEM_BVH, OPT_OVERLAP, OPT_GRAPH, OPT_PDL, OPT_FRAME_KERNEL, OPT_PRESENT, OPT_FRAME_THREADS = 21, 22, 23, 24, 25, 26, 27, 28
 KERNEL_CLASSES = ["raygen", "intersect", "miss", "hit", "intersect_shadow", "accumulate", "extend_shade",
                   "shadow_accumulate", "resolve", "aov", "misc", "trace_closest", "shade_queues", "trace_both"]
 
@@ -30,7 +30,8 @@ SYMBOLS = ["rt_create", "rt_destroy", "rt_last_error", "rt_set_partition", "rt_u
            "rt_accumulate_direct", "rt_denoise", "rt_copy_history", "rt_resolve", "rt_resolve_async", "rt_resolve_wait", "rt_resolve_gathered", "rt_resolve_gathered_async", "rt_extend_shade", "rt_shadow_accumulate",
            "rt_integrate", "rt_sync", "rt_read_hits", "rt_read_rays", "rt_read_radiance", "rt_read_frame_stats",
            "rt_read_sample_count", "rt_read_aovs", "rt_kernel_times", "rt_launch_count", "rt_local_pixel_count",
-           "rt_radiance_device_ptr", "rt_stream_handle"]
+           "rt_radiance_device_ptr", "rt_stream_handle",
+           "rt_create_multi", "rt_device_count", "rt_gather_radiance", "rt_host_register", "rt_host_unregister", "rt_math_eval"]
 
 
 class RtSceneDesc(C.Structure):
@@ -97,6 +98,12 @@ def load_library():
     L.rt_local_pixel_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.rt_radiance_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.rt_stream_handle.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.rt_create_multi.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_void_p)]
+    L.rt_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.rt_gather_radiance.argtypes = [C.c_void_p]
+    L.rt_host_register.argtypes = [C.c_void_p, C.c_uint64]
+    L.rt_host_unregister.argtypes = [C.c_void_p]
+    L.rt_math_eval.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     _lib = L
     return L
 
@@ -104,18 +111,29 @@ def load_library():
 class Context:
     """One render context (== one CLPathTraceIntegrator + CLContext in the reference) on one GPU."""
 
-    def __init__(self, width: int, height: int, device: int = 0, rank: int = 0, world: int = 1):
+    def __init__(self, width: int, height: int, device: int = 0, rank: int = 0, world: int = 1, devices=None):
+        """devices = [d0, d1, ...]: ONE context over several GPUs of the node (rt_create_multi: device i renders rank i of a
+        len(devices)-way scanline partition, every call fans out inside the library); otherwise a single-device context,
+        optionally one rank of a partition driven from outside (one process per GPU)."""
         self.lib = load_library()
         self.width, self.height = width, height
         h = C.c_void_p()
-        rc = self.lib.rt_create(width, height, device, C.byref(h))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.rt_create_multi(width, height, arr, len(devices), C.byref(h))
+        else:
+            rc = self.lib.rt_create(width, height, device, C.byref(h))
         if rc != 0:
             raise RtError(rc, self.lib.rt_last_error(None).decode())
         self.h = h
         self.rank, self.world = rank, world
+        self.devices = list(devices) if devices is not None else None
         if world != 1:
             self._ck(self.lib.rt_set_partition(self.h, rank, world))
         self._keep = None
+
+    def gather_radiance(self):
+        self._ck(self.lib.rt_gather_radiance(self.h))
 
     def _ck(self, rc):
         if rc != 0:
@@ -291,3 +309,34 @@ class Context:
         p = C.c_void_p()
         self._ck(self.lib.rt_stream_handle(self.h, C.byref(p)))
         return p.value
+
+
+def device_count() -> int:
+    n = C.c_int()
+    load_library().rt_device_count(C.byref(n))
+    return n.value
+
+
+def host_register(array) -> None:
+    """Page-locks a numpy array's memory (the image handed to Context.resolve) — rt_host_register."""
+    rc = load_library().rt_host_register(array.ctypes.data, array.nbytes)
+    if rc != 0:
+        raise RtError(rc, load_library().rt_last_error(None).decode())
+
+
+def host_unregister(array) -> None:
+    load_library().rt_host_unregister(array.ctypes.data)
+
+
+MATH_FUNCTIONS = {"sin": 0, "cos": 1, "tan": 2, "atan2": 3, "acos": 4, "pow": 5, "fmin": 6, "fmax": 7, "rsqrt": 8, "div": 9}
+
+
+def math_eval(fn: str, a, b=None, device: int = 0):
+    """include/rt_math.h function `fn` evaluated on the device (rt_math_eval)."""
+    a = np.ascontiguousarray(a, dtype="<f4")
+    b = np.ascontiguousarray(np.zeros_like(a) if b is None else b, dtype="<f4")
+    out = np.zeros_like(a)
+    rc = load_library().rt_math_eval(device, MATH_FUNCTIONS[fn], a.ctypes.data, b.ctypes.data, out.ctypes.data, a.size)
+    if rc != 0:
+        raise RtError(rc, load_library().rt_last_error(None).decode())
+    return out

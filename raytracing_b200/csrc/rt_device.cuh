@@ -205,6 +205,8 @@ __device__ __forceinline__ f3 unpack_rgb8(uint32_t d)
 }
 
 // kernels/common/material.h:251-264 (OpenCL branch), utils.h:123-190
+// (inlined on purpose: as a called function it costs the hot path more (call ABI: registers, stack) than its size saves —
+// measured on B200, profiles/r02_code_size_ab.txt)
 __device__ __forceinline__ Material unpack_material(const DevScene& sc, uint32_t mtl_index, f2 uv)
 {
     const uint32_t* pm = sc.materials + (size_t)mtl_index * 5;
@@ -318,6 +320,10 @@ __device__ __forceinline__ f3 sample_bxdf(float s1, f2 s, Material m, f3 normal,
     }
     f3 bxdf;
     float phi = RT_TWO_PI * s.x;
+    // sin/cos of phi are needed by the rough-specular and by the diffuse lobe: evaluated once, ahead of the branch (a warp that
+    // holds both kinds of hits runs both sides of it)
+    double sphi, cphi;
+    rt_sincos_d((double)phi, &sphi, &cphi);
     if (s1 <= specular_pdf)
     {
         f3 spec;
@@ -334,8 +340,6 @@ __device__ __forceinline__ f3 sample_bxdf(float s1, f2 s, Material m, f3 normal,
             float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
             f3 t, b;
             tangent_frame(normal, t, b);
-            double sphi, cphi;
-            rt_sincos_d((double)phi, &sphi, &cphi);
             f3 wh = normalize(b * (float)cphi * sin_theta + t * (float)sphi * sin_theta + normal * cos_theta);
             outgoing = reflect(-incoming, wh);
             float n_dot_o = dot(normal, outgoing);
@@ -354,8 +358,6 @@ __device__ __forceinline__ f3 sample_bxdf(float s1, f2 s, Material m, f3 normal,
         float sin_theta = sqrtf(s.y);
         float cos_theta = sqrtf(1.0f - s.y);
         pdf = cos_theta * RT_INV_PI;
-        double sphi, cphi;
-        rt_sincos_d((double)phi, &sphi, &cphi);
         f3 tbn = mk3((float)cphi * sin_theta, (float)sphi * sin_theta, cos_theta);
         f3 t, b;
         tangent_frame(normal, t, b);

@@ -47,6 +47,10 @@ using namespace rt;
 #ifndef RT_MINB_SHADE
 #define RT_MINB_SHADE 4
 #endif
+// The whole-frame kernel (k_frame) is compiled for up to 1024 threads per CTA (64 registers): the CTA size is chosen at launch
+// (RT_OPT_FRAME_THREADS) — 1024 threads = one CTA per SM, all 32 warps of an SM in the same phase; 256 threads = 4 CTAs per SM
+// in different phases
+#define RT_FRAME_MAX_THREADS 1024
 
 namespace
 {
@@ -268,7 +272,9 @@ __device__ __forceinline__ uint32_t trace_literal(const DevScene& sc, f3 o, f3 d
 // the same arithmetic per box / triangle test as trace_literal, so results are bit-identical
 // for finite rays; non-finite rays (NaN/inf components; their traversal is garbage-in but must
 // still match) take the literal path.
-template <bool ANY, bool COUNT, bool SMEM>
+// PIN: the whole-frame kernel shares its register budget with the shading code and ptxas then re-derives the sign bits on
+// every step and recomputes the determinant after its branch; an empty asm makes both values opaque (kept in registers).
+template <bool ANY, bool COUNT, bool SMEM, bool PIN = false>
 __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4* wnodes, const float4* wtris, f3 o, f3 d, float t_min, float t_max,
                                                float& bu, float& bv, float& bt, uint32_t& nv, uint32_t& nt)
 {
@@ -278,7 +284,8 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
 
     f3 inv = splat(1.0f) / d;
     const bool sx = inv.x < 0, sy = inv.y < 0, sz = inv.z < 0;
-    const uint32_t sign_bits = (sx ? 1u : 0u) | (sy ? 2u : 0u) | (sz ? 4u : 0u);
+    uint32_t sign_bits = (sx ? 1u : 0u) | (sy ? 2u : 0u) | (sz ? 4u : 0u);
+    if (PIN) asm volatile("" : "+r"(sign_bits));
     uint32_t prim = RT_INVALID_ID;
     int sp = 0;
     int cur = sc.root_ref;
@@ -359,6 +366,7 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
             bool last = __float_as_uint(q2.y) != 0u;
             f3 pvec = cross(d, e2);
             float det = dot(e1, pvec);
+            if (PIN) asm volatile("" : "+f"(det));
             if (!(det < 1e-8f || -det > 1e-8f))
             {
                 float inv_det = 1.0f / det;
@@ -848,6 +856,244 @@ __global__ void __launch_bounds__(256, RT_MINB_SHADE) k_shade_queues(FrameParams
     }
 }
 
+// ---- whole-frame kernel (RT_OPT_FRAME_KERNEL, default) ---------------------------------------------------------
+// ONE launch per frame.  Every CTA is an independent wavefront path tracer over its own subset of the partition's pixels
+// (groups of 32 consecutive local pixels, dealt round-robin to the resident CTAs), with its own region of every queue:
+// a path never leaves the CTA that generated its primary ray.  The per-bounce schedule is the one of rt_extend_shade /
+// rt_shadow_accumulate (integrator.cpp:27-59 fused the same way):
+//     T(b): closest-hit traversal of bounce b  +  shadow pass of bounce b-1   -> hit queue / miss queue
+//     S(b): shading of the hit queue, then of the miss queue                   -> shadow queue, ray queue of bounce b+1
+// but the queue cursors and counters live in SHARED memory and the phases are separated by __syncthreads(): no global
+// atomics on the ray path, no grid-wide synchronisation, no launch boundary between phases (the ~10-15 us floor that 22
+// dependent launches per frame cost a small multi-GPU partition), and the 4 CTAs of an SM are in different phases at any
+// time, so a CTA waiting for its slowest warp at a barrier leaves the issue slots to its neighbours.  Primary rays are
+// generated inside T(0) (no separate pass over the queue).  Results are bit-identical: every per-pixel quantity is a
+// function of (pixel, sample index, bounce) only, and the order of the additions into a pixel's radiance is unchanged.
+struct CtaFrame
+{
+    uint32_t cur_trace, cur_shade;           // work cursors of the current T / S phase
+    uint32_t ext_n[2], shadow_n[2];          // rays entering bounce b (parity b & 1), shadow rays spawned by S(b) (parity b & 1)
+    unsigned long long hm[2];                // hits (low word) and misses (high word) of T(b), parity b & 1
+    unsigned long long emit[2];              // shadow rays (low word) and continuation rays (high word) spawned by S(b): slot reservation
+    uint32_t n_emissive, n_unoccluded;
+};
+
+template <bool SMEM>
+__global__ void __launch_bounds__(RT_FRAME_MAX_THREADS, 1) k_frame(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance,
+                                                              AovParams aov, uint32_t max_bounces, uint32_t slots_per_cta,
+                                                              const __grid_constant__ FrameDyn dyn)
+{
+    extern __shared__ __align__(128) float4 s_bvh[];
+    __shared__ uint64_t s_mbar;
+    __shared__ CtaFrame s;
+    p.dyn = &dyn;                                  // per-frame constants (sample index, camera) arrive as a kernel parameter
+    if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    const int lane = threadIdx.x & 31;
+    const uint32_t base = blockIdx.x * slots_per_cta;          // this CTA's region of every queue: slots [base, base + slots_per_cta)
+    // (queue pointers are re-read from the kernel parameters where they are used: nothing but `base` stays live across the
+    // traversal and shading loops)
+#define FQ(plane, i) (q.plane)[base + (i)]
+    if (threadIdx.x == 0)
+    {
+        const uint32_t n_groups = (p.n_local + 31u) / 32u;
+        const uint32_t cta = blockIdx.x, n_cta = gridDim.x;
+        const uint32_t my_groups = cta < n_groups ? (n_groups - cta + n_cta - 1u) / n_cta : 0u;
+        s.cur_trace = 0; s.cur_shade = 0; s.ext_n[0] = my_groups * 32u; s.ext_n[1] = 0; s.shadow_n[0] = s.shadow_n[1] = 0;
+        s.hm[0] = s.hm[1] = 0ull; s.emit[0] = s.emit[1] = 0ull; s.n_emissive = 0; s.n_unoccluded = 0;
+        if (blockIdx.x == 0) ctr->n_primary = p.n_local;
+    }
+    __syncthreads();
+    const uint32_t sample_idx = p.dyn->sample_idx;
+    uint32_t nv = 0, nt = 0;     // (not counted here: RT_OPT_COUNT_TRAVERSAL uses the per-phase kernels)
+
+    for (uint32_t b = 0; b <= max_bounces + 1u; ++b)
+    {
+        // ---------------------------------------------------------------- T(b): extension rays of bounce b, then shadow rays of bounce b-1
+        {
+            const int in = b & 1;
+            const uint32_t n_ext = b <= max_bounces ? s.ext_n[in] : 0u;          // the last round is the shadow pass of the last bounce only
+            const uint32_t ext_span = (n_ext + 31u) & ~31u;
+            const uint32_t n_sh = b == 0 ? 0u : s.shadow_n[(b - 1u) & 1];
+            const uint32_t total = ext_span + n_sh;
+            if (threadIdx.x == 0)
+            {   // state of the NEXT phases that nobody reads during this one
+                s.cur_shade = 0; s.ext_n[(b + 1u) & 1] = 0; s.shadow_n[in] = 0; s.emit[in] = 0ull;
+            }
+            for (;;)
+            {
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(&s.cur_trace, 32u);
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (at >= total) break;
+                if (at < ext_span)
+                {
+                    const uint32_t i = at + lane;
+                    bool live = i < n_ext, hit = false;
+                    float bu = 0.0f, bv = 0.0f, bt = 0.0f;
+                    uint32_t prim = RT_INVALID_ID;
+                    float4 a, bb;
+                    if (b == 0)
+                    {   // RayGeneration (raygeneration.cl:65-139) fused into the first traversal pass; slot i <-> local pixel li
+                        const uint32_t li = (blockIdx.x + (i >> 5) * gridDim.x) * 32u + (uint32_t)lane;
+                        live = li < p.n_local;
+                        if (live)
+                        {
+                            const uint32_t px = li % p.width, py = (li / p.width) * p.world + p.rank;
+                            f3 o, d;
+                            generate_primary_ray(p.dyn->raygen, py * p.width + px, px, py, sample_idx, o, d);
+                            a = make_float4(o.x, o.y, o.z, __uint_as_float(pack_pixel(px, py)));
+                            bb = make_float4(d.x, d.y, d.z, RT_MAX_RENDER_DIST);
+                            FQ(A[0], i) = a; FQ(B[0], i) = bb; FQ(C[0], i) = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+                            if (aov.enabled)
+                            {   // raygeneration.cl:129-133
+                                aov.albedo[li] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                                aov.depth[li] = RT_MAX_RENDER_DIST;
+                                aov.normal[li] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                                aov.velocity[li] = make_float2(0.0f, 0.0f);
+                            }
+                        }
+                    }
+                    else if (live) { a = FQ(A[in], i); bb = FQ(B[in], i); }
+                    if (live)
+                    {
+                        if (SMEM) prim = trace_fast<false, false, true, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt);
+                        else prim = trace<false, false>(sc, mode, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt);
+                        hit = prim != RT_INVALID_ID;
+                    }
+                    const unsigned hmask = __ballot_sync(0xffffffffu, hit);
+                    const unsigned mmask = __ballot_sync(0xffffffffu, live && !hit);
+                    unsigned long long slot = 0ull;
+                    if (lane == 0)
+                        slot = atomicAdd(&s.hm[in], (unsigned long long)__popc(hmask) | ((unsigned long long)__popc(mmask) << 32));
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    const unsigned lt_mask = (1u << lane) - 1u;
+                    if (hit) FQ(hitq, (uint32_t)slot + __popc(hmask & lt_mask)) = make_float4(bu, bv, __uint_as_float(prim), __uint_as_float(i));
+                    else if (live) FQ(missq, (uint32_t)(slot >> 32) + __popc(mmask & lt_mask)) = i;
+                }
+                else
+                {   // IntersectShadowRays + AccumulateDirectSamples of bounce b-1
+                    const uint32_t i = at - ext_span + lane;
+                    bool un = false;
+                    if (i < n_sh)
+                    {
+                        const float4 a = FQ(sA, i), bb = FQ(sB, i);
+                        float bu, bv, bt;
+                        if (SMEM) un = trace_fast<true, false, true, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
+                        else un = trace<true, false>(sc, mode, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
+                        if (un)
+                        {
+                            const float4 c = FQ(sC, i);
+                            const uint32_t li = local_index(p, __float_as_uint(a.w));
+                            float4 r = radiance[li];
+                            r.x += c.x; r.y += c.y; r.z += c.z;
+                            radiance[li] = r;
+                        }
+                    }
+                    const unsigned umask = __ballot_sync(0xffffffffu, un);
+                    if (lane == 0 && umask) atomicAdd(&s.n_unoccluded, (uint32_t)__popc(umask));
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {   // per-bounce statistics (rt_read_frame_stats): one fire-and-forget global add per CTA and counter
+                const unsigned long long hm = s.hm[in];
+                if (b <= max_bounces && hm) atomicAdd((unsigned long long*)&ctr->hm[b], hm);
+                if (b > 0 && s.n_unoccluded) atomicAdd(&ctr->n_unoccluded[b - 1u], s.n_unoccluded);
+                s.n_unoccluded = 0;
+            }
+        }
+        if (b > max_bounces) break;
+        // ---------------------------------------------------------------- S(b): ShadeSurfaceHits over the hit queue, ShadeMissedRays over the miss queue
+        {
+            const int in = b & 1, out = (b + 1u) & 1;
+            const unsigned long long hm = s.hm[in];
+            const uint32_t n_hit = (uint32_t)hm, n_miss = (uint32_t)(hm >> 32);
+            const uint32_t hit_span = (n_hit + 31u) & ~31u;            // warps never mix hits and misses
+            const uint32_t total = hit_span + n_miss;
+            if (threadIdx.x == 0) { s.cur_trace = 0; s.hm[out] = 0ull; }
+            for (;;)
+            {
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(&s.cur_shade, 32u);
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (at >= total) break;
+                if (at < hit_span)
+                {
+                    const uint32_t k = at + lane;
+                    const bool hit = k < n_hit;
+                    uint32_t pixel = 0;
+                    ShadeOut so;
+                    so.emissive = so.spawn_next = so.spawn_shadow = false;
+                    if (hit)
+                    {
+                        const float4 h = FQ(hitq, k);
+                        const uint32_t i = __float_as_uint(h.w);
+                        const float4 a = FQ(A[in], i), bb = FQ(B[in], i), c = FQ(C[in], i);
+                        pixel = __float_as_uint(a.w);
+                        shade_hit(sc, p, aov, b, pixel, mk3(a), mk3(bb), mk3(c), __float_as_uint(h.z), h.x, h.y, so);
+                        if (so.emissive)
+                        {
+                            const uint32_t li = local_index(p, pixel);
+                            float4 r = radiance[li];
+                            r.x += so.emission_add.x; r.y += so.emission_add.y; r.z += so.emission_add.z;
+                            radiance[li] = r;
+                        }
+                    }
+                    const bool ss = hit && so.spawn_shadow, sn = hit && so.spawn_next;
+                    const unsigned smask = __ballot_sync(0xffffffffu, ss), nmask = __ballot_sync(0xffffffffu, sn);
+                    const unsigned emask = __ballot_sync(0xffffffffu, hit && so.emissive);
+                    unsigned long long slot = 0ull;
+                    if ((smask | nmask | emask) != 0u)
+                    {
+                        if (lane == 0)
+                        {
+                            slot = atomicAdd(&s.emit[in], (unsigned long long)__popc(smask) | ((unsigned long long)__popc(nmask) << 32));
+                            if (emask) atomicAdd(&s.n_emissive, (uint32_t)__popc(emask));
+                        }
+                        slot = __shfl_sync(0xffffffffu, slot, 0);
+                    }
+                    const unsigned lt_mask = (1u << lane) - 1u;
+                    if (ss)
+                    {
+                        const uint32_t si = (uint32_t)slot + __popc(smask & lt_mask);
+                        FQ(sA, si) = make_float4(so.s_origin.x, so.s_origin.y, so.s_origin.z, __uint_as_float(pixel));
+                        FQ(sB, si) = make_float4(so.s_dir.x, so.s_dir.y, so.s_dir.z, so.s_tmax);
+                        FQ(sC, si) = make_float4(so.s_sample.x, so.s_sample.y, so.s_sample.z, 0.0f);
+                    }
+                    if (sn)
+                    {
+                        const uint32_t ni = (uint32_t)(slot >> 32) + __popc(nmask & lt_mask);
+                        FQ(A[out], ni) = make_float4(so.n_origin.x, so.n_origin.y, so.n_origin.z, __uint_as_float(pixel));
+                        FQ(B[out], ni) = make_float4(so.n_dir.x, so.n_dir.y, so.n_dir.z, RT_MAX_RENDER_DIST);
+                        FQ(C[out], ni) = make_float4(so.n_throughput.x, so.n_throughput.y, so.n_throughput.z, 0.0f);
+                    }
+                }
+                else
+                {
+                    const uint32_t k = at - hit_span + lane;
+                    if (k < n_miss)
+                    {
+                        const uint32_t i = FQ(missq, k);
+                        const float4 a = FQ(A[in], i), bb = FQ(B[in], i), c = FQ(C[in], i);
+                        shade_miss(sc, p, radiance, __float_as_uint(a.w), mk3(bb), mk3(c));
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                const unsigned long long em = s.emit[in];
+                s.shadow_n[in] = (uint32_t)em; s.ext_n[out] = (uint32_t)(em >> 32);
+                if (em) atomicAdd((unsigned long long*)&ctr->emit[b], em);
+                if (s.n_emissive) atomicAdd(&ctr->n_emissive[b], s.n_emissive);
+                s.n_emissive = 0;
+            }
+            __syncthreads();
+        }
+    }
+}
+#undef FQ
+
 // resolve_radiance.cl:31-86: shaded colour (radiance / sample_count unless the denoiser is on, then Reinhard x/(1+x))
 // or one of the AOV views
 __global__ void __launch_bounds__(256) k_resolve(const float4* radiance, float4* out, uint32_t n, uint32_t sample_count, int denoiser,
@@ -906,6 +1152,30 @@ __global__ void __launch_bounds__(256) k_temporal(uint32_t width, uint32_t heigh
     radiance[idx] = cur;
 }
 
+// rt_math_eval: the functions of include/rt_math.h evaluated on the device (parity tap: tests compare them bitwise with the
+// same header compiled for the host)
+__global__ void k_math_eval(int fn, const float* a, const float* b, float* out, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = a[i], y = b[i];
+    float r = 0.0f;
+    switch (fn)
+    {
+    case 0: r = rt_sinf(x); break;
+    case 1: r = rt_cosf(x); break;
+    case 2: r = rt_tanf(x); break;
+    case 3: r = rt_atan2f(x, y); break;
+    case 4: r = rt_acosf(x); break;
+    case 5: r = rt_powf(x, y); break;
+    case 6: r = rt_fminf(x, y); break;
+    case 7: r = rt_fmaxf(x, y); break;
+    case 8: r = 1.0f / sqrtf(x); break;          // the normalize() building blocks: IEEE sqrt and division
+    case 9: r = x / y; break;
+    }
+    out[i] = r;
+}
+
 __global__ void k_unpack_rays(const float4* A, const float4* B, const uint32_t* count, uint32_t width, RtRay* rays, uint32_t* pixels)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -923,6 +1193,12 @@ __global__ void k_unpack_rays(const float4* A, const float4* B, const uint32_t* 
 struct rt_ctx
 {
     int device = 0;
+    // A multi-device context (rt_create_multi) owns no device memory itself: it holds one child context per device (child i
+    // renders rank i of an n-way scanline partition) and every call on it fans out to the children from the caller's thread.
+    std::vector<rt_ctx*> children;
+    int present = 0;                               // RT_OPT_PRESENT (groups): 0 parallel read-back, 1 gather to device 0 over NVLink
+    float4* gather_buf = nullptr; size_t gather_stride_f4 = 0;   // device 0: the gathered radiance slabs (rt_gather_radiance)
+    std::vector<cudaEvent_t> gather_events;
     uint32_t width = 0, height = 0, rank = 0, world = 1, n_local = 0, local_rows = 0;
     cudaStream_t stream = nullptr;
     int num_sms = 0;
@@ -967,6 +1243,9 @@ struct rt_ctx
     DevCounters* counters = nullptr;
     FrameDyn* d_dyn = nullptr;
     bool pdl = true;               // RT_OPT_PDL
+    int frame_kernel = 2;          // RT_OPT_FRAME_KERNEL: 1 rt_integrate launches ONE persistent kernel per frame (k_frame), 0 one kernel per phase, 2 by partition size
+    int frame_threads = 0;         // RT_OPT_FRAME_THREADS: threads per CTA of k_frame (0 = by partition size)
+    size_t n_alloc = 0;            // entries of every per-pixel queue: n_local + one group of 32 per CTA that can be resident (k_frame's regions)
     int* d_bn = nullptr;           // sobol | scrambling | ranking (rt_upload_sampler_tables)
     struct Occupancy { const void* kernel; size_t smem; int per_sm; };
     std::vector<Occupancy> occupancy;   // resident CTAs per SM of each persistent kernel (persistent_grid)
@@ -1010,6 +1289,23 @@ static std::string g_create_error;
     } while (0)
 
 #define RT_CHECK_CTX(ctx) do { if (!(ctx)) return RT_ERR_INVALID_ARGUMENT; } while (0)
+
+// Multi-device contexts: forward the call to every child (variable `k`), in rank order, from the caller's thread.  Kernel
+// launches and copies are asynchronous, so the devices work concurrently; the first failing child's message is kept.
+#define RT_FANOUT(ctx, call)                                                             \
+    do {                                                                                 \
+        if (!(ctx)->children.empty())                                                    \
+        {                                                                                \
+            for (rt_ctx* k : (ctx)->children)                                            \
+            {                                                                            \
+                int rt_frc_ = (call);                                                    \
+                if (rt_frc_ != RT_OK) { (ctx)->error = k->error; return rt_frc_; }       \
+            }                                                                            \
+            return RT_OK;                                                                \
+        }                                                                                \
+    } while (0)
+#define RT_NOT_ON_GROUP(ctx, what)                                                       \
+    do { if (!(ctx)->children.empty()) RT_FAIL(ctx, RT_ERR_UNSUPPORTED, what " is a single-device call: use it on a context of rt_create"); } while (0)
 
 struct rt_ctx;
 extern "C" {   // defined with rt_shadow_accumulate
@@ -1080,11 +1376,14 @@ int require_ready(rt_ctx* c)
 }
 
 void free_aov_buffers(rt_ctx* c);
+bool aov_wanted(const rt_ctx* c);
+int ensure_aov_buffers(rt_ctx* c);
 
 int alloc_frame_buffers(rt_ctx* c)
 {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->shadow_stream) cudaStreamSynchronize(c->shadow_stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream); // a pipelined read-back may still be reading the resolve buffers
     c->shadow_pending = false; c->shadow_deferred = false;     // the frame in flight (if any) is abandoned with its buffers
     ++c->config_gen;
     auto freep = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
@@ -1095,7 +1394,9 @@ int alloc_frame_buffers(rt_ctx* c)
     free_aov_buffers(c);
     c->local_rows = (c->height > c->rank) ? (c->height - c->rank + c->world - 1) / c->world : 0;
     c->n_local = c->local_rows * c->width;
-    size_t n = c->n_local ? c->n_local : 1;
+    // k_frame gives every resident CTA its own region of each queue, rounded up to whole groups of 32 slots
+    size_t n = (size_t)c->n_local + 32u + (size_t)c->num_sms * 8u * 32u;
+    c->n_alloc = n;
     for (int i = 0; i < 2; ++i)
     {
         RT_CUDA(c, cudaMalloc(&c->q.A[i], n * 16)); RT_CUDA(c, cudaMalloc(&c->q.B[i], n * 16)); RT_CUDA(c, cudaMalloc(&c->q.C[i], n * 16));
@@ -1105,6 +1406,8 @@ int alloc_frame_buffers(rt_ctx* c)
     RT_CUDA(c, cudaMalloc(&c->q.hitq, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.missq, n * 4));
     RT_CUDA(c, cudaMalloc(&c->radiance, n * 16)); RT_CUDA(c, cudaMalloc(&c->resolved, n * 16));
     RT_CUDA(c, cudaMemsetAsync(c->radiance, 0, n * 16, c->stream));
+    c->copy_pending[0] = c->copy_pending[1] = false;          // both streams were drained above
+    if (aov_wanted(c)) return ensure_aov_buffers(c);           // a selected view / the denoiser keeps its buffers across a re-partition
     return RT_OK;
 }
 
@@ -1250,6 +1553,16 @@ int rt_create(uint32_t width, uint32_t height, int device, rt_ctx** out_ctx)
 int rt_destroy(rt_ctx* c)
 {
     if (!c) return RT_ERR_INVALID_ARGUMENT;
+    if (!c->children.empty())
+    {   // multi-device context: the gather buffer lives on the first child's device
+        cudaSetDevice(c->children[0]->device);
+        for (rt_ctx* k : c->children) if (k->stream) cudaStreamSynchronize(k->stream);
+        cudaFree(c->gather_buf);
+        for (cudaEvent_t e : c->gather_events) cudaEventDestroy(e);
+        for (rt_ctx* k : c->children) rt_destroy(k);
+        delete c;
+        return RT_OK;
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->shadow_stream) cudaStreamSynchronize(c->shadow_stream);
@@ -1275,8 +1588,10 @@ int rt_destroy(rt_ctx* c)
 
 int rt_set_partition(rt_ctx* c, uint32_t rank, uint32_t world)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_NOT_ON_GROUP(c, "rt_set_partition");
     if (world == 0 || rank >= world) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_set_partition: need rank < world, world >= 1");
+    if (world > 1 && c->denoiser)
+        RT_FAIL(c, RT_ERR_UNSUPPORTED, "the temporal denoiser reprojects across the whole image and is not available with a multi-GPU partition");
     RT_CUDA(c, cudaSetDevice(c->device));
     c->rank = rank; c->world = world;
     return alloc_frame_buffers(c);
@@ -1284,7 +1599,7 @@ int rt_set_partition(rt_ctx* c, uint32_t rank, uint32_t world)
 
 int rt_upload_scene(rt_ctx* c, const RtSceneDesc* s)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_upload_scene(k, s));
     if (!s) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: null scene");
     // cl_pt_integrator.cpp:385,404 assert non-empty triangles/materials; light.h:46 divides by the light count
     if (!s->triangles || s->n_triangles == 0) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_scene: scene has no triangles");
@@ -1372,7 +1687,7 @@ int rt_upload_scene(rt_ctx* c, const RtSceneDesc* s)
 
 int rt_set_camera(rt_ctx* c, const RtCamera* cam)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_set_camera(k, cam));
     if (!cam) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_set_camera: null camera");
     c->camera = *cam;
     c->aov_prev_camera = c->prev_camera;        // the AOV kernel sees the camera of the previous SetCameraData call
@@ -1395,6 +1710,12 @@ int rt_set_camera(rt_ctx* c, const RtCamera* cam)
 int rt_set_option(rt_ctx* c, int key, uint32_t value)
 {
     RT_CHECK_CTX(c);
+    if (key == RT_OPT_PRESENT)
+    {
+        if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "present mode must be 0 (parallel read-back) or 1 (gather to the first device)");
+        c->present = (int)value; return RT_OK;
+    }
+    RT_FANOUT(c, rt_set_option(k, key, value));
     ++c->config_gen;
     switch (key)
     {
@@ -1423,6 +1744,12 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
     case RT_OPT_KERNEL_TIMING: c->kernel_timing = value != 0; return RT_OK;
     case RT_OPT_GRAPH: c->use_graph = value != 0; return RT_OK;
     case RT_OPT_PDL: c->pdl = value != 0; return RT_OK;
+    case RT_OPT_FRAME_THREADS:
+        if (value != 0 && (value % 32 != 0 || value > RT_FRAME_MAX_THREADS)) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "frame-kernel CTA size must be 0 (automatic) or a multiple of 32 up to 1024");
+        c->frame_threads = (int)value; return RT_OK;
+    case RT_OPT_FRAME_KERNEL:
+        if (value > 2) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "frame-kernel mode must be 0 (per-phase kernels), 1 (one kernel per frame) or 2 (by partition size)");
+        c->frame_kernel = (int)value; return RT_OK;
     case RT_OPT_SMEM_BVH: c->smem_bvh = value != 0; return RT_OK;
     case RT_OPT_OVERLAP:
     {
@@ -1440,7 +1767,7 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
 
 int rt_upload_sampler_tables(rt_ctx* c, const int32_t* sobol, const int32_t* scrambling, const int32_t* ranking)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_upload_sampler_tables(k, sobol, scrambling, ranking));
     if (!sobol || !scrambling || !ranking) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_upload_sampler_tables: null table");
     for (int i = 0; i < RT_BN_TILE_COUNT; ++i)
         if (ranking[i] < 0 || ranking[i] > 255)
@@ -1459,7 +1786,7 @@ int rt_upload_sampler_tables(rt_ctx* c, const int32_t* sobol, const int32_t* scr
 
 int rt_reset(rt_ctx* c)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_reset(k));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     RT_CUDA(c, cudaSetDevice(c->device));
     if (!c->denoiser) c->sample_count = 0;                                   // cl_pt_integrator.cpp:499-504
@@ -1470,7 +1797,7 @@ int rt_reset(rt_ctx* c)
 
 int rt_advance_sample_count(rt_ctx* c)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_advance_sample_count(k));
     int rc = join_shadow(c); if (rc) return rc;     // end of the bounce loop: everything of this frame is ordered on the render stream
     ++c->sample_count;
     return RT_OK;
@@ -1478,7 +1805,7 @@ int rt_advance_sample_count(rt_ctx* c)
 
 int rt_generate_rays(rt_ctx* c)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_generate_rays(k));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     int rc = require_ready(c); if (rc) return rc;
     RT_CUDA(c, cudaSetDevice(c->device));
@@ -1504,7 +1831,7 @@ int rt_generate_rays(rt_ctx* c)
 
 int rt_intersect(rt_ctx* c, uint32_t bounce)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_intersect(k, bounce));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; } RT_BOUNCE_CHECK(c, bounce);
     TimedLaunch t(c, RT_K_INTERSECT);
     if (c->count_traversal) k_intersect<true><<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
@@ -1517,7 +1844,7 @@ int rt_intersect(rt_ctx* c, uint32_t bounce)
  * needs them; with the default view (shaded colour, no denoiser) no AOV work is done at all. */
 int rt_compute_aovs(rt_ctx* c)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_compute_aovs(k));
     if (!aov_wanted(c)) return RT_OK;
     RT_CUDA(c, cudaSetDevice(c->device));
     return ensure_aov_buffers(c);
@@ -1525,7 +1852,7 @@ int rt_compute_aovs(rt_ctx* c)
 
 int rt_shade_miss(rt_ctx* c, uint32_t bounce)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_shade_miss(k, bounce));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; } RT_BOUNCE_CHECK(c, bounce);
     TimedLaunch t(c, RT_K_MISS);
     k_shade_miss<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->q, c->counters, c->radiance, bounce);
@@ -1537,7 +1864,7 @@ int rt_clear_shadow_counter(rt_ctx* c) { RT_CHECK_CTX(c); return RT_OK; }
 
 int rt_shade_hits(rt_ctx* c, uint32_t bounce)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_shade_hits(k, bounce));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; } RT_BOUNCE_CHECK(c, bounce);
     c->cur_bounce = bounce;
     TimedLaunch t(c, RT_K_HIT);
@@ -1547,7 +1874,7 @@ int rt_shade_hits(rt_ctx* c, uint32_t bounce)
 
 int rt_intersect_shadow(rt_ctx* c)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_intersect_shadow(k));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; } RT_BOUNCE_CHECK(c, c->cur_bounce);
     TimedLaunch t(c, RT_K_INTERSECT_SHADOW);
     if (c->count_traversal) k_intersect_shadow<true><<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->cur_bounce);
@@ -1557,7 +1884,7 @@ int rt_intersect_shadow(rt_ctx* c)
 
 int rt_accumulate_direct(rt_ctx* c)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_accumulate_direct(k));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; } RT_BOUNCE_CHECK(c, c->cur_bounce);
     TimedLaunch t(c, RT_K_ACCUMULATE);
     k_accumulate<<<grid_for(c->n_local), 256, 0, c->stream>>>(frame_params(c), c->q, c->counters, c->radiance, c->cur_bounce);
@@ -1566,7 +1893,7 @@ int rt_accumulate_direct(rt_ctx* c)
 
 int rt_denoise(rt_ctx* c)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_denoise(k));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!c->denoiser) return RT_OK;
     if (c->world != 1) RT_FAIL(c, RT_ERR_UNSUPPORTED, "temporal denoiser is single-GPU only");
@@ -1579,7 +1906,7 @@ int rt_denoise(rt_ctx* c)
 
 int rt_copy_history(rt_ctx* c)
 {   // cl_pt_integrator.cpp:670-675
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_copy_history(k));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!c->denoiser) return RT_OK;
     RT_CUDA(c, cudaSetDevice(c->device));
@@ -1591,7 +1918,7 @@ int rt_copy_history(rt_ctx* c)
 
 int rt_extend_shade(rt_ctx* c, uint32_t bounce)
 {
-    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_extend_shade(k, bounce)); RT_BOUNCE_CHECK(c, bounce);
     c->cur_bounce = bounce;
     if (c->shadow_deferred && merged_trace_available(c))
     {   // this bounce's closest-hit traversal + the previous bounce's shadow pass in one kernel
@@ -1629,7 +1956,7 @@ static int launch_shadow_pass(rt_ctx* c, uint32_t bounce, cudaStream_t st)
 
 int rt_shadow_accumulate(rt_ctx* c, uint32_t bounce)
 {
-    RT_CHECK_CTX(c); RT_BOUNCE_CHECK(c, bounce);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_shadow_accumulate(k, bounce)); RT_BOUNCE_CHECK(c, bounce);
     int rc = join_shadow(c); if (rc) return rc;
     // The shadow pass of bounce b only shares the radiance buffer with LATER shading passes, so it may overlap the
     // closest-hit traversal of bounce b+1 (which touches neither).
@@ -1721,10 +2048,66 @@ static int capture_frame_graph(rt_ctx* c, uint32_t max_bounces)
     return RT_OK;
 }
 
+// Which schedule rt_integrate runs.  Measured on B200 (profiles/r02_frame_kernel.txt): with ~4 or more 32-ray items per
+// resident warp and phase the per-phase kernels are faster (specialised register budgets: 5 CTAs/SM for traversal, and
+// every SM runs one kind of code at a time); below that the launch boundaries and kernel tails dominate and the one-kernel
+// frame wins (1.3x on a 1/8 partition of a 1080p frame).  RT_OPT_FRAME_KERNEL = 2 switches at 4096 pixels per SM.
+static bool frame_kernel_selected(const rt_ctx* c)
+{
+    if (c->frame_kernel == 2) return (size_t)c->n_local <= (size_t)c->num_sms * 4096u;
+    return c->frame_kernel == 1;
+}
+
+// CTA size of k_frame.  Measured (profiles/r02_frame_kernel.txt): one 1024-thread CTA per SM keeps all warps of an SM in the same
+// phase (one kind of code in the instruction caches) and is the fastest shape while every warp has several items per phase;
+// small partitions prefer 4 CTAs of 256 threads whose phases interleave.
+static int frame_kernel_threads(const rt_ctx* c)
+{
+    if (c->frame_threads) return c->frame_threads;
+    return (size_t)c->n_local > (size_t)c->num_sms * 2048u ? 1024 : 256;
+}
+
+// The whole frame as ONE persistent kernel (k_frame): a counter clear and a launch.
+static int integrate_frame_kernel(rt_ctx* c, uint32_t max_bounces)
+{
+    int rc = require_ready(c); if (rc) return rc;
+    if ((rc = join_shadow(c))) return rc;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    RT_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(DevCounters), c->stream));
+    const size_t stage = smem_stage_bytes(c);
+    const void* kern = stage ? (const void*)k_frame<true> : (const void*)k_frame<false>;
+    const int threads = frame_kernel_threads(c);
+    int per_sm = 0;
+    for (auto& e : c->occupancy) if (e.kernel == kern && e.smem == stage + ((size_t)threads << 32)) { per_sm = e.per_sm; break; }
+    if (!per_sm)
+    {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, stage) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        c->occupancy.push_back({ kern, stage + ((size_t)threads << 32), per_sm });
+    }
+    const uint32_t n_groups = (c->n_local + 31u) / 32u;
+    uint32_t grid = (uint32_t)(c->num_sms * per_sm);
+    if (grid > n_groups) grid = n_groups;
+    if (grid < 1) grid = 1;
+    const uint32_t slots_per_cta = ((n_groups + grid - 1u) / grid) * 32u;
+    if ((size_t)grid * slots_per_cta > c->n_alloc) RT_FAIL(c, RT_ERR_CUDA, "frame kernel: queue regions exceed the allocation");
+    const FrameDyn dyn = frame_dyn(c);
+    {
+        TimedLaunch t(c, RT_K_MISC);
+        if (stage) k_frame<true><<<grid, threads, stage, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
+        else k_frame<false><<<grid, threads, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
+    }
+    if ((rc = post_launch(c, "k_frame"))) return rc;
+    c->frame_started = true; c->cur_bounce = max_bounces;
+    ++c->sample_count;
+    return RT_OK;
+}
+
 int rt_integrate(rt_ctx* c, uint32_t max_bounces)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_integrate(k, max_bounces));
     if (max_bounces > RT_MAX_BOUNCES) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "max_bounces %u exceeds RT_MAX_BOUNCES", max_bounces);
+    if (frame_kernel_selected(c) && !c->kernel_timing && !c->count_traversal) return integrate_frame_kernel(c, max_bounces);
     if (!c->use_graph || c->kernel_timing || c->count_traversal) return integrate_body(c, max_bounces);
     int rc = require_ready(c); if (rc) return rc;
     RT_CUDA(c, cudaSetDevice(c->device));
@@ -1746,11 +2129,12 @@ int rt_integrate(rt_ctx* c, uint32_t max_bounces)
     return RT_OK;
 }
 
-int rt_resolve(rt_ctx* c, float* dst)
+// resolve kernel + device->host copy of this context's rows, enqueued on its stream (no synchronisation)
+static int resolve_enqueue(rt_ctx* c, float* dst)
 {
-    RT_CHECK_CTX(c);
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     RT_CUDA(c, cudaSetDevice(c->device));
+    if (c->copy_pending[0]) RT_CUDA(c, cudaStreamWaitEvent(c->stream, c->copy_done[0], 0));   // rt_resolve_async may still copy out of c->resolved
     {
         TimedLaunch t(c, RT_K_RESOLVE);
         k_resolve<<<grid_for(c->n_local), 256, 0, c->stream>>>(c->radiance, c->resolved, c->n_local, c->sample_count, c->denoiser,
@@ -1760,6 +2144,33 @@ int rt_resolve(rt_ctx* c, float* dst)
     if (dst && c->local_rows)
         RT_CUDA(c, cudaMemcpy2DAsync(dst + (size_t)c->rank * c->width * 4, (size_t)c->world * c->width * 16, c->resolved,
                                      (size_t)c->width * 16, (size_t)c->width * 16, c->local_rows, cudaMemcpyDeviceToHost, c->stream));
+    return RT_OK;
+}
+
+int rt_resolve(rt_ctx* c, float* dst)
+{
+    RT_CHECK_CTX(c);
+    if (!c->children.empty())
+    {
+        if (c->present == 1)
+        {   // the frame's ONE collective: radiance slabs -> first device over NVLink, resolved and read back there
+            int rc = rt_gather_radiance(c); if (rc) return rc;
+            rt_ctx* k0 = c->children[0];
+            rc = rt_resolve_gathered(k0, c->gather_buf, (uint64_t)c->gather_stride_f4 * 16, dst);
+            if (rc) c->error = k0->error;
+            return rc;
+        }
+        // parallel read-back: every device resolves its rows and copies them into the caller's image over its own PCIe
+        // link (page-lock the image, rt_host_register, for the copies to overlap); all enqueued first, then awaited
+        for (rt_ctx* k : c->children) { int rc = resolve_enqueue(k, dst); if (rc) { c->error = k->error; return rc; } }
+        for (rt_ctx* k : c->children)
+        {
+            if (cudaSetDevice(k->device) != cudaSuccess || cudaStreamSynchronize(k->stream) != cudaSuccess)
+                RT_FAIL(c, RT_ERR_CUDA, "rt_resolve: device %d failed: %s", k->device, cudaGetErrorString(cudaGetLastError()));
+        }
+        return RT_OK;
+    }
+    int rc = resolve_enqueue(c, dst); if (rc) return rc;
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
     return RT_OK;
 }
@@ -1770,7 +2181,7 @@ int rt_resolve(rt_ctx* c, float* dst)
  * untouched until rt_resolve_wait() (or the second-next rt_resolve_async) returns. */
 int rt_resolve_async(rt_ctx* c, float* dst)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_resolve_async(k, dst));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!dst) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_resolve_async: null destination");
     RT_CUDA(c, cudaSetDevice(c->device));
@@ -1805,7 +2216,7 @@ int rt_resolve_async(rt_ctx* c, float* dst)
 
 static int resolve_gathered_impl(rt_ctx* c, const void* slabs, uint64_t stride_bytes, float* dst, bool async)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_NOT_ON_GROUP(c, "rt_resolve_gathered");
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!slabs || !dst) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_resolve_gathered: null pointer");
     const size_t rows_max = ((size_t)c->height + c->world - 1) / c->world;
@@ -1854,7 +2265,7 @@ int rt_resolve_gathered_async(rt_ctx* c, const void* slabs, uint64_t stride_byte
 
 int rt_resolve_wait(rt_ctx* c)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_resolve_wait(k));
     RT_CUDA(c, cudaSetDevice(c->device));
     if (c->copy_stream) RT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     c->copy_pending[0] = c->copy_pending[1] = false;
@@ -1863,7 +2274,7 @@ int rt_resolve_wait(rt_ctx* c)
 
 int rt_sync(rt_ctx* c)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_sync(k));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1881,7 +2292,7 @@ static int ensure_scratch(rt_ctx* c, size_t bytes)
 
 int rt_read_hits(rt_ctx* c, uint32_t bounce, RtHit* hits, uint32_t* pixels, uint32_t* n_out)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_NOT_ON_GROUP(c, "rt_read_hits");
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (bounce > RT_MAX_BOUNCES || !n_out) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_hits: bad arguments");
     RT_CUDA(c, cudaSetDevice(c->device));
@@ -1901,7 +2312,7 @@ int rt_read_hits(rt_ctx* c, uint32_t bounce, RtHit* hits, uint32_t* pixels, uint
 
 int rt_read_rays(rt_ctx* c, uint32_t bounce, RtRay* rays, uint32_t* pixels, uint32_t* n_out)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_NOT_ON_GROUP(c, "rt_read_rays");
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (bounce > RT_MAX_BOUNCES || !n_out || !rays || !pixels) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_rays: bad arguments");
     RT_CUDA(c, cudaSetDevice(c->device));
@@ -1925,7 +2336,7 @@ int rt_read_rays(rt_ctx* c, uint32_t bounce, RtRay* rays, uint32_t* pixels, uint
 
 int rt_read_radiance(rt_ctx* c, float* dst)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_read_radiance(k, dst));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!dst) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_radiance: null destination");
     RT_CUDA(c, cudaSetDevice(c->device));
@@ -1939,6 +2350,24 @@ int rt_read_radiance(rt_ctx* c, float* dst)
 int rt_read_frame_stats(rt_ctx* c, RtFrameStats* out)
 {
     RT_CHECK_CTX(c);
+    if (!c->children.empty())
+    {   // whole-frame counters = sums over the partitions
+        if (!out) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_frame_stats: null destination");
+        static thread_local RtFrameStats part;
+        memset(out, 0, sizeof(*out));
+        for (rt_ctx* k : c->children)
+        {
+            int rc = rt_read_frame_stats(k, &part); if (rc) { c->error = k->error; return rc; }
+            for (uint32_t b = 0; b <= RT_MAX_BOUNCES; ++b)
+            {
+                out->n_ext[b] += part.n_ext[b]; out->n_miss[b] += part.n_miss[b]; out->n_emissive_hits[b] += part.n_emissive_hits[b];
+                out->n_shadow[b] += part.n_shadow[b]; out->n_cont[b] += part.n_cont[b]; out->n_unoccluded[b] += part.n_unoccluded[b];
+                out->nodes_ext[b] += part.nodes_ext[b]; out->tris_ext[b] += part.tris_ext[b];
+                out->nodes_shadow[b] += part.nodes_shadow[b]; out->tris_shadow[b] += part.tris_shadow[b];
+            }
+        }
+        return RT_OK;
+    }
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!out) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_read_frame_stats: null destination");
     RT_CUDA(c, cudaSetDevice(c->device));
@@ -1956,11 +2385,11 @@ int rt_read_frame_stats(rt_ctx* c, RtFrameStats* out)
     return RT_OK;
 }
 
-int rt_read_sample_count(rt_ctx* c, uint32_t* out) { RT_CHECK_CTX(c); if (!out) return RT_ERR_INVALID_ARGUMENT; *out = c->sample_count; return RT_OK; }
+int rt_read_sample_count(rt_ctx* c, uint32_t* out) { RT_CHECK_CTX(c); if (!out) return RT_ERR_INVALID_ARGUMENT; *out = c->children.empty() ? c->sample_count : c->children[0]->sample_count; return RT_OK; }
 
 int rt_read_aovs(rt_ctx* c, float* albedo, float* depth, float* normal, float* velocity)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_FANOUT(c, rt_read_aovs(k, albedo, depth, normal, velocity));
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     if (!c->aov_albedo) RT_FAIL(c, RT_ERR_NOT_READY, "AOV buffers do not exist: select an AOV view, enable the denoiser or set RT_OPT_AOV_ALWAYS first");
     RT_CUDA(c, cudaSetDevice(c->device));
@@ -1979,6 +2408,17 @@ int rt_read_aovs(rt_ctx* c, float* albedo, float* depth, float* normal, float* v
 int rt_kernel_times(rt_ctx* c, float* ms, uint32_t* launches)
 {
     RT_CHECK_CTX(c);
+    if (!c->children.empty())
+    {   // the devices run concurrently: per class the slowest device's time, launches summed
+        float m[RT_K_CLASS_COUNT]; uint32_t n[RT_K_CLASS_COUNT];
+        for (int i = 0; i < RT_K_CLASS_COUNT; ++i) { if (ms) ms[i] = 0.0f; if (launches) launches[i] = 0; }
+        for (rt_ctx* k : c->children)
+        {
+            int rc = rt_kernel_times(k, m, n); if (rc) { c->error = k->error; return rc; }
+            for (int i = 0; i < RT_K_CLASS_COUNT; ++i) { if (ms && m[i] > ms[i]) ms[i] = m[i]; if (launches) launches[i] += n[i]; }
+        }
+        return RT_OK;
+    }
     { int rt_j_ = join_shadow(c); if (rt_j_) return rt_j_; }
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1999,17 +2439,152 @@ int rt_kernel_times(rt_ctx* c, float* ms, uint32_t* launches)
     return RT_OK;
 }
 
-int rt_launch_count(rt_ctx* c, uint64_t* out) { RT_CHECK_CTX(c); if (!out) return RT_ERR_INVALID_ARGUMENT; *out = c->launches; return RT_OK; }
-int rt_local_pixel_count(rt_ctx* c, uint32_t* out) { RT_CHECK_CTX(c); if (!out) return RT_ERR_INVALID_ARGUMENT; *out = c->n_local; return RT_OK; }
+int rt_launch_count(rt_ctx* c, uint64_t* out)
+{
+    RT_CHECK_CTX(c); if (!out) return RT_ERR_INVALID_ARGUMENT;
+    *out = c->launches;
+    for (rt_ctx* k : c->children) *out += k->launches;
+    return RT_OK;
+}
+int rt_local_pixel_count(rt_ctx* c, uint32_t* out)
+{
+    RT_CHECK_CTX(c); if (!out) return RT_ERR_INVALID_ARGUMENT;
+    *out = c->n_local;
+    for (rt_ctx* k : c->children) *out += k->n_local;
+    return RT_OK;
+}
 
 int rt_radiance_device_ptr(rt_ctx* c, void** out_ptr, uint64_t* out_bytes)
 {
-    RT_CHECK_CTX(c);
+    RT_CHECK_CTX(c); RT_NOT_ON_GROUP(c, "rt_radiance_device_ptr");
     if (!out_ptr || !out_bytes) return RT_ERR_INVALID_ARGUMENT;
     *out_ptr = c->radiance; *out_bytes = (uint64_t)c->n_local * 16;
     return RT_OK;
 }
 
-int rt_stream_handle(rt_ctx* c, void** out) { RT_CHECK_CTX(c); if (!out) return RT_ERR_INVALID_ARGUMENT; *out = (void*)c->stream; return RT_OK; }
+int rt_stream_handle(rt_ctx* c, void** out) { RT_CHECK_CTX(c); RT_NOT_ON_GROUP(c, "rt_stream_handle"); if (!out) return RT_ERR_INVALID_ARGUMENT; *out = (void*)c->stream; return RT_OK; }
+
+/* One context over several devices of the node ("multi-GPU fan-out internal to the shim"; the reference's CLContext
+ * enumerates every device of its platform, cl_context.cpp:64-89, and uses one).  devices[i] renders rank i of an n-way scanline
+ * partition with the scene replicated; the caller stays single-threaded and every call fans out.  A device may be listed more
+ * than once (two partitions time-share it). */
+int rt_create_multi(uint32_t width, uint32_t height, const int* devices, uint32_t n_devices, rt_ctx** out_ctx)
+{
+    if (!out_ctx || !devices || n_devices == 0 || n_devices > 64)
+    {
+        g_create_error = "rt_create_multi: bad arguments (need 1..64 devices)"; return RT_ERR_INVALID_ARGUMENT;
+    }
+    *out_ctx = nullptr;
+    if (n_devices == 1) return rt_create(width, height, devices[0], out_ctx);
+    rt_ctx* g = new rt_ctx;
+    g->width = width; g->height = height; g->world = n_devices; g->device = devices[0];
+    for (uint32_t i = 0; i < n_devices; ++i)
+    {
+        rt_ctx* k = nullptr;
+        int rc = rt_create(width, height, devices[i], &k);
+        if (rc == RT_OK) { rc = rt_set_partition(k, i, n_devices); if (rc != RT_OK) { g_create_error = k->error; rt_destroy(k); } }
+        if (rc != RT_OK) { for (rt_ctx* o : g->children) rt_destroy(o); delete g; return rc; }
+        g->children.push_back(k);
+    }
+    // peer access towards the first device for the NVLink gather (ignored where it is already on / not available:
+    // cudaMemcpyPeerAsync then stages through the host)
+    for (uint32_t i = 1; i < n_devices; ++i)
+        if (devices[i] != devices[0])
+        {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) == cudaSuccess && can)
+            {
+                cudaSetDevice(devices[i]);
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
+                if (e != cudaSuccess) cudaGetLastError();       // cudaErrorPeerAccessAlreadyEnabled included
+            }
+        }
+    *out_ctx = g;
+    return RT_OK;
+}
+
+/* The single collective of a multi-device frame (north_star): every device's radiance slab is copied to the first device
+ * (cudaMemcpyPeerAsync on the source device's stream: NVLink / NVSwitch between peers), into world slabs of stride
+ * rows_max * width float4 — the layout rt_resolve_gathered reads.  The first device's stream then waits for all copies. */
+int rt_gather_radiance(rt_ctx* c)
+{
+    RT_CHECK_CTX(c);
+    if (c->children.empty()) RT_FAIL(c, RT_ERR_UNSUPPORTED, "rt_gather_radiance needs a multi-device context (rt_create_multi)");
+    rt_ctx* k0 = c->children[0];
+    const size_t rows_max = ((size_t)c->height + c->world - 1) / c->world;
+    const size_t stride = rows_max * c->width;
+    RT_CUDA(c, cudaSetDevice(k0->device));
+    if (!c->gather_buf)
+    {
+        RT_CUDA(c, cudaMalloc(&c->gather_buf, stride * c->world * 16));
+        RT_CUDA(c, cudaMemsetAsync(c->gather_buf, 0, stride * c->world * 16, k0->stream));
+        RT_CUDA(c, cudaStreamSynchronize(k0->stream));
+        c->gather_stride_f4 = stride;
+        c->gather_events.resize(c->world, nullptr);
+    }
+    for (uint32_t i = 0; i < c->world; ++i)
+    {
+        rt_ctx* k = c->children[i];
+        { int rc = join_shadow(k); if (rc) { c->error = k->error; return rc; } }
+        RT_CUDA(c, cudaSetDevice(k->device));
+        if (!c->gather_events[i]) RT_CUDA(c, cudaEventCreateWithFlags(&c->gather_events[i], cudaEventDisableTiming));
+        if (k->n_local)
+            RT_CUDA(c, cudaMemcpyPeerAsync(c->gather_buf + (size_t)i * stride, k0->device, k->radiance, k->device, (size_t)k->n_local * 16, k->stream));
+        RT_CUDA(c, cudaEventRecord(c->gather_events[i], k->stream));
+    }
+    RT_CUDA(c, cudaSetDevice(k0->device));
+    for (uint32_t i = 1; i < c->world; ++i) RT_CUDA(c, cudaStreamWaitEvent(k0->stream, c->gather_events[i], 0));
+    return RT_OK;
+}
+
+int rt_device_count(int* out)
+{
+    if (!out) return RT_ERR_INVALID_ARGUMENT;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *out = n;
+    return RT_OK;
+}
+
+/* Page-locks / releases a caller-owned host buffer (the image handed to rt_resolve): device->host copies into page-locked
+ * memory are asynchronous, which is what lets the devices of a multi-device context read back in parallel. */
+int rt_host_register(void* ptr, uint64_t bytes)
+{
+    if (!ptr || !bytes) return RT_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); g_create_error = std::string("rt_host_register: ") + cudaGetErrorString(e); return RT_ERR_CUDA; }
+    return RT_OK;
+}
+int rt_host_unregister(void* ptr)
+{
+    if (!ptr) return RT_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); g_create_error = std::string("rt_host_unregister: ") + cudaGetErrorString(e); return RT_ERR_CUDA; }
+    return RT_OK;
+}
+
+/* Parity tap: out[i] = f(a[i], b[i]) for a function of include/rt_math.h, evaluated on `device` (host pointers; blocking).
+ * fn: 0 sin 1 cos 2 tan 3 atan2(a, b) 4 acos 5 pow(a, b) 6 fmin 7 fmax 8 1/sqrt(a) 9 a / b. */
+int rt_math_eval(int device, int fn, const float* a, const float* b, float* out, uint64_t n)
+{
+    if (!a || !b || !out || fn < 0 || fn > 9) return RT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return RT_OK;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); g_create_error = "rt_math_eval: no such CUDA device"; return RT_ERR_NO_DEVICE; }
+    float *da = nullptr, *db = nullptr, *dout = nullptr;
+    cudaError_t e = cudaMalloc(&da, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&db, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, n * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(da, a, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(db, b, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+    {
+        k_math_eval<<<(unsigned)((n + 255) / 256), 256>>>(fn, da, db, dout, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    if (e != cudaSuccess) { g_create_error = std::string("rt_math_eval: ") + cudaGetErrorString(e); return RT_ERR_CUDA; }
+    return RT_OK;
+}
 
 } // extern "C"

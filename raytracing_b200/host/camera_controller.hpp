@@ -44,6 +44,7 @@ public:
     void SetAperture(float a) { camera_data_.aperture = a; }
     void SetFocusDistance(float d) { camera_data_.focus_distance = d; }
     void SetPosition(float3 p) { camera_data_.position = p; }
+    void SetData(Camera const& c) { camera_data_ = c; }     // headless drivers place the camera directly (no fly controls)
 
 private:
     Camera camera_data_;

@@ -24,9 +24,35 @@ CUDAPathTraceIntegrator::CUDAPathTraceIntegrator(std::uint32_t width, std::uint3
     Reset();            // "Don't forget to reset frame index", cl_pt_integrator.cpp:257-258
 }
 
+CUDAPathTraceIntegrator::CUDAPathTraceIntegrator(std::uint32_t width, std::uint32_t height, AccelerationStructure& acc_structure,
+                                                 std::vector<int> const& devices, Schedule schedule)
+    : Integrator(width, height, acc_structure), schedule_(schedule)
+{
+    std::vector<int> list = devices;
+    if (list.empty())
+    {
+        int n = 0;
+        rt_device_count(&n);
+        for (int i = 0; i < n; ++i) list.push_back(i);
+    }
+    int status = list.empty() ? RT_ERR_NO_DEVICE : rt_create_multi(width, height, list.data(), (std::uint32_t)list.size(), &ctx_);
+    if (status != RT_OK)
+        throw std::runtime_error(std::string("Failed to create the CUDA path tracing context: ") + (list.empty() ? "no CUDA device" : rt_last_error(nullptr)));
+    CreateKernels();
+    Reset();
+}
+
 CUDAPathTraceIntegrator::~CUDAPathTraceIntegrator()
 {
+    if (resolve_target_ && resolve_target_locked_) rt_host_unregister(resolve_target_);
     if (ctx_) rt_destroy(ctx_);
+}
+
+void CUDAPathTraceIntegrator::SetResolveTarget(float* host_rgba, bool page_lock)
+{
+    if (resolve_target_ && resolve_target_locked_) rt_host_unregister(resolve_target_);
+    resolve_target_ = host_rgba;
+    resolve_target_locked_ = host_rgba && page_lock && rt_host_register(host_rgba, (std::uint64_t)width_ * height_ * 16) == RT_OK;
 }
 
 // Kernel variants are compiled ahead of time for sm_100a (there is no runtime compilation / hot reload,
@@ -91,8 +117,41 @@ void CUDAPathTraceIntegrator::EnableDenoiser(bool enable)
 }
 
 void CUDAPathTraceIntegrator::Reset() { Check(rt_reset(ctx_), "Reset"); }
-void CUDAPathTraceIntegrator::AdvanceSampleCount() { Check(rt_advance_sample_count(ctx_), "AdvanceSampleCount"); }
-void CUDAPathTraceIntegrator::GenerateRays() { Check(rt_generate_rays(ctx_), "GenerateRays"); }
+
+// ---- the per-frame steps.  kFrame: Integrate() (integrator.cpp:27-59, not virtual) calls them in a fixed order; they are
+// checked against that order and the frame is submitted as a whole in AdvanceSampleCount().
+void CUDAPathTraceIntegrator::GenerateRays()
+{
+    if (schedule_ == Schedule::kFrame) { frame_deferred_ = true; deferred_shaded_ = deferred_accumulated_ = 0; return; }
+    Check(rt_generate_rays(ctx_), "GenerateRays");
+}
+
+void CUDAPathTraceIntegrator::FlushDeferredFrame()
+{
+    if (!frame_deferred_) return;
+    frame_deferred_ = false;
+    Check(rt_generate_rays(ctx_), "GenerateRays");
+    for (std::uint32_t b = 0; b < deferred_shaded_; ++b)
+    {
+        Check(rt_extend_shade(ctx_, b), "ShadeSurfaceHits (fused intersect+miss+shade)");
+        if (b < deferred_accumulated_) Check(rt_shadow_accumulate(ctx_, b), "AccumulateDirectSamples (fused shadow trace+accumulate)");
+    }
+}
+
+void CUDAPathTraceIntegrator::AdvanceSampleCount()
+{
+    if (frame_deferred_)
+    {
+        if (deferred_shaded_ == max_bounces_ + 1 && deferred_accumulated_ == max_bounces_ + 1)
+        {   // the canonical frame: one call, rt_integrate advances the sample count itself
+            frame_deferred_ = false;
+            Check(rt_integrate(ctx_, max_bounces_), "Integrate (whole frame)");
+            return;
+        }
+        FlushDeferredFrame();
+    }
+    Check(rt_advance_sample_count(ctx_), "AdvanceSampleCount");
+}
 
 void CUDAPathTraceIntegrator::IntersectRays(std::uint32_t bounce)
 {
@@ -113,6 +172,11 @@ void CUDAPathTraceIntegrator::ClearShadowRayCounter() { Check(rt_clear_shadow_co
 void CUDAPathTraceIntegrator::ShadeSurfaceHits(std::uint32_t bounce)
 {
     current_bounce_ = bounce;
+    if (frame_deferred_)
+    {
+        if (bounce == deferred_shaded_ && deferred_accumulated_ == deferred_shaded_) { ++deferred_shaded_; return; }
+        FlushDeferredFrame();                 // not the canonical order: run what was recorded, continue call by call
+    }
     if (schedule_ == Schedule::kStepwise) Check(rt_shade_hits(ctx_, bounce), "ShadeSurfaceHits");
     else Check(rt_extend_shade(ctx_, bounce), "ShadeSurfaceHits (fused intersect+miss+shade)");
 }
@@ -124,6 +188,11 @@ void CUDAPathTraceIntegrator::IntersectShadowRays()
 
 void CUDAPathTraceIntegrator::AccumulateDirectSamples()
 {
+    if (frame_deferred_)
+    {
+        if (deferred_accumulated_ + 1 == deferred_shaded_ && current_bounce_ + 1 == deferred_shaded_) { ++deferred_accumulated_; return; }
+        FlushDeferredFrame();
+    }
     if (schedule_ == Schedule::kStepwise) Check(rt_accumulate_direct(ctx_), "AccumulateDirectSamples");
     else Check(rt_shadow_accumulate(ctx_, current_bounce_), "AccumulateDirectSamples (fused shadow trace+accumulate)");
 }

@@ -6,7 +6,12 @@
  * std::runtime_error, the behaviour callers of the OpenCL backend see (CLException).
  *
  * Schedules:
- *   kFused (default)  the seven per-bounce virtuals map onto TWO kernels: ShadeSurfaceHits(b) launches
+ *   kFrame (default)  Integrate() is not virtual and calls the 15 virtuals in a fixed order (integrator.cpp:27-59); here the
+ *                     steps between GenerateRays() and AdvanceSampleCount() only check that order, and AdvanceSampleCount()
+ *                     submits the WHOLE frame with one rt_integrate call (one persistent kernel, or one graph replay of the
+ *                     per-phase kernels: the schedule bench.py measures).  A caller that drives the virtuals in another
+ *                     order falls back to kFused for that frame: the steps seen so far are replayed, the rest run as they come.
+ *   kFused            the seven per-bounce virtuals map onto TWO kernels: ShadeSurfaceHits(b) launches
  *                     the fused intersect+miss+shade kernel, AccumulateDirectSamples() the fused
  *                     shadow-trace+accumulate kernel; IntersectRays, ShadeMissedRays, the two counter
  *                     clears and IntersectShadowRays are empty (the OpenGL backend of the reference
@@ -24,6 +29,7 @@
 #pragma once
 
 #include <string>
+#include <vector>
 
 #include "reference_api.hpp"
 #include "rt_b200.h"
@@ -34,10 +40,14 @@ namespace rt_host
 class CUDAPathTraceIntegrator : public Integrator
 {
 public:
-    enum class Schedule { kFused, kStepwise };
+    enum class Schedule { kFrame, kFused, kStepwise };
 
     CUDAPathTraceIntegrator(std::uint32_t width, std::uint32_t height, AccelerationStructure& acc_structure,
-                            int device = 0, Schedule schedule = Schedule::kFused);
+                            int device = 0, Schedule schedule = Schedule::kFrame);
+    // several devices of the node behind ONE integrator (rt_create_multi: device i renders the rows y % n == i); an empty
+    // list means every CUDA device of the node, as CLContext enumerates every device of its platform (cl_context.cpp:64-89)
+    CUDAPathTraceIntegrator(std::uint32_t width, std::uint32_t height, AccelerationStructure& acc_structure,
+                            std::vector<int> const& devices, Schedule schedule = Schedule::kFrame);
     ~CUDAPathTraceIntegrator() override;
 
     void UploadGPUData(Scene const& scene, AccelerationStructure const& acc_structure) override;
@@ -48,7 +58,9 @@ public:
 
     // sobol_256spp_256d[256*256], scramblingTile[128*128*8], rankingTile[128*128*8]; copied to the device
     void SetBlueNoiseTables(const int* sobol_256spp_256d, const int* scrambling_tile, const int* ranking_tile);
-    void SetResolveTarget(float* host_rgba) { resolve_target_ = host_rgba; }
+    // host RGBA32F image that ResolveRadiance() fills; page_lock = true registers it with the driver (rt_host_register) so that
+    // the device->host copies are asynchronous (several devices then read back in parallel)
+    void SetResolveTarget(float* host_rgba, bool page_lock = false);
     void SetSchedule(Schedule s) { schedule_ = s; }
     rt_ctx* Context() const { return ctx_; }
 
@@ -72,10 +84,16 @@ protected:
 private:
     void Check(int status, const char* what) const;
 
+    void FlushDeferredFrame();     // kFrame: replay the recorded steps through the per-call API (order was not the canonical one)
+
     rt_ctx* ctx_ = nullptr;
     Schedule schedule_;
     std::uint32_t current_bounce_ = 0;
     float* resolve_target_ = nullptr;
+    bool resolve_target_locked_ = false;
+    // kFrame bookkeeping: a frame is "deferred" from GenerateRays() until AdvanceSampleCount()
+    bool frame_deferred_ = false;
+    std::uint32_t deferred_shaded_ = 0, deferred_accumulated_ = 0;   // bounces whose ShadeSurfaceHits / AccumulateDirectSamples were seen
 };
 
 } // namespace rt_host

@@ -29,6 +29,21 @@ void* rth_scene_load(const char* obj_path, float scale, int flip_yz)
     try { auto* h = new SceneHandle; h->scene.reset(new Scene(obj_path, scale, flip_yz != 0)); return h; }
     catch (std::exception& e) { g_error = e.what(); return nullptr; }
 }
+// Scene from arrays in the reference layout (a scene dump); the triangles are copied (Render's BVH build reorders them)
+void* rth_scene_from_arrays(const RtTriangle* triangles, size_t n_triangles, const RtPackedMaterial* materials, size_t n_materials,
+                            const RtLight* lights, size_t n_lights, const RtTexture* textures, size_t n_textures,
+                            const std::uint32_t* texels, size_t n_texels)
+{
+    try
+    {
+        auto* h = new SceneHandle;
+        h->scene.reset(new Scene(std::vector<Triangle>(triangles, triangles + n_triangles), std::vector<PackedMaterial>(materials, materials + n_materials),
+                                 std::vector<Light>(lights, lights + n_lights), std::vector<Texture>(textures, textures + n_textures),
+                                 std::vector<std::uint32_t>(texels, texels + n_texels)));
+        return h;
+    }
+    catch (std::exception& e) { g_error = e.what(); return nullptr; }
+}
 void rth_scene_free(void* h) { delete (SceneHandle*)h; }
 
 int rth_scene_add_directional_light(void* h, float dx, float dy, float dz, float r, float g, float b)
@@ -110,6 +125,47 @@ void* rth_render_create(void* scene_handle, std::uint32_t width, std::uint32_t h
         return h;
     }
     catch (std::exception& e) { g_error = e.what(); return nullptr; }
+}
+// Same over several devices (n_devices == 0: every CUDA device of the node); schedule: 0 whole frame (default), 1 fused per bounce, 2 stepwise
+void* rth_render_create_multi(void* scene_handle, std::uint32_t width, std::uint32_t height, const char* env_path, const int* devices, std::uint32_t n_devices, int schedule)
+{
+    try
+    {
+        auto* s = (SceneHandle*)scene_handle;
+        auto* h = new RenderHandle;
+        std::vector<int> list(devices, devices + n_devices);
+        h->render.reset(new Render(width, height, Render::RenderBackend::kCUDA, *s->scene, env_path, list));
+        auto& it = static_cast<CUDAPathTraceIntegrator&>(h->render->GetIntegrator());
+        it.SetSchedule(schedule == 2 ? CUDAPathTraceIntegrator::Schedule::kStepwise : (schedule == 1 ? CUDAPathTraceIntegrator::Schedule::kFused : CUDAPathTraceIntegrator::Schedule::kFrame));
+        return h;
+    }
+    catch (std::exception& e) { g_error = e.what(); return nullptr; }
+}
+// Same with the environment image handed over decoded (RGBA32F, env_w x env_h)
+void* rth_render_create_env(void* scene_handle, std::uint32_t width, std::uint32_t height, const float* env, std::uint32_t env_w, std::uint32_t env_h,
+                            const int* devices, std::uint32_t n_devices, int schedule)
+{
+    try
+    {
+        auto* s = (SceneHandle*)scene_handle;
+        auto* h = new RenderHandle;
+        Image img; img.width = env_w; img.height = env_h; img.data.assign(env, env + (size_t)env_w * env_h * 4);
+        h->render.reset(new Render(width, height, Render::RenderBackend::kCUDA, *s->scene, img, std::vector<int>(devices, devices + n_devices)));
+        auto& it = static_cast<CUDAPathTraceIntegrator&>(h->render->GetIntegrator());
+        it.SetSchedule(schedule == 2 ? CUDAPathTraceIntegrator::Schedule::kStepwise : (schedule == 1 ? CUDAPathTraceIntegrator::Schedule::kFused : CUDAPathTraceIntegrator::Schedule::kFrame));
+        return h;
+    }
+    catch (std::exception& e) { g_error = e.what(); return nullptr; }
+}
+int rth_render_set_camera(void* h, const RtCamera* cam)
+{
+    ((RenderHandle*)h)->render->GetCamera().SetData(*cam); ((RenderHandle*)h)->render->NotifyCameraChanged(); return 0;
+}
+int rth_render_set_schedule(void* h, int schedule)
+{
+    auto& it = static_cast<CUDAPathTraceIntegrator&>(((RenderHandle*)h)->render->GetIntegrator());
+    it.SetSchedule(schedule == 2 ? CUDAPathTraceIntegrator::Schedule::kStepwise : (schedule == 1 ? CUDAPathTraceIntegrator::Schedule::kFused : CUDAPathTraceIntegrator::Schedule::kFrame));
+    return 0;
 }
 void rth_render_free(void* h) { delete (RenderHandle*)h; }
 int rth_render_set_max_bounces(void* h, std::uint32_t b)

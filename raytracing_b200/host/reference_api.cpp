@@ -125,6 +125,16 @@ void parse_mtl(const std::string& path, std::vector<MtlRecord>& mats, std::map<s
 
 Scene::Scene(const char* filename, float scale, bool flip_yz) { Load(filename, scale, flip_yz); }
 
+Scene::Scene(std::vector<Triangle> triangles, std::vector<PackedMaterial> materials, std::vector<Light> lights,
+             std::vector<Texture> textures, std::vector<std::uint32_t> texture_data)
+    : triangles_(std::move(triangles)), materials_(std::move(materials)), lights_(std::move(lights)),
+      textures_(std::move(textures)), texture_data_(std::move(texture_data))
+{
+    if (triangles_.empty() || materials_.empty()) throw std::runtime_error("Scene: triangles and materials are required");
+    for (Triangle const& t : triangles_)
+        if (t.mtlIndex >= materials_.size()) throw std::runtime_error("Scene: triangle references a missing material");
+}
+
 // scene.cpp:127-274
 void Scene::Load(const char* filename, float scale, bool flip_yz)
 {
@@ -215,6 +225,7 @@ void Scene::Load(const char* filename, float scale, bool flip_yz)
             const Corner& c = face.c[k];
             if (c.v < 0 || (size_t)c.v * 3 + 2 >= positions.size()) throw std::runtime_error("OBJ face references a missing vertex");
             if (c.vn < 0 || (size_t)c.vn * 3 + 2 >= normals.size()) throw std::runtime_error("OBJ face has no normal (normals are required, scene.cpp:222-224)");
+            if (c.vt >= 0 && (size_t)c.vt * 2 + 1 >= texcoords.size()) throw std::runtime_error("OBJ face references a missing texture coordinate");
             Vertex& v = *vs[k];
             v.position = make_float3(positions[c.v * 3 + 0] * scale, positions[c.v * 3 + 1] * scale, positions[c.v * 3 + 2] * scale);
             v.normal = make_float3(normals[c.vn * 3 + 0], normals[c.vn * 3 + 1], normals[c.vn * 3 + 2]);
@@ -280,6 +291,7 @@ bool read_flat(std::vector<Rgbe>& line, size_t from, FILE* f)
         if (e == EOF) return false;
         if (r == 1 && g == 1 && b == 1)
         {
+            if (i == 0) return false;             // a run marker needs a previous pixel to repeat
             for (int n = e << rshift; n > 0 && i < line.size(); --n) { line[i] = line[i - 1]; ++i; }
             rshift += 8;
         }

@@ -107,6 +107,10 @@ class Scene
 {
 public:
     Scene(const char* filename, float scale, bool flip_yz);
+    // Headless construction from arrays that are already in the reference layout (a scene dump: Triangle[160 B], PackedMaterial[20 B],
+    // Light[48 B], Texture[16 B] + texels) — the state a Scene is in after Load() and the Add*Light calls; bench/test plumbing.
+    Scene(std::vector<Triangle> triangles, std::vector<PackedMaterial> materials, std::vector<Light> lights,
+          std::vector<Texture> textures, std::vector<std::uint32_t> texture_data);
 
     std::vector<Triangle>& GetTriangles() { return triangles_; }
     std::vector<Triangle> const& GetTriangles() const { return triangles_; }

@@ -26,6 +26,12 @@ public:
 
     Render(std::uint32_t width, std::uint32_t height, RenderBackend backend, Scene& scene,
            const char* env_map_path = "assets/ibl/CGSkies_0036_free.hdr", int device = 0);
+    // kCUDA over several devices of the node (empty list = all of them): one integrator, the image partitioned by scanline
+    Render(std::uint32_t width, std::uint32_t height, RenderBackend backend, Scene& scene,
+           const char* env_map_path, std::vector<int> const& devices);
+    // headless: the environment image is handed over decoded (RGBA32F rows) instead of being read from an .hdr file
+    Render(std::uint32_t width, std::uint32_t height, RenderBackend backend, Scene& scene,
+           Image const& env_image, std::vector<int> const& devices);
 
     void RenderFrame();
     Integrator& GetIntegrator() { return *integrator_; }
@@ -36,6 +42,7 @@ public:
     void NotifyCameraChanged() { camera_changed_ = true; }
 
 private:
+    void Init(RenderBackend backend, const char* env_map_path, const Image* env_image, const std::vector<int>* devices, int device);
     Scene& scene_;
     std::uint32_t width_, height_;
     std::unique_ptr<Integrator> integrator_;

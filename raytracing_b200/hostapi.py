@@ -122,16 +122,73 @@ class HostScene:
             self.h = None
 
 
+def scene_from_arrays(scene: dict):
+    """HostScene holding a scene dump (dict of arrays in the reference layout): the C++ Scene as it is after Load() and the
+    Add*Light calls (bench/test plumbing; the triangles are copied)."""
+    from .layouts import LIGHT_DT, MATERIAL_DT, TEXTURE_DT, TRIANGLE_DT
+    hs = HostScene.__new__(HostScene)
+    hs.L = load_library()
+    hs.L.rth_scene_from_arrays.restype = C.c_void_p
+    hs.L.rth_scene_from_arrays.argtypes = [C.c_void_p, C.c_size_t] * 5
+    t = np.ascontiguousarray(scene["triangles"], dtype=TRIANGLE_DT); m = np.ascontiguousarray(scene["materials"], dtype=MATERIAL_DT)
+    li = np.ascontiguousarray(scene["lights"], dtype=LIGHT_DT); tx = np.ascontiguousarray(scene["textures"], dtype=TEXTURE_DT)
+    te = np.ascontiguousarray(scene["texels"], dtype="<u4")
+    hs.h = hs.L.rth_scene_from_arrays(t.ctypes.data, len(t), m.ctypes.data, len(m), li.ctypes.data, len(li), tx.ctypes.data, len(tx), te.ctypes.data, len(te))
+    if not hs.h:
+        raise _err(hs.L)
+    return hs
+
+
 class HostRender:
     """rt_host::Render(width, height, RenderBackend::kCUDA, scene): builds the BVH, finalizes the scene, creates the
     CUDAPathTraceIntegrator and uploads, like Render::Render in the reference (render.cpp:38-83)."""
 
-    def __init__(self, scene: HostScene, width, height, env_path, device=0, stepwise=False):
+    SCHEDULES = {"frame": 0, "fused": 1, "stepwise": 2}
+
+    def __init__(self, scene: HostScene, width, height, env_path, device=0, stepwise=False, devices=None, schedule=None):
+        """devices = [d0, d1, ...] (or [] for every CUDA device of the node): one CUDAPathTraceIntegrator over several GPUs
+        (rt_create_multi).  schedule: "frame" (default: Integrate() submits the whole frame with one call), "fused" (two
+        kernels per bounce as the virtuals arrive), "stepwise" (one kernel per virtual)."""
         self.L = scene.L
         self.width, self.height = width, height
-        self.h = self.L.rth_render_create(scene.h, width, height, env_path.encode(), device, int(stepwise))
+        sched = self.SCHEDULES[schedule] if schedule else (2 if stepwise else 0)
+        if env_path is None:
+            raise ValueError("env_path is required (use HostRender.with_env_image for a decoded environment image)")
+        if devices is not None:
+            self.L.rth_render_create_multi.restype = C.c_void_p
+            self.L.rth_render_create_multi.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_int), C.c_uint32, C.c_int]
+            arr = (C.c_int * max(len(devices), 1))(*devices)
+            self.h = self.L.rth_render_create_multi(scene.h, width, height, env_path.encode(), arr, len(devices), sched)
+        else:
+            self.h = self.L.rth_render_create(scene.h, width, height, env_path.encode(), device, int(stepwise))
         if not self.h:
             raise _err(self.L)
+        if devices is None and schedule:
+            self.set_schedule(schedule)
+
+    @classmethod
+    def with_env_image(cls, scene: HostScene, width, height, env_rgba, env_width, env_height, devices, schedule="frame"):
+        """Render over `devices` with the environment image handed over decoded (RGBA32F rows)."""
+        self = cls.__new__(cls)
+        self.L = scene.L
+        self.width, self.height = width, height
+        self.L.rth_render_create_env.restype = C.c_void_p
+        self.L.rth_render_create_env.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_int), C.c_uint32, C.c_int]
+        env = np.ascontiguousarray(env_rgba, dtype="<f4")
+        arr = (C.c_int * max(len(devices), 1))(*devices)
+        self.h = self.L.rth_render_create_env(scene.h, width, height, env.ctypes.data, env_width, env_height, arr, len(devices), cls.SCHEDULES[schedule])
+        if not self.h:
+            raise _err(self.L)
+        return self
+
+    def set_camera(self, cam):
+        c = np.ascontiguousarray(cam)
+        self.L.rth_render_set_camera.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.rth_render_set_camera(self.h, c.ctypes.data)
+
+    def set_schedule(self, schedule):
+        self.L.rth_render_set_schedule.argtypes = [C.c_void_p, C.c_int]
+        self.L.rth_render_set_schedule(self.h, self.SCHEDULES[schedule])
 
     def set_max_bounces(self, b):
         if self.L.rth_render_set_max_bounces(self.h, b) != 0:

@@ -198,26 +198,58 @@ def test_gathered_frame_resolves_like_a_single_gpu_frame():
         c.destroy()
 
 
-def test_full_size_properties_1080p():
-    """BASELINE config C2 at full size (CornellBox 1920x1080, 8 bounces): size-independent properties.
-    fused == stepwise bit-for-bit; live-ray counters are monotone and consistent; a 64-row band equals the oracle."""
-    name, w, h, mb = "CornellBox", 1920, 1080, 8
-    a = make_ctx(name, w, h); b = make_ctx(name, w, h)
-    a.reset(); b.reset()
-    a.integrate(mb); b.integrate_stepwise(mb)
-    ra, rb = a.read_radiance(), b.read_radiance()
+@pytest.mark.parametrize("name,w,h,mb,row_first,row_step", [
+    ("CornellBox", 1920, 1080, 8, 5, 17),              # BASELINE C2: 64 oracle rows
+    ("ShaderBalls", 1920, 1080, 8, 3, 23),             # C3: 47 oracle rows
+    ("CornellBox_Dragon", 3840, 2160, 16, 11, 97),     # C4: 23 oracle rows of the 4K frame, 16 bounces
+])
+def test_full_size_properties(name, w, h, mb, row_first, row_step):
+    """The benchmarked configurations AT THE BENCHMARKED SIZE: the three schedules (per-phase kernels, one-kernel frame,
+    stepwise) agree bit for bit on the whole frame; live-ray counters are monotone and consistent; a band of rows spread over
+    the frame equals the oracle."""
+    a = make_ctx(name, w, h); a.set_option(capi.OPT_FRAME_KERNEL, 0)
+    f = make_ctx(name, w, h); f.set_option(capi.OPT_FRAME_KERNEL, 1)
+    b = make_ctx(name, w, h)
+    for c in (a, f, b):
+        c.reset()
+    a.integrate(mb); f.integrate(mb); b.integrate_stepwise(mb)
+    ra, rf, rb = a.read_radiance(), f.read_radiance(), b.read_radiance()
     assert np.array_equal(bits(ra), bits(rb))
+    assert np.array_equal(bits(ra), bits(rf))
     st = a.frame_stats()
+    for k in ("n_ext", "n_miss", "n_shadow", "n_cont", "n_unoccluded", "n_emissive_hits"):
+        assert np.array_equal(st[k][: mb + 1], f.frame_stats()[k][: mb + 1]), k
     n_ext = st["n_ext"][: mb + 1]
     assert n_ext[0] == w * h and (np.diff(n_ext.astype(np.int64)) <= 0).all()
     assert np.array_equal(st["n_cont"][:mb], n_ext[1:])
     assert (st["n_shadow"][: mb + 1] <= n_ext - st["n_miss"][: mb + 1]).all()
     assert (st["n_unoccluded"][: mb + 1] <= st["n_shadow"][: mb + 1]).all()
-    # oracle on every 17th row (row partition with step 17 traces 64 rows)
-    orad, _, _ = Oracle(scene(name)).render(default_camera(w, h), w, h, mb, row_first=5, row_step=17)
-    rows = np.arange(5, h, 17)
+    orad, _, _ = Oracle(scene(name)).render(default_camera(w, h), w, h, mb, row_first=row_first, row_step=row_step)
+    rows = np.arange(row_first, h, row_step)
     assert np.array_equal(bits(ra[rows][..., :3]), bits(orad[rows][..., :3]))
-    a.destroy(); b.destroy()
+    for c in (a, f, b):
+        c.destroy()
+
+
+@pytest.mark.slow
+def test_full_size_synthetic_10m_triangles():
+    """BASELINE C5 at full size: 183 copies of ShaderBalls + ground = 10 026 572 triangles, 1920x1080, 8 bounces (scene build and
+    host BVH build take a minute: RT_TEST_SLOW=1).  Per-phase kernels == one-kernel frame on the whole frame, a band of 31 rows
+    equals the oracle, and more than 90 % of the primary rays hit geometry."""
+    from raytracing_b200 import scene_io, synthetic
+    w, h, mb = 1920, 1080, 8
+    sc = synthetic.bistro_scale_scene(scene_io.load_scene("ShaderBalls"), 183, w, h)
+    cam = sc["camera_pose"]
+    imgs = []
+    for fk in (0, 1):
+        c = capi.Context(w, h); c.set_option(capi.OPT_FRAME_KERNEL, fk)
+        c.upload_scene(sc); c.set_camera(cam); c.reset(); c.integrate(mb)
+        imgs.append(c.read_radiance()); st = c.frame_stats(); c.destroy()
+    assert np.array_equal(bits(imgs[0]), bits(imgs[1]))
+    assert 1.0 - st["n_miss"][0] / st["n_ext"][0] > 0.9
+    orad, _, _ = Oracle(sc).render(cam, w, h, mb, row_first=7, row_step=35)
+    rows = np.arange(7, h, 35)
+    assert np.array_equal(bits(imgs[0][rows][..., :3]), bits(orad[rows][..., :3]))
 
 
 def test_synthetic_field_matches_oracle():
@@ -389,6 +421,7 @@ def test_shadow_pass_overlap_modes_are_equivalent(name, w, h, mb):
     for overlap in (0, 1, 2):
         for graph, pdl in ((1, 1), (0, 1), (0, 0)):
             c = make_ctx(name, w, h)
+            c.set_option(capi.OPT_FRAME_KERNEL, 0)           # the per-phase kernels (rt_integrate's default is the one-kernel frame)
             c.set_option(capi.OPT_OVERLAP, overlap); c.set_option(capi.OPT_GRAPH, graph); c.set_option(capi.OPT_PDL, pdl)
             c.reset(); c.integrate(mb)
             check_stats(c.frame_stats(), ost, mb)
@@ -473,6 +506,79 @@ def test_fuzzed_frames_match_oracle():
             check_stats(c.frame_stats(), ost, mb)
             assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(oacc[..., :3])), (name, w, h, mb, kw, wf, sample)
         c.destroy()
+
+
+@pytest.mark.parametrize("name,w,h,mb", [("CornellBox", 333, 127, 8), ("ShaderBalls", 480, 270, 6), ("CornellBox_Dragon", 200, 112, 12), ("CornellBox", 37, 5, 3)])
+def test_frame_kernel_matches_phase_kernels(name, w, h, mb):
+    """RT_OPT_FRAME_KERNEL 1 (one persistent kernel per frame, CTA-private queues) vs 0 (one kernel per phase): radiance,
+    counters and AOVs bit for bit, over three progressive samples, whole image and a 3-way scanline partition, with the BVH
+    staged in shared memory and fetched through L1."""
+    sc = scene(name); cam = default_camera(w, h)
+    for world in (1, 3):
+        for smem in (1, 0):
+            imgs = {}
+            for fk in (1, 0):
+                rad = np.zeros((h, w, 4), "<f4"); stats = []; aovs = []
+                for rank in range(world):
+                    c = capi.Context(w, h, rank=rank, world=world)
+                    c.set_option(capi.OPT_FRAME_KERNEL, fk); c.set_option(capi.OPT_SMEM_BVH, smem); c.set_option(capi.OPT_AOV_ALWAYS, 1)
+                    c.upload_scene(sc); c.set_camera(cam); c.reset()
+                    for _ in range(3):
+                        c.integrate(mb)
+                    c.read_radiance(rad)
+                    stats.append(c.frame_stats()); aovs.append(c.read_aovs())
+                    c.destroy()
+                imgs[fk] = (rad, stats, aovs)
+            assert np.array_equal(bits(imgs[1][0]), bits(imgs[0][0])), (world, smem)
+            for a, b in zip(imgs[1][1], imgs[0][1]):
+                for k in ("n_ext", "n_miss", "n_shadow", "n_cont", "n_unoccluded", "n_emissive_hits"):
+                    assert np.array_equal(a[k][: mb + 1], b[k][: mb + 1]), (k, world, smem)
+            for a, b in zip(imgs[1][2], imgs[0][2]):
+                for x, y in zip(a, b):
+                    assert np.array_equal(bits(np.asarray(x)), bits(np.asarray(y))), (world, smem)
+
+
+@pytest.mark.parametrize("name,w,h,mb", [("CornellBox", 203, 117, 6), ("ShaderBalls", 320, 180, 5)])
+def test_multi_device_context_matches_single_device(name, w, h, mb):
+    """rt_create_multi: ONE context over several devices (here the devices of the box, or device 0 listed three times when it has
+    only one: three partitions time-share it), every call fanned out inside the library.  Radiance, counters, resolved image
+    (parallel read-back and NVLink-gather presentation) and AOVs equal the single-device frame bit for bit."""
+    sc = scene(name); cam = default_camera(w, h)
+    n_dev = capi.device_count()
+    devices = list(range(n_dev)) if n_dev >= 2 else [0, 0, 0]
+    one = capi.Context(w, h); one.set_option(capi.OPT_AOV_ALWAYS, 1); one.upload_scene(sc); one.set_camera(cam); one.reset()
+    many = capi.Context(w, h, devices=devices); many.set_option(capi.OPT_AOV_ALWAYS, 1); many.upload_scene(sc); many.set_camera(cam); many.reset()
+    for sample in range(3):
+        one.integrate(mb); many.integrate(mb)
+    assert many.sample_count() == 3
+    a, b = one.frame_stats(), many.frame_stats()
+    for k in ("n_ext", "n_miss", "n_shadow", "n_cont", "n_unoccluded", "n_emissive_hits"):
+        assert np.array_equal(a[k][: mb + 1], b[k][: mb + 1]), k
+    assert np.array_equal(bits(one.read_radiance()), bits(many.read_radiance()))
+    want = one.resolve()
+    host = np.zeros((h, w, 4), "<f4"); capi.host_register(host)
+    try:
+        assert np.array_equal(bits(want), bits(many.resolve(host)))               # parallel read-back into a page-locked image
+        many.set_option(capi.OPT_PRESENT, 1)
+        host[:] = 0
+        assert np.array_equal(bits(want), bits(many.resolve(host)))               # gather to devices[0] (peer copies) + resolve there
+        many.set_option(capi.OPT_PRESENT, 0)
+        host[:] = 0
+        many.resolve_async(host); many.resolve_wait()
+        assert np.array_equal(bits(want), bits(host))
+    finally:
+        capi.host_unregister(host)
+    for x, y in zip(one.read_aovs(), many.read_aovs()):
+        assert np.array_equal(bits(x), bits(y))
+    # the stepwise per-virtual calls fan out too
+    one.reset(); many.reset()
+    one.integrate_stepwise(mb); many.integrate_stepwise(mb)
+    assert np.array_equal(bits(one.read_radiance()), bits(many.read_radiance()))
+    with pytest.raises(capi.RtError):
+        many.set_option(capi.OPT_DENOISER, 1)                # temporal reprojection needs the whole image on one device
+    with pytest.raises(capi.RtError):
+        many.stream_handle()                                 # single-device call
+    one.destroy(); many.destroy()
 
 
 def test_scene_reupload_and_camera_change_on_one_context():

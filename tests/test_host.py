@@ -145,7 +145,33 @@ def test_standalone_bvh_build_on_fixture_triangles():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("stepwise", [False, True], ids=["fused", "stepwise"])
+@pytest.mark.parametrize("schedule", ["frame", "fused", "stepwise"])
+def test_render_kcuda_over_several_devices_matches_oracle(tmp_path, schedule):
+    """Render(kCUDA, devices): ONE CUDAPathTraceIntegrator over several GPUs behind the unchanged Integrator interface (the
+    devices of the box, or device 0 listed twice when it has one) — Integrate() x3 in every schedule, resolved image against
+    the oracle.  "frame" is the deferred schedule: the virtuals only check their order and AdvanceSampleCount submits the frame."""
+    from raytracing_b200 import capi
+    w, h, mb = 180, 101, 5
+    env_path, _ = make_env(tmp_path, w=64, h=32)
+    s = hostapi.HostScene(PROC_OBJ)
+    s.add_directional_light((-0.6, -1.5, 3.5), (15, 10, 5))
+    n_dev = capi.device_count()
+    r = hostapi.HostRender(s, w, h, env_path, devices=list(range(n_dev)) if n_dev >= 2 else [0, 0], schedule=schedule)
+    r.set_max_bounces(mb)
+    a = s.arrays(); a["nodes"] = r.nodes()
+    o = Oracle(a)
+    cam = hostapi.default_camera(w, h)
+    acc = np.zeros((h, w, 4), dtype="<f4")
+    for sample in range(3):
+        r.render_frame()
+        acc, _, _ = o.render(cam, w, h, mb, sample_idx=sample, radiance=acc)
+        hdr = acc[..., :3] / np.float32(sample + 1)
+        assert np.array_equal(bits(r.image()[..., :3]), bits(hdr / (hdr + np.float32(1.0)))), (schedule, sample)
+    r.close(); s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stepwise", [False, True], ids=["frame", "stepwise"])
 def test_render_kcuda_backend_matches_oracle(tmp_path, stepwise):
     """The whole C++ host path — Scene(OBJ) -> Render(kCUDA) -> Bvh::BuildCPU -> Finalize -> CUDAPathTraceIntegrator
     -> UploadGPUData -> RenderFrame() x2 (Integrator::Integrate schedule) — against the oracle on the same arrays."""
