@@ -45,8 +45,21 @@ def load_workload_scene(name, w, h, copies=183):
     from raytracing_b200 import scene_io
     from raytracing_b200.camera import default_camera
     if name == "Synthetic10M":
+        import pickle
+        import tempfile
         from raytracing_b200 import synthetic
-        sc = synthetic.bistro_scale_scene(scene_io.load_scene("ShaderBalls"), copies, w, h)
+        # the scene (numpy replication + host BVH build, about a minute) is cached per box: several processes of one run reuse it
+        cache = os.path.join(tempfile.gettempdir(), f"rt_b200_synthetic_{copies}_{w}x{h}.pkl")
+        try:
+            sc = pickle.load(open(cache, "rb"))
+        except Exception:
+            sc = synthetic.bistro_scale_scene(scene_io.load_scene("ShaderBalls"), copies, w, h)
+            try:
+                tmp = cache + f".{os.getpid()}"
+                pickle.dump(sc, open(tmp, "wb"), protocol=4)
+                os.replace(tmp, cache)
+            except OSError:
+                pass
         return sc, sc["camera_pose"]
     return scene_io.load_scene(name), default_camera(w, h)
 
@@ -273,6 +286,7 @@ def main():
     ap.add_argument("--scene", default="CornellBox", choices=sorted(WORKLOADS))
     ap.add_argument("--stepwise", action="store_true", help="time the one-kernel-per-reference-step schedule instead of the fused one")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-host-e2e", action="store_true", help="skip the end-to-end leg through the C++ host classes (librt_host.so)")
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for the whole run (split over warm-up + steps)")
     ap.add_argument("--traversal", type=int, default=None, help="RT_OPT_TRAVERSAL override (0 literal reference-order traversal, 1 child-box layout)")
     ap.add_argument("--frame-kernel", type=int, default=2, help="RT_OPT_FRAME_KERNEL: 2 by partition size (default), 1 one persistent kernel per frame, 0 one kernel per phase")
@@ -433,7 +447,7 @@ def main():
             dist.all_reduce(cm, op=dist.ReduceOp.MAX)
             collective_ms = float(cm[0])
         n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-        fk_used = args.frame_kernel == 1 or (args.frame_kernel == 2 and n_local <= n_sms * 4096)
+        fk_used = args.frame_kernel == 1 or (args.frame_kernel == 2 and n_local <= n_sms * 7168)
         schedule = ("stepwise: one kernel per reference kernel" if args.stepwise else
                     ("one persistent kernel per frame, CTA-private wavefronts: T(b) [closest-hit trace(b) + shadow pass(b-1)] -> S(b) [shade hit/miss queues]" if fk_used else
                      "per-phase kernels: [closest-hit trace(b) + shadow pass(b-1)] -> hit/miss queues -> shade(b), one CUDA graph per frame"))
@@ -521,6 +535,38 @@ def main():
         dist.all_reduce(e2e_pipe_ms, op=dist.ReduceOp.MAX)
     e2e_pipe_value = rays_per_frame / (float(e2e_pipe_ms[0]) * 1e-3) / 1e6
 
+    # ---- the same end-to-end step through the C++ drop-in: librt_host.so's Render::RenderFrame() (SetCameraData + RequestReset +
+    # Integrate(), which ends with ResolveRadiance into Render's page-locked host image) on ALL N devices behind one
+    # CUDAPathTraceIntegrator (rt_create_multi: fan-out, partition and read-back inside the library, ONE caller thread).
+    # Rank 0 drives it; under torchrun the other ranks wait at the barrier (their contexts are idle).
+    host_e2e = None
+    barrier()
+    if rank == 0 and not args.no_host_e2e:
+        try:
+            from raytracing_b200 import hostapi
+            hs = hostapi.scene_from_arrays(scene)
+            hr = hostapi.HostRender.with_env_image(hs, w, h, scene["env"], scene["env_width"], scene["env_height"], list(range(world)), schedule="frame")
+            hr.set_max_bounces(mb); hr.set_camera(cam)
+            for _ in range(3):
+                hr.request_reset(); hr.render_frame()
+            reps = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    hr.set_camera(cam)                  # per-frame input (render.cpp:188); marks the camera as changed -> RequestReset -> frame restarts
+                    hr.render_frame()
+                reps.append((time.perf_counter() - t0) * 1e3 / e2e_steps)
+            hms = min(reps)
+            host_e2e = {"value": rays_per_frame / (hms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": hms, "repetitions_ms_per_step": [round(x, 4) for x in reps],
+                        "devices": world, "h2d_bytes_per_step": 64 * world, "d2h_bytes_per_step": w * h * 16,
+                        "api": "librt_host.so: rt_host::Render::RenderFrame() = CameraController data -> Integrator::SetCameraData, RequestReset, Integrator::Integrate() "
+                               "(15 virtuals of CUDAPathTraceIntegrator, whole-frame schedule: one rt_integrate per frame) ending in ResolveRadiance() into the page-locked "
+                               "host image; one thread, rt_create_multi over the N devices, parallel read-back; best of 2 repetitions"}
+            hr.close(); hs.close()
+        except Exception as e:          # noqa: BLE001
+            host_e2e = {"value": None, "error": repr(e)[:300]}
+    barrier()
+
     # ---- second north_star scene (BASELINE configs[4]): device-timed on the same N GPUs, reported under "secondary"
     secondary = None
     sec_name = args.secondary if args.secondary in WORKLOADS and args.secondary != args.scene else None
@@ -571,7 +617,8 @@ def main():
                     "gathered_api": "rank 0: rt_resolve_gathered(whole host image) after the NCCL gather (one PCIe link)" if e2e_gathered_ms else None,
                     "host_image_page_locked": (shared.pinned if shared is not None else True),
                     "pipelined_value": e2e_pipe_value, "pipelined_ms_per_step": float(e2e_pipe_ms[0]),
-                    "pipelined_api": "same, with rt_resolve_async: image D2H of frame i overlaps frame i+1"},
+                    "pipelined_api": "same, with rt_resolve_async: image D2H of frame i overlaps frame i+1",
+                    "host_cpp": host_e2e},
             "gpu_launches": int(launches),
             "roofline": roof,
             "collective_ms": R.collective_ms,

@@ -85,11 +85,14 @@ typedef enum RtOption {
     RT_OPT_FRAME_KERNEL = 26,   /* how rt_integrate runs a frame.  1: ONE persistent kernel in which every CTA is an independent
                                    wavefront over its own pixels (queue cursors in shared memory, no global atomics, no launch
                                    boundaries); 0: one kernel per phase (graph replay / PDL chain as configured above);
-                                   2 (default): the one-kernel frame for small partitions (<= 4096 pixels per SM, e.g. a 1/4 or
-                                   smaller share of a 1080p frame), per-phase kernels otherwise.  Results are bit-identical */
+                                   2 (default): the one-kernel frame for partitions of up to 7168 pixels per SM (half a 1080p
+                                   frame or less on a B200), per-phase kernels for larger ones.  Results are bit-identical */
     RT_OPT_PRESENT = 27,        /* multi-device contexts, rt_resolve: 0 (default) parallel read-back of every device's rows,
                                    1 gather to devices[0] over NVLink, resolve and read back there */
-    RT_OPT_FRAME_THREADS = 28   /* threads per CTA of the one-kernel frame: 0 (default) by partition size, else a multiple of 32 <= 1024 */
+    RT_OPT_FRAME_THREADS = 28,  /* threads per CTA of the one-kernel frame: 0 (default) by partition size, else a multiple of 32 <= 1024 */
+    RT_OPT_TOP_SMEM = 29        /* scenes whose traversal records do not fit shared memory: number of top-of-tree interior records
+                                   (breadth-first, 64 B each, <= 640 = 40 KB) that every traversal CTA stages with one TMA bulk copy;
+                                   0 (default) = none.  Results are bit-identical */
 } RtOption;
 
 #define RT_MAX_BOUNCES 255u     /* bounce index range supported per frame (reference GUI: 0..5) */

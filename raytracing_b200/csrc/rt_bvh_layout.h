@@ -19,6 +19,10 @@
  *             p1.xyz, e1.x | e1.yz, e2.xy | e2.z, end_of_leaf flag, 0, 0     (e1 = p2-p1, e2 = p3-p1,
  *           the two subtractions trace_bvh.cl:30-31 performs per test, done once here in the same
  *           IEEE arithmetic)
+ * Record ORDER: the first `top_n` interior records are the top of the tree in breadth-first order (root = record 0), the rest follow
+ * in the reference's depth-first order.  Any prefix of the array is therefore a connected top part of the tree, which is what
+ * lets a traversal kernel stage "the first k records" into shared memory with one TMA bulk copy (RT_OPT_TOP_SMEM) when the whole
+ * structure does not fit.  Record indices are internal (child references); primitive ids are untouched.
  * The visiting order of the traversal is unchanged (near child by ray sign of the split axis,
  * far child deferred), so hit results are identical to the reference order; see trace_fast().
  */
@@ -43,7 +47,12 @@ struct WideLayout
     std::vector<F4> tris;    // 3 per triangle
     int root_ref = 0;
     int max_depth = 0;
+    uint32_t top_n = 0;      // records [0, top_n) are the top of the tree in breadth-first order
 };
+
+#ifndef RT_BVH_TOP_RECORDS
+#define RT_BVH_TOP_RECORDS 1024u     // 64 KB of records: upper bound of what a kernel may stage (it stages a prefix)
+#endif
 
 inline float int_bits(int v) { float f; memcpy(&f, &v, 4); return f; }
 
@@ -91,6 +100,25 @@ inline bool build_layout(const RtLinearBVHNode* nodes, uint64_t n_nodes, const R
     // the reference kernel's private stack holds 64 entries (trace_bvh.cl:142)
     if (max_depth > 64) { err = "BVH deeper than the 64-entry traversal stack of trace_bvh.cl:142"; return false; }
     out.max_depth = max_depth;
+    {   // renumber: breadth-first for the first top_n interior nodes, depth-first (the order found above) for the others
+        const uint32_t top_n = (uint32_t)n_interior < RT_BVH_TOP_RECORDS ? (uint32_t)n_interior : RT_BVH_TOP_RECORDS;
+        std::vector<uint32_t> bfs;                     // binary node indices of interior nodes in BFS order (prefix only)
+        bfs.reserve(top_n);
+        if (n_interior > 0) bfs.push_back(0u);
+        for (size_t head = 0; head < bfs.size() && bfs.size() < top_n; ++head)
+        {
+            const RtLinearBVHNode& n = nodes[bfs[head]];
+            const uint32_t kids[2] = { bfs[head] + 1u, n.offset };
+            for (uint32_t k : kids)
+                if ((nodes[k].num_primitives_axis >> 16) == 0 && bfs.size() < top_n) bfs.push_back(k);
+        }
+        std::vector<uint8_t> in_top(n_nodes, 0);
+        for (uint32_t b : bfs) in_top[b] = 1;
+        int next = 0;
+        for (uint32_t b : bfs) wide_index[b] = next++;
+        for (uint32_t node : interior_order) if (!in_top[node]) wide_index[node] = next++;
+        out.top_n = (uint32_t)bfs.size();
+    }
 
     auto ref_of = [&](uint32_t child) -> int {
         const RtLinearBVHNode& c = nodes[child];

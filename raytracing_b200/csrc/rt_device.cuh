@@ -144,6 +144,8 @@ struct DevScene
     const float4* wnodes;          // 4 x float4 per interior node
     const float4* wtris;           // 3 x float4 per triangle: p1, e1, e2 (+ end-of-leaf flag)
     uint32_t wnodes_f4, wtris_f4;  // sizes of the two arrays in float4 (for the TMA staging of small scenes)
+    uint32_t top_n;                // interior records [0, top_n) are the top of the tree in breadth-first order
+    uint32_t top_k;                // of those, the records a kernel staged into shared memory (set per launch; 0 = none)
     int root_ref;
 };
 

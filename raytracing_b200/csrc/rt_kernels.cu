@@ -186,6 +186,31 @@ __device__ __forceinline__ void tma_stage_bvh(float4* dst, const DevScene& sc, u
                      : "=r"(done) : "r"(bar), "r"(0) : "memory");
 }
 
+// Scenes that do not fit: only the top of the tree — the first `n_records` interior records, breadth-first (rt_bvh_layout.h) — is
+// staged, with one TMA bulk copy per CTA; deeper records and all triangles stay behind L1/L2 (RT_OPT_TOP_SMEM).
+__device__ __forceinline__ void tma_stage_top(float4* dst, const float4* wnodes, uint32_t n_records, uint64_t* mbar)
+{
+    const uint32_t bar = smem_u32(mbar);
+    const uint32_t bytes = n_records * 64u;
+    if (threadIdx.x == 0)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst)), "l"(wnodes), "r"(bytes), "r"(bar) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(0) : "memory");
+}
+
 // Programmatic dependent launch (RT_OPT_PDL): a kernel launched with the programmatic-stream-serialization attribute may
 // start (launch its CTAs, stage the BVH) while the previous kernel of the stream is still draining; pdl_wait() blocks
 // until that kernel has completed and its memory is visible, and is a no-op for a normal launch.  Every persistent
@@ -194,7 +219,9 @@ __device__ __forceinline__ void tma_stage_bvh(float4* dst, const DevScene& sc, u
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-template <bool SMEM>
+// SMEM: 0 records behind L1/L2 (ld.global.nc), 1 all records in shared memory, 2 the first sc.top_k interior records in shared
+// memory and the rest in global memory (one generic load serves both)
+template <int SMEM>
 __device__ __forceinline__ float4 ld_bvh(const float4* p) { return SMEM ? *p : __ldg(p); }
 
 // ------------------------------------------------------------------------------------ traversal
@@ -274,7 +301,7 @@ __device__ __forceinline__ uint32_t trace_literal(const DevScene& sc, f3 o, f3 d
 // still match) take the literal path.
 // PIN: the whole-frame kernel shares its register budget with the shading code and ptxas then re-derives the sign bits on
 // every step and recomputes the determinant after its branch; an empty asm makes both values opaque (kept in registers).
-template <bool ANY, bool COUNT, bool SMEM, bool PIN = false>
+template <bool ANY, bool COUNT, int SMEM, bool PIN = false>
 __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4* wnodes, const float4* wtris, f3 o, f3 d, float t_min, float t_max,
                                                float& bu, float& bv, float& bt, uint32_t& nv, uint32_t& nt)
 {
@@ -293,9 +320,9 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
     // (measured, same results): with the records in shared memory the kernel is purely issue-bound and the packed
     // 64-bit stack entry + the sign-bit axis test win (CornellBox frame -2.7 %); with the records behind L1/L2 the two
     // 32-bit arrays (a discarded pop costs one load) and predicate selects are faster (ShaderBalls +1 %, Dragon +3.5 %).
-    int2 stack[SMEM ? 64 : 1];
-    int stack_ref[SMEM ? 1 : 64];
-    float stack_t[SMEM ? 1 : 64];
+    int2 stack[SMEM == 1 ? 64 : 1];
+    int stack_ref[SMEM == 1 ? 1 : 64];
+    float stack_t[SMEM == 1 ? 1 : 64];
     if (cur < 0)
     {   // single-leaf tree: the root box is tested like any visited node
         float4 r0 = __ldg(sc.nodes_ref), r1 = __ldg(sc.nodes_ref + 1);
@@ -316,7 +343,8 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
     {
         while (cur >= 0)
         {
-            const float4* np = wnodes + (size_t)cur * 4;
+            // SMEM == 2: `wnodes` is the staged top of the tree (records [0, sc.top_k)), deeper records come from sc.wnodes
+            const float4* np = (SMEM == 2 && (uint32_t)cur >= sc.top_k) ? sc.wnodes + (size_t)cur * 4 : wnodes + (size_t)cur * 4;
             float4 a = ld_bvh<SMEM>(np), b = ld_bvh<SMEM>(np + 1), c = ld_bvh<SMEM>(np + 2), m = ld_bvh<SMEM>(np + 3);
             // child 0 box: min (a.x,a.y,a.z) max (a.w,b.x,b.y); child 1 box: min (b.z,b.w,c.x) max (c.y,c.z,c.w)
             f3 t00 = (mk3(a.x, a.y, a.z) - o) * inv, t01 = (mk3(a.w, b.x, b.y) - o) * inv;
@@ -328,7 +356,7 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
             bool h0 = fminf(hi0, t_max) >= lo0, h1 = fminf(hi1, t_max) >= lo1;
             int r0 = __float_as_int(m.x), r1 = __float_as_int(m.y);
             uint32_t axis = __float_as_uint(m.z);
-            bool swap = SMEM ? ((sign_bits >> axis) & 1u) != 0u : (axis == 0 ? sx : (axis == 1 ? sy : sz));   // near child = second iff inv_dir[axis] < 0
+            bool swap = SMEM == 1 ? ((sign_bits >> axis) & 1u) != 0u : (axis == 0 ? sx : (axis == 1 ? sy : sz));   // near child = second iff inv_dir[axis] < 0
             int near_ref = swap ? r1 : r0, far_ref = swap ? r0 : r1;
             bool near_hit = swap ? h1 : h0, far_hit = swap ? h0 : h1;
             float far_lo = swap ? lo0 : lo1;
@@ -336,7 +364,7 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
             {
                 if (far_hit)
                 {
-                    if (SMEM) stack[sp] = make_int2(far_ref, __float_as_int(far_lo));
+                    if (SMEM == 1) stack[sp] = make_int2(far_ref, __float_as_int(far_lo));
                     else { stack_ref[sp] = far_ref; stack_t[sp] = far_lo; }
                     ++sp;
                 }
@@ -350,7 +378,7 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
                 while (sp > 0)
                 {
                     --sp;
-                    if (SMEM) { int2 e = stack[sp]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
+                    if (SMEM == 1) { int2 e = stack[sp]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
                     else if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; }
                 }
                 if (!found) return prim;
@@ -361,7 +389,7 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
         for (;;)
         {
             const float4* tp = wtris + (size_t)ti * 3;
-            float4 q0 = ld_bvh<SMEM>(tp), q1 = ld_bvh<SMEM>(tp + 1), q2 = ld_bvh<SMEM>(tp + 2);
+            float4 q0 = ld_bvh<(SMEM == 1)>(tp), q1 = ld_bvh<(SMEM == 1)>(tp + 1), q2 = ld_bvh<(SMEM == 1)>(tp + 2);
             f3 p1 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
             bool last = __float_as_uint(q2.y) != 0u;
             f3 pvec = cross(d, e2);
@@ -394,7 +422,7 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
         while (sp > 0)
                 {
                     --sp;
-                    if (SMEM) { int2 e = stack[sp]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
+                    if (SMEM == 1) { int2 e = stack[sp]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
                     else if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; }
                 }
         if (!found) return prim;
@@ -406,7 +434,7 @@ __device__ __forceinline__ uint32_t trace(const DevScene& sc, int mode, f3 o, f3
                                           float& bu, float& bv, float& bt, uint32_t& nv, uint32_t& nt)
 {
     if (mode == 0) return trace_literal<ANY, COUNT>(sc, o, d, t_min, t_max, bu, bv, bt, nv, nt);
-    return trace_fast<ANY, COUNT, false>(sc, sc.wnodes, sc.wtris, o, d, t_min, t_max, bu, bv, bt, nv, nt);
+    return trace_fast<ANY, COUNT, 0>(sc, sc.wnodes, sc.wtris, o, d, t_min, t_max, bu, bv, bt, nv, nt);
 }
 
 // ------------------------------------------------------------------------------------ shading
@@ -686,7 +714,7 @@ __global__ void __launch_bounds__(256) k_accumulate(FrameParams p, Queues q, Dev
 
 // Fused IntersectShadowRays + AccumulateDirectSamples: persistent warps drain the bounce's shadow-ray queue through a
 // global atomic cursor (work_shadow[bounce]), 32 consecutive rays per grab.
-template <bool COUNT, bool SMEM>
+template <bool COUNT, int SMEM>
 __device__ __forceinline__ void shadow_phase(const FrameParams& p, const DevScene& sc, int mode, const Queues& q, DevCounters* ctr, float4* radiance,
                                              uint32_t bounce, const float4* s_bvh)
 {
@@ -706,7 +734,8 @@ __device__ __forceinline__ void shadow_phase(const FrameParams& p, const DevScen
         {
             float4 a = q.sA[i], b = q.sB[i];
             float bu, bv, bt;
-            if (SMEM) un = trace_fast<true, false, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
+            if (SMEM == 1) un = trace_fast<true, false, 1>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
+            else if (SMEM == 2) un = trace_fast<true, false, 2>(sc, s_bvh, sc.wtris, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
             else un = trace<true, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
             if (un)
             {
@@ -724,12 +753,13 @@ __device__ __forceinline__ void shadow_phase(const FrameParams& p, const DevScen
     if (COUNT) { warp_sum64(&ctr->nodes_shadow[bounce], nv); warp_sum64(&ctr->tris_shadow[bounce], nt); }
 }
 
-template <bool COUNT, bool SMEM>
+template <bool COUNT, int SMEM>
 __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance, uint32_t bounce)
 {
     extern __shared__ __align__(128) float4 s_bvh[];
     __shared__ uint64_t s_mbar;
-    if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    if (SMEM == 1) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    if (SMEM == 2) tma_stage_top(s_bvh, sc.wnodes, sc.top_k, &s_mbar);
     pdl_wait(); pdl_launch_dependents();
     shadow_phase<COUNT, SMEM>(p, sc, mode, q, ctr, radiance, bounce, s_bvh);
 }
@@ -741,7 +771,7 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_shadow_accumulate(FrameP
 // warps of hits (Lambert/GGX + NEE) and full warps of misses (environment lookup) instead of warps that
 // mix the two and idle through each other's code.  Both kernels drain their queues through a global atomic
 // cursor, 32 entries per grab.
-template <bool COUNT, bool SMEM>
+template <bool COUNT, int SMEM>
 __device__ __forceinline__ void closest_phase(const FrameParams& p, const DevScene& sc, int mode, const Queues& q, DevCounters* ctr, uint32_t bounce,
                                               const float4* s_bvh)
 {
@@ -767,7 +797,8 @@ __device__ __forceinline__ void closest_phase(const FrameParams& p, const DevSce
             if (live)
             {
                 float4 a = q.A[in][i], b = q.B[in][i];
-                if (SMEM) prim = trace_fast<false, false, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
+                if (SMEM == 1) prim = trace_fast<false, false, 1>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
+                else if (SMEM == 2) prim = trace_fast<false, false, 2>(sc, s_bvh, sc.wtris, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
                 else prim = trace<false, COUNT>(sc, mode, mk3(a), mk3(b), 0.0f, b.w, bu, bv, bt, nv, nt);
                 hit = prim != RT_INVALID_ID;
             }
@@ -784,12 +815,13 @@ __device__ __forceinline__ void closest_phase(const FrameParams& p, const DevSce
     if (COUNT) { warp_sum64(&ctr->nodes_ext[bounce], nv); warp_sum64(&ctr->tris_ext[bounce], nt); }
 }
 
-template <bool COUNT, bool SMEM>
+template <bool COUNT, int SMEM>
 __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_closest(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, uint32_t bounce)
 {
     extern __shared__ __align__(128) float4 s_bvh[];
     __shared__ uint64_t s_mbar;
-    if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    if (SMEM == 1) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    if (SMEM == 2) tma_stage_top(s_bvh, sc.wnodes, sc.top_k, &s_mbar);
     pdl_wait(); pdl_launch_dependents();
     closest_phase<COUNT, SMEM>(p, sc, mode, q, ctr, bounce, s_bvh);
 }
@@ -798,13 +830,14 @@ __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_closest(FrameParam
 // default): the two are independent (the shadow pass only shares the radiance buffer with LATER shading passes), every
 // warp drains the extension queue and then the shadow queue, so the short shadow rays fill the tail of the long
 // extension rays without a second launch, a second staging of the BVH or cross-stream events.
-template <bool SMEM>
+template <int SMEM>
 __global__ void __launch_bounds__(256, RT_MINB_TRACE) k_trace_both(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance,
                                                                    uint32_t bounce, uint32_t shadow_bounce)
 {
     extern __shared__ __align__(128) float4 s_bvh[];
     __shared__ uint64_t s_mbar;
-    if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    if (SMEM == 1) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    if (SMEM == 2) tma_stage_top(s_bvh, sc.wnodes, sc.top_k, &s_mbar);
     pdl_wait(); pdl_launch_dependents();
     closest_phase<false, SMEM>(p, sc, mode, q, ctr, bounce, s_bvh);
     shadow_phase<false, SMEM>(p, sc, mode, q, ctr, radiance, shadow_bounce, s_bvh);
@@ -878,7 +911,7 @@ struct CtaFrame
     uint32_t n_emissive, n_unoccluded;
 };
 
-template <bool SMEM>
+template <int SMEM>
 __global__ void __launch_bounds__(RT_FRAME_MAX_THREADS, 1) k_frame(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance,
                                                               AovParams aov, uint32_t max_bounces, uint32_t slots_per_cta,
                                                               const __grid_constant__ FrameDyn dyn)
@@ -887,7 +920,8 @@ __global__ void __launch_bounds__(RT_FRAME_MAX_THREADS, 1) k_frame(FrameParams p
     __shared__ uint64_t s_mbar;
     __shared__ CtaFrame s;
     p.dyn = &dyn;                                  // per-frame constants (sample index, camera) arrive as a kernel parameter
-    if (SMEM) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    if (SMEM == 1) tma_stage_bvh(s_bvh, sc, &s_mbar);
+    if (SMEM == 2) tma_stage_top(s_bvh, sc.wnodes, sc.top_k, &s_mbar);
     const int lane = threadIdx.x & 31;
     const uint32_t base = blockIdx.x * slots_per_cta;          // this CTA's region of every queue: slots [base, base + slots_per_cta)
     // (queue pointers are re-read from the kernel parameters where they are used: nothing but `base` stays live across the
@@ -956,7 +990,8 @@ __global__ void __launch_bounds__(RT_FRAME_MAX_THREADS, 1) k_frame(FrameParams p
                     else if (live) { a = FQ(A[in], i); bb = FQ(B[in], i); }
                     if (live)
                     {
-                        if (SMEM) prim = trace_fast<false, false, true, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt);
+                        if (SMEM == 1) prim = trace_fast<false, false, 1, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt);
+                        else if (SMEM == 2) prim = trace_fast<false, false, 2, true>(sc, s_bvh, sc.wtris, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt);
                         else prim = trace<false, false>(sc, mode, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt);
                         hit = prim != RT_INVALID_ID;
                     }
@@ -978,7 +1013,8 @@ __global__ void __launch_bounds__(RT_FRAME_MAX_THREADS, 1) k_frame(FrameParams p
                     {
                         const float4 a = FQ(sA, i), bb = FQ(sB, i);
                         float bu, bv, bt;
-                        if (SMEM) un = trace_fast<true, false, true, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
+                        if (SMEM == 1) un = trace_fast<true, false, 1, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
+                        else if (SMEM == 2) un = trace_fast<true, false, 2, true>(sc, s_bvh, sc.wtris, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
                         else un = trace<true, false>(sc, mode, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
                         if (un)
                         {
@@ -1206,6 +1242,7 @@ struct rt_ctx
 
     // options
     int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 1, smem_bvh = 1;
+    uint32_t top_smem_records = 0;                 // RT_OPT_TOP_SMEM
 
     // per-pixel buffers
     Queues q = {};
@@ -1446,14 +1483,25 @@ cudaError_t launch_chain(rt_ctx* c, void (*kernel)(KArgs...), int grid, size_t s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-// Bytes of dynamic shared memory for the TMA-staged BVH, or 0 when staging does not apply: only the optimised
-// traversal (mode 1) on a scene whose records fit 40 KB (5 resident CTAs x 40 KB stay under the 227 KB of an SM).
-size_t smem_stage_bytes(const rt_ctx* c)
+// How a traversal kernel stages the BVH (TMA bulk copies into dynamic shared memory), decided per launch:
+//   mode 1  the whole structure (interior records + triangle records) when it fits 40 KB (5 resident CTAs x 40 KB stay under
+//           the 227 KB of an SM): CornellBox;
+//   mode 2  only the top of the tree — the first top_k interior records in breadth-first order (RT_OPT_TOP_SMEM records,
+//           default 0 = off, see DESIGN.md for the measurements) — when the structure does not fit;
+//   mode 0  nothing staged: literal traversal (RT_OPT_TRAVERSAL 0), RT_OPT_SMEM_BVH off.
+struct Stage { int mode; size_t bytes; uint32_t top_k; };
+Stage bvh_stage(const rt_ctx* c)
 {
-    if (!c->smem_bvh || c->traversal != 1) return 0;
+    Stage st = { 0, 0, 0 };
+    if (!c->smem_bvh || c->traversal != 1) return st;
     size_t bytes = ((size_t)c->scene.wnodes_f4 + c->scene.wtris_f4) * 16;
-    return bytes <= 40 * 1024 ? bytes : 0;
+    if (bytes <= 40 * 1024) { st.mode = 1; st.bytes = bytes; return st; }
+    uint32_t k = c->top_smem_records < c->scene.top_n ? c->top_smem_records : c->scene.top_n;
+    if (k >= 8) { st.mode = 2; st.bytes = (size_t)k * 64; st.top_k = k; }
+    return st;
 }
+size_t smem_stage_bytes(const rt_ctx* c) { return bvh_stage(c).bytes; }
+DevScene staged_scene(const rt_ctx* c, const Stage& st) { DevScene sc = c->scene; sc.top_k = st.top_k; return sc; }
 
 AovCam aov_cam(const RtCamera& cam);
 
@@ -1679,6 +1727,7 @@ int rt_upload_scene(rt_ctx* c, const RtSceneDesc* s)
         if ((rc = upload(wl.tris.data(), wl.tris.size() * 16, (const void**)&ds.wtris))) return rc;
         ds.root_ref = wl.root_ref;
         ds.wnodes_f4 = (uint32_t)wl.nodes.size(); ds.wtris_f4 = (uint32_t)wl.tris.size();
+        ds.top_n = wl.top_n; ds.top_k = 0;
     }
     c->scene_ready = true;
     ++c->config_gen;
@@ -1751,6 +1800,9 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
         if (value > 2) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "frame-kernel mode must be 0 (per-phase kernels), 1 (one kernel per frame) or 2 (by partition size)");
         c->frame_kernel = (int)value; return RT_OK;
     case RT_OPT_SMEM_BVH: c->smem_bvh = value != 0; return RT_OK;
+    case RT_OPT_TOP_SMEM:
+        if (value > 640u) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "at most 640 top-of-tree records (40 KB per CTA) can be staged");
+        c->top_smem_records = value; return RT_OK;
     case RT_OPT_OVERLAP:
     {
         if (value > 2) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "overlap mode must be 0, 1 or 2");
@@ -1924,18 +1976,22 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
     {   // this bounce's closest-hit traversal + the previous bounce's shadow pass in one kernel
         c->shadow_deferred = false;
         TimedLaunch t(c, RT_K_TRACE_BOTH);
-        size_t stage = smem_stage_bytes(c);
-        if (stage) launch_chain(c, k_trace_both<true>, RT_PGRID(c, k_trace_both<true>, stage), stage, c->stream, frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
-        else launch_chain(c, k_trace_both<false>, RT_PGRID(c, k_trace_both<false>, 0), 0, c->stream, frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
+        const Stage sg = bvh_stage(c);
+        const DevScene sc = staged_scene(c, sg);
+        if (sg.mode == 1) launch_chain(c, k_trace_both<1>, RT_PGRID(c, k_trace_both<1>, sg.bytes), sg.bytes, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
+        else if (sg.mode == 2) launch_chain(c, k_trace_both<2>, RT_PGRID(c, k_trace_both<2>, sg.bytes), sg.bytes, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
+        else launch_chain(c, k_trace_both<0>, RT_PGRID(c, k_trace_both<0>, 0), 0, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
         int rc = post_launch(c, "k_trace_both"); if (rc) return rc;
     }
     else
     {
         TimedLaunch t(c, RT_K_TRACE_CLOSEST);
-        size_t stage = smem_stage_bytes(c);
-        if (c->count_traversal) k_trace_closest<true, false><<<RT_PGRID(c, (k_trace_closest<true, false>), 0), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
-        else if (stage) launch_chain(c, k_trace_closest<false, true>, RT_PGRID(c, (k_trace_closest<false, true>), stage), stage, c->stream, frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
-        else launch_chain(c, k_trace_closest<false, false>, RT_PGRID(c, (k_trace_closest<false, false>), 0), 0, c->stream, frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
+        const Stage sg = bvh_stage(c);
+        const DevScene sc = staged_scene(c, sg);
+        if (c->count_traversal) k_trace_closest<true, 0><<<RT_PGRID(c, (k_trace_closest<true, 0>), 0), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
+        else if (sg.mode == 1) launch_chain(c, k_trace_closest<false, 1>, RT_PGRID(c, (k_trace_closest<false, 1>), sg.bytes), sg.bytes, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, bounce);
+        else if (sg.mode == 2) launch_chain(c, k_trace_closest<false, 2>, RT_PGRID(c, (k_trace_closest<false, 2>), sg.bytes), sg.bytes, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, bounce);
+        else launch_chain(c, k_trace_closest<false, 0>, RT_PGRID(c, (k_trace_closest<false, 0>), 0), 0, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, bounce);
         int rc = post_launch(c, "k_trace_closest"); if (rc) return rc;
     }
     { int rc = join_shadow(c); if (rc) return rc; }     // the shading pass accumulates into radiance and refills the shadow queue
@@ -1947,10 +2003,12 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
 static int launch_shadow_pass(rt_ctx* c, uint32_t bounce, cudaStream_t st)
 {
     TimedLaunch t(c, RT_K_SHADOW_ACCUMULATE, st);
-    size_t stage = smem_stage_bytes(c);
-    if (c->count_traversal) k_shadow_accumulate<true, false><<<RT_PGRID(c, (k_shadow_accumulate<true, false>), 0), 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-    else if (stage) k_shadow_accumulate<false, true><<<RT_PGRID(c, (k_shadow_accumulate<false, true>), stage), 256, stage, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-    else k_shadow_accumulate<false, false><<<RT_PGRID(c, (k_shadow_accumulate<false, false>), 0), 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    const Stage sg = bvh_stage(c);
+    const DevScene sc = staged_scene(c, sg);
+    if (c->count_traversal) k_shadow_accumulate<true, 0><<<RT_PGRID(c, (k_shadow_accumulate<true, 0>), 0), 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
+    else if (sg.mode == 1) k_shadow_accumulate<false, 1><<<RT_PGRID(c, (k_shadow_accumulate<false, 1>), sg.bytes), 256, sg.bytes, st>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce);
+    else if (sg.mode == 2) k_shadow_accumulate<false, 2><<<RT_PGRID(c, (k_shadow_accumulate<false, 2>), sg.bytes), 256, sg.bytes, st>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce);
+    else k_shadow_accumulate<false, 0><<<RT_PGRID(c, (k_shadow_accumulate<false, 0>), 0), 256, 0, st>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce);
     return post_launch(c, "k_shadow_accumulate");
 }
 
@@ -2048,23 +2106,30 @@ static int capture_frame_graph(rt_ctx* c, uint32_t max_bounces)
     return RT_OK;
 }
 
-// Which schedule rt_integrate runs.  Measured on B200 (profiles/r02_frame_kernel.txt): with ~4 or more 32-ray items per
-// resident warp and phase the per-phase kernels are faster (specialised register budgets: 5 CTAs/SM for traversal, and
-// every SM runs one kind of code at a time); below that the launch boundaries and kernel tails dominate and the one-kernel
-// frame wins (1.3x on a 1/8 partition of a 1080p frame).  RT_OPT_FRAME_KERNEL = 2 switches at 4096 pixels per SM.
+// Which schedule rt_integrate runs, and the CTA shape of the one-kernel frame.  Measured on B200 (profiles/r02_frame_kernel_ab.txt,
+// ms per frame of a 1/world partition of the 1080p frame, per-phase kernels vs k_frame at its best CTA size):
+//   CornellBox   world 1: 2.141 / 2.181   2: 1.157 / 1.134   4: 0.657 / 0.611   8: 0.419 / 0.350
+//   ShaderBalls  world 1: 3.985 / 4.041   2: 2.485 / 2.452   4: 1.768 / 1.571   8: 1.406 / 1.106
+//   Dragon 4K    world 1: 24.74 / 26.59                                         8: 4.273 / 4.102
+// With a whole frame per GPU the per-phase kernels win by 2-7 % (specialised register budgets — 5 CTAs/SM of 48 registers for
+// traversal — and one kind of code per SM at a time); from half a 1080p frame down the launch boundaries and kernel tails of
+// 20+ dependent launches cost more and the one-kernel frame wins (1.2-1.3x on a 1/8 partition).  RT_OPT_FRAME_KERNEL = 2
+// switches at 7168 pixels per SM (1.06 M pixels on 148 SMs).
 static bool frame_kernel_selected(const rt_ctx* c)
 {
-    if (c->frame_kernel == 2) return (size_t)c->n_local <= (size_t)c->num_sms * 4096u;
+    if (c->frame_kernel == 2) return (size_t)c->n_local <= (size_t)c->num_sms * 7168u;
     return c->frame_kernel == 1;
 }
 
-// CTA size of k_frame.  Measured (profiles/r02_frame_kernel.txt): one 1024-thread CTA per SM keeps all warps of an SM in the same
-// phase (one kind of code in the instruction caches) and is the fastest shape while every warp has several items per phase;
-// small partitions prefer 4 CTAs of 256 threads whose phases interleave.
+// CTA size of k_frame (same measurements).  One 1024-thread CTA per SM keeps all 32 warps of an SM in the same phase — one kind
+// of code in the instruction caches — and is the best shape when the BVH lives in shared memory (CornellBox, every partition
+// size) or every warp still has several items per phase; scenes traversed through L1/L2 on small partitions (<= 4096 pixels
+// per SM) prefer 4 CTAs of 256 threads per SM whose phases interleave (ShaderBalls, 1/8 partition: 1.106 vs 1.252 ms).
 static int frame_kernel_threads(const rt_ctx* c)
 {
     if (c->frame_threads) return c->frame_threads;
-    return (size_t)c->n_local > (size_t)c->num_sms * 2048u ? 1024 : 256;
+    if (bvh_stage(c).mode == 1) return 1024;
+    return (size_t)c->n_local > (size_t)c->num_sms * 4096u ? 1024 : 256;
 }
 
 // The whole frame as ONE persistent kernel (k_frame): a counter clear and a launch.
@@ -2074,8 +2139,10 @@ static int integrate_frame_kernel(rt_ctx* c, uint32_t max_bounces)
     if ((rc = join_shadow(c))) return rc;
     RT_CUDA(c, cudaSetDevice(c->device));
     RT_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(DevCounters), c->stream));
-    const size_t stage = smem_stage_bytes(c);
-    const void* kern = stage ? (const void*)k_frame<true> : (const void*)k_frame<false>;
+    const Stage sg = bvh_stage(c);
+    const DevScene sc = staged_scene(c, sg);
+    const size_t stage = sg.bytes;
+    const void* kern = sg.mode == 1 ? (const void*)k_frame<1> : (sg.mode == 2 ? (const void*)k_frame<2> : (const void*)k_frame<0>);
     const int threads = frame_kernel_threads(c);
     int per_sm = 0;
     for (auto& e : c->occupancy) if (e.kernel == kern && e.smem == stage + ((size_t)threads << 32)) { per_sm = e.per_sm; break; }
@@ -2094,8 +2161,9 @@ static int integrate_frame_kernel(rt_ctx* c, uint32_t max_bounces)
     const FrameDyn dyn = frame_dyn(c);
     {
         TimedLaunch t(c, RT_K_MISC);
-        if (stage) k_frame<true><<<grid, threads, stage, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
-        else k_frame<false><<<grid, threads, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
+        if (sg.mode == 1) k_frame<1><<<grid, threads, stage, c->stream>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
+        else if (sg.mode == 2) k_frame<2><<<grid, threads, stage, c->stream>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
+        else k_frame<0><<<grid, threads, 0, c->stream>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
     }
     if ((rc = post_launch(c, "k_frame"))) return rc;
     c->frame_started = true; c->cur_bounce = max_bounces;

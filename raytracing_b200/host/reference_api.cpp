@@ -68,8 +68,40 @@ struct MtlRecord
 {   // tinyobjloader defaults, tiny_obj_loader.h:1331-1340
     float diffuse[3] = { 0, 0, 0 }, specular[3] = { 0, 0, 0 }, transmittance[3] = { 0, 0, 0 }, emission[3] = { 0, 0, 0 };
     float ior = 1.0f, roughness = 0.0f, metallic = 0.0f;
-    bool has_texture = false;
+    // tinyobjloader's texture names (tiny_obj_loader.h: map_Kd, map_Ks, map_Pr, map_Pm, map_Ke, map_d)
+    std::string diffuse_tex, specular_tex, roughness_tex, metallic_tex, emissive_tex, alpha_tex;
 };
+
+// "map_Xx [-options ...] file name": the texture name is what follows the options (tinyobjloader parses -blendu, -o, -s, ... and
+// keeps the rest of the line); options with their numeric arguments are skipped here
+std::string texture_name(const char* p)
+{
+    std::string rest(p);
+    while (!rest.empty() && (rest.back() == '\r' || rest.back() == ' ' || rest.back() == '\t')) rest.pop_back();
+    size_t i = 0;
+    for (;;)
+    {
+        while (i < rest.size() && (rest[i] == ' ' || rest[i] == '\t')) ++i;
+        if (i < rest.size() && rest[i] == '-' && i + 1 < rest.size() && isalpha((unsigned char)rest[i + 1]))
+        {   // option: skip its name and the numeric / on / off arguments that follow
+            while (i < rest.size() && rest[i] != ' ' && rest[i] != '\t') ++i;
+            for (;;)
+            {
+                size_t j = i;
+                while (j < rest.size() && (rest[j] == ' ' || rest[j] == '\t')) ++j;
+                size_t k = j;
+                while (k < rest.size() && rest[k] != ' ' && rest[k] != '\t') ++k;
+                std::string tok = rest.substr(j, k - j);
+                char* end = nullptr;
+                bool numeric = !tok.empty() && (std::strtod(tok.c_str(), &end), end && *end == 0);
+                if (numeric || tok == "on" || tok == "off") i = k; else break;
+            }
+            continue;
+        }
+        break;
+    }
+    return rest.substr(i);
+}
 
 std::string dirname_of(const std::string& p)
 {
@@ -117,7 +149,12 @@ void parse_mtl(const std::string& path, std::vector<MtlRecord>& mats, std::map<s
         else if (key("Ni")) { const char* q = p + 2; cur->ior = parse_real(q); }
         else if (key("Pr")) { const char* q = p + 2; cur->roughness = parse_real(q); }
         else if (key("Pm")) { const char* q = p + 2; cur->metallic = parse_real(q); }
-        else if (strncmp(p, "map_", 4) == 0) cur->has_texture = true;
+        else if (key("map_Kd")) cur->diffuse_tex = texture_name(p + 6);
+        else if (key("map_Ks")) cur->specular_tex = texture_name(p + 6);
+        else if (key("map_Pr")) cur->roughness_tex = texture_name(p + 6);
+        else if (key("map_Pm")) cur->metallic_tex = texture_name(p + 6);
+        else if (key("map_Ke")) cur->emissive_tex = texture_name(p + 6);
+        else if (key("map_d")) cur->alpha_tex = texture_name(p + 5);
     }
 }
 
@@ -204,13 +241,19 @@ void Scene::Load(const char* filename, float scale, bool flip_yz)
     for (size_t i = 0; i < mtls.size(); ++i)
     {
         const MtlRecord& m = mtls[i];
-        if (m.has_texture) throw std::runtime_error("material uses image textures (map_*): not supported by this loader");
+        // scene.cpp:155-186: textures are loaded in this order (diffuse, specular, roughness, metallic, emissive, alpha), which fixes
+        // their indices
+        auto tex = [&](const std::string& name) -> std::uint32_t {
+            return name.empty() ? kInvalidTextureIndex : (std::uint32_t)LoadTexture(folder + "/" + name);
+        };
         PackedMaterial& o = materials_[i];
-        o.diffuse_albedo = PackAlbedo(std::pow(m.diffuse[0], kGamma), std::pow(m.diffuse[1], kGamma), std::pow(m.diffuse[2], kGamma), kInvalidTextureIndex);
-        o.specular_albedo = PackAlbedo(std::pow(m.specular[0], kGamma), std::pow(m.specular[1], kGamma), std::pow(m.specular[2], kGamma), kInvalidTextureIndex);
+        o.diffuse_albedo = PackAlbedo(std::pow(m.diffuse[0], kGamma), std::pow(m.diffuse[1], kGamma), std::pow(m.diffuse[2], kGamma), tex(m.diffuse_tex));
+        o.specular_albedo = PackAlbedo(std::pow(m.specular[0], kGamma), std::pow(m.specular[1], kGamma), std::pow(m.specular[2], kGamma), tex(m.specular_tex));
         o.emission = PackRGBE(m.emission[0], m.emission[1], m.emission[2]);
-        o.roughness_metalness = PackRoughnessMetalness(m.roughness, kInvalidTextureIndex, m.metallic, kInvalidTextureIndex);
-        o.ior_emission_idx_transparency = PackIorEmissionIdxTransparency(m.ior, kInvalidTextureIndex, m.transmittance[0], kInvalidTextureIndex);
+        const std::uint32_t rt = tex(m.roughness_tex), mt = tex(m.metallic_tex);
+        o.roughness_metalness = PackRoughnessMetalness(m.roughness, rt, m.metallic, mt);
+        const std::uint32_t et = tex(m.emissive_tex), at = tex(m.alpha_tex);
+        o.ior_emission_idx_transparency = PackIorEmissionIdxTransparency(m.ior, et, m.transmittance[0], at);
     }
 
     auto flip = [flip_yz](float3& v) { if (flip_yz) { float t = v.y; v.y = v.z; v.z = t; v.y = -v.y; } };
@@ -243,6 +286,23 @@ void Scene::CollectEmissiveTriangles()
     for (std::uint32_t i = 0; i < triangles_.size(); ++i)
         if (EmissionSum(materials_[triangles_[i].mtlIndex].emission) > 0.0f) emissive_indices_.push_back(i);
     scene_info_.emissive_count = (std::uint32_t)emissive_indices_.size();
+}
+
+// scene.cpp:276-323
+std::size_t Scene::LoadTexture(const std::string& filename)
+{
+    auto it = loaded_textures_.find(filename);
+    if (it != loaded_textures_.end()) return it->second;
+    TextureImage image; std::string why;
+    if (!LoadTextureImage(filename.c_str(), image, why)) throw std::runtime_error("Failed to load file " + filename + ": " + why);
+    if (textures_.size() >= 0xFF) throw std::runtime_error("more than 255 textures: the packed material format holds 8-bit texture indices (0xFF = none)");
+    Texture t; memset(&t, 0, sizeof(t));
+    t.width = (int)image.width; t.height = (int)image.height; t.data_start = (int)texture_data_.size();
+    std::size_t idx = textures_.size();
+    textures_.push_back(t);
+    texture_data_.insert(texture_data_.end(), image.data.begin(), image.data.end());
+    loaded_textures_.emplace(filename, idx);
+    return idx;
 }
 
 void Scene::AddPointLight(float3 origin, float3 radiance)

@@ -13,6 +13,7 @@
 #pragma once
 
 #include <cstdint>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -89,15 +90,23 @@ protected:
 
 // ---------------------------------------------------------------------------------------------------------------
 // Scene.  The OBJ/MTL reader is a small purpose-built parser (triangulated faces with v//vn or v/vt/vn indices, the MTL
-// keys the reference consumes: Kd Ks Ke Ni Tf Pr Pm map_*), with tinyobjloader's defaults for absent keys
-// (tiny_obj_loader.h:1331-1340).  Image textures (map_*) need an image decoder and are not supported by the loader
-// (none of the shipped scenes has one): loading such a material fails loudly.
+// keys the reference consumes: Kd Ks Ke Ni Tf Pr Pm map_Kd map_Ks map_Pr map_Pm map_Ke map_d), with tinyobjloader's defaults
+// for absent keys (tiny_obj_loader.h:1331-1340).  Image textures are decoded by image_loader.cpp (PNG, TGA; the reference goes
+// through stb_image, loaders/image_loader.cpp:30-63) into the reference's packed texel words; JPEG files fail loudly.
 // ---------------------------------------------------------------------------------------------------------------
 struct Image
 {
     std::uint32_t width = 0, height = 0;
     std::vector<float> data;      // RGBA32F
 };
+
+// 8-bit texture image as the reference stores it (loaders/image_loader.hpp: Image with uint32 texels r | g<<8 | b<<16 | a<<24)
+struct TextureImage
+{
+    std::uint32_t width = 0, height = 0;
+    std::vector<std::uint32_t> data;
+};
+bool LoadTextureImage(const char* filename, TextureImage& result, std::string& error);
 
 // Radiance .hdr reader with the reference's conversion (loaders/hdr_loader.cpp:29-120):
 // rows in file order, value = (mantissa / 256) * 2^(e - 128), alpha left 0.
@@ -132,6 +141,8 @@ public:
 private:
     void Load(const char* filename, float scale, bool flip_yz);
     void CollectEmissiveTriangles();
+    std::size_t LoadTexture(const std::string& filename);      // scene.cpp:276-323 (cached by file name)
+    std::map<std::string, std::size_t> loaded_textures_;
 
     std::vector<Triangle> triangles_;
     std::vector<std::uint32_t> emissive_indices_;

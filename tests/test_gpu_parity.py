@@ -538,6 +538,26 @@ def test_frame_kernel_matches_phase_kernels(name, w, h, mb):
                     assert np.array_equal(bits(np.asarray(x)), bits(np.asarray(y))), (world, smem)
 
 
+@pytest.mark.parametrize("name,w,h,mb", [("ShaderBalls", 320, 180, 6), ("CornellBox_Dragon", 240, 135, 10)])
+def test_top_of_tree_staging_is_bit_identical(name, w, h, mb):
+    """RT_OPT_TOP_SMEM: scenes whose records do not fit shared memory stage the first k interior records (breadth-first top of the
+    tree) with one TMA bulk copy per CTA; every k, in the per-phase kernels and in the one-kernel frame, gives the oracle's bits."""
+    sc = scene(name); cam = default_camera(w, h)
+    want, _, ost = Oracle(sc).render(cam, w, h, mb)
+    for k in (8, 100, 640):
+        for fk in (0, 1):
+            c = make_ctx(name, w, h)
+            c.set_option(capi.OPT_TOP_SMEM, k); c.set_option(capi.OPT_FRAME_KERNEL, fk)
+            c.reset(); c.integrate(mb)
+            check_stats(c.frame_stats(), ost, mb)
+            assert np.array_equal(bits(c.read_radiance()[..., :3]), bits(want[..., :3])), (k, fk)
+            c.destroy()
+    c = make_ctx(name, w, h)
+    with pytest.raises(capi.RtError):
+        c.set_option(capi.OPT_TOP_SMEM, 641)
+    c.destroy()
+
+
 @pytest.mark.parametrize("name,w,h,mb", [("CornellBox", 203, 117, 6), ("ShaderBalls", 320, 180, 5)])
 def test_multi_device_context_matches_single_device(name, w, h, mb):
     """rt_create_multi: ONE context over several devices (here the devices of the box, or device 0 listed three times when it has

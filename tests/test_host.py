@@ -108,6 +108,134 @@ def test_procedural_obj_loads_and_bvh_is_a_valid_tree():
     s.close()
 
 
+def _pack_like_stb(img):
+    """PIL image -> the reference's texel words the way LoadSTB builds them from stb_image's channel count
+    (image_loader.cpp:30-63): L -> (y,0,0,0), LA -> (y,a,0,0), RGB -> (r,g,b,0), RGBA -> (r,g,b,a); 16-bit -> high byte."""
+    a = np.asarray(img)
+    if a.dtype == np.uint16 or a.dtype == np.int32:
+        a = (a.astype(np.uint32) >> 8).astype(np.uint8)
+    if a.ndim == 2:
+        a = a[..., None]
+    c = a.shape[2]
+    w = a[..., 0].astype(np.uint32)
+    for k in range(1, c):
+        w |= a[..., k].astype(np.uint32) << (8 * k)
+    return w.reshape(-1)
+
+
+def _textured_obj(tmp_path, files):
+    """A quad (two triangles, uv 0..1) per texture file, one material each, every map_* key in use."""
+    keys = ["map_Kd", "map_Ks", "map_Pr", "map_Pm", "map_Ke", "map_d"]
+    with open(tmp_path / "tex.mtl", "w") as f:
+        for i, name in enumerate(files):
+            f.write(f"newmtl m{i}\nKd 0.5 0.5 0.5\nKs 0.5 0.5 0.5\nKe 0.2 0.2 0.2\nTf 1 1 1\nPr 0.5\n{keys[i % len(keys)]} -s 1 1 1 {name}\n")
+            if i == 0:
+                f.write(f"map_Ks {files[-1]}\n")               # the same file twice: cached, one texture
+    with open(tmp_path / "tex.obj", "w") as f:
+        f.write("mtllib tex.mtl\nvn 0 0 1\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\n")
+        for i in range(len(files)):
+            x = 1.5 * i
+            f.write(f"v {x} 0 0\nv {x + 1} 0 0\nv {x + 1} 1 0\nv {x} 1 0\nusemtl m{i}\n")
+            b = 4 * i
+            f.write(f"f {b + 1}/1/1 {b + 2}/2/1 {b + 3}/3/1\nf {b + 1}/1/1 {b + 3}/3/1 {b + 4}/4/1\n")
+    return str(tmp_path / "tex.obj")
+
+
+def test_image_textures_png_tga(tmp_path):
+    """map_* textures: PNG (grey 1/8/16 bit, grey+alpha, RGB, RGBA, palette with and without tRNS, every row
+    filter) and TGA (24/32 bit, grey, RLE, both row orders) decoded by host/image_loader.cpp into the reference's texel words,
+    checked against PIL's decode packed like LoadSTB; texture indices in the order scene.cpp:155-186 loads them; same file -> one
+    texture; JPEG fails loudly."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    imgs = {}
+
+    def rnd(shape, dtype=np.uint8, hi=256):
+        return rng.integers(0, hi, size=shape).astype(dtype)
+    imgs["rgb.png"] = Image.fromarray(rnd((13, 17, 3)), "RGB")
+    imgs["rgba.png"] = Image.fromarray(rnd((9, 31, 4)), "RGBA")
+    imgs["grey.png"] = Image.fromarray(rnd((7, 5)), "L")
+    imgs["la.png"] = Image.fromarray(rnd((6, 6, 2)), "LA")
+    imgs["grey16.png"] = Image.fromarray(rnd((5, 9), np.uint16, 65536))
+    imgs["bits1.png"] = Image.fromarray(rnd((11, 19), hi=2) * 255, "L").convert("1")
+    pal = Image.fromarray(rnd((10, 12), hi=16), "P"); pal.putpalette(list(rnd(48)))
+    imgs["pal.png"] = pal
+    imgs["rgb.tga"] = Image.fromarray(rnd((8, 14, 3)), "RGB")
+    imgs["rgba_rle.tga"] = Image.fromarray(np.repeat(rnd((6, 5, 4)), 4, axis=1), "RGBA")     # runs: RLE packets of both kinds
+    imgs["grey.tga"] = Image.fromarray(rnd((4, 7)), "L")
+    expect = {}
+    for name, im in imgs.items():
+        path = str(tmp_path / name)
+        if name == "rgba_rle.tga":
+            im.save(path, compression="tga_rle")
+        elif name == "rgb.tga":
+            im.save(path, orientation=1)             # top-left origin; the default writer stores bottom-up
+        else:
+            im.save(path)
+        back = Image.open(path)
+        if name == "bits1.png":
+            expect[name] = _pack_like_stb(back.convert("L"))
+        elif name == "pal.png":
+            expect[name] = _pack_like_stb(back.convert("RGB"))
+        else:
+            expect[name] = _pack_like_stb(back)
+    files = list(imgs)
+    s = hostapi.HostScene(_textured_obj(tmp_path, files))
+    s.add_directional_light((0, 0, 1), (1, 1, 1))
+    s.finalize(env=np.zeros(4, dtype=np.float32), env_width=1, env_height=1)
+    a = s.arrays()
+    # load order: material 0 loads its map_Kd (files[0]) then its map_Ks (files[-1]); the others follow, files[-1] is cached
+    order = [files[0], files[-1]] + files[1:-1]
+    assert len(a["textures"]) == len(files)
+    for idx, name in enumerate(order):
+        t = a["textures"][idx]
+        w, h = imgs[name].size
+        assert (t["width"], t["height"]) == (w, h), name
+        got = a["texels"][t["data_start"]: t["data_start"] + w * h]
+        assert np.array_equal(got, expect[name]), name
+    m = a["materials"]
+    tex_of = {name: i for i, name in enumerate(order)}
+    assert m["diffuse_albedo"][0] >> 24 == tex_of[files[0]] and m["specular_albedo"][0] >> 24 == tex_of[files[-1]]
+    assert (m["specular_albedo"][1] >> 24) == tex_of[files[1]]                       # material 1: map_Ks
+    assert ((m["roughness_metalness"][2] >> 8) & 0xFF) == tex_of[files[2]]           # material 2: map_Pr
+    assert (m["roughness_metalness"][3] >> 24) == tex_of[files[3]]                   # material 3: map_Pm
+    assert ((m["ior_emission_idx_transparency"][4] >> 8) & 0xFF) == tex_of[files[4]] # material 4: map_Ke
+    assert (m["ior_emission_idx_transparency"][5] >> 24) == tex_of[files[5]]         # material 5: map_d
+    assert (m["diffuse_albedo"][1] >> 24) == 0xFF                                    # no diffuse texture there
+    s.close()
+    Image.fromarray(rnd((4, 4, 3)), "RGB").save(str(tmp_path / "x.jpg"))
+    with pytest.raises(hostapi.HostError, match="JPEG"):
+        hostapi.HostScene(_textured_obj(tmp_path, ["x.jpg"]))
+
+
+@pytest.mark.gpu
+def test_textured_obj_renders_like_the_oracle(tmp_path):
+    """OBJ with image textures -> C++ Scene (image_loader.cpp) -> Render(kCUDA) -> the texture sampling path of the kernels
+    (material.h:251-264,319-369), against the oracle on the arrays the loader produced."""
+    from PIL import Image
+    rng = np.random.default_rng(8)
+    names = ["a.png", "b.tga", "c.png", "d.png", "e.tga", "f.png"]
+    for n in names:
+        Image.fromarray(rng.integers(0, 256, size=(16, 16, 4 if n != "c.png" else 3)).astype(np.uint8)).save(str(tmp_path / n))
+    env_path, _ = make_env(tmp_path, w=64, h=32)
+    w, h, mb = 160, 90, 4
+    s = hostapi.HostScene(_textured_obj(tmp_path, names))
+    s.add_directional_light((-0.3, -0.4, 1.0), (8, 8, 8))
+    r = hostapi.HostRender(s, w, h, env_path)
+    r.set_max_bounces(mb)
+    cam = hostapi.default_camera(w, h); cam["position"][:3] = (4.0, -2.5, 1.6)
+    r.set_camera(cam)
+    a = s.arrays(); a["nodes"] = r.nodes()
+    assert len(a["textures"]) == 6
+    o = Oracle(a)
+    r.render_frame()
+    acc, _, ost = o.render(cam, w, h, mb)
+    assert ost["n_ext"][1] > 500 and ost["n_shadow"][0] > 300           # the quads are in view and lit
+    expect = acc[..., :3] / (acc[..., :3] + np.float32(1.0))
+    assert np.array_equal(bits(r.image()[..., :3]), bits(expect))
+    r.close(); s.close()
+
+
 @pytest.mark.skipif(not os.path.isdir(REF_ASSETS), reason="reference assets only exist in the build container")
 @pytest.mark.parametrize("name", ["CornellBox", "ShaderBalls", "CornellBox_Dragon"])
 def test_loader_and_builder_reproduce_reference_dumps(name):

@@ -1,6 +1,6 @@
 """Same-box A/B of library variants (tools/build_variant.py): ms/frame of a 1/world partition for every library given.
-usage: ab_probe.py scene worlds lib[:fk[:threads]] ...   (lib = path, variant name or "cur" for the in-tree library; fk = RT_OPT_FRAME_KERNEL
-value, threads = RT_OPT_FRAME_THREADS value; default: the library's defaults)"""
+usage: ab_probe.py scene worlds lib[:fk[:threads[:top]]] ...   (lib = path, variant name or "cur" for the in-tree library; fk = RT_OPT_FRAME_KERNEL
+value, threads = RT_OPT_FRAME_THREADS value, top = RT_OPT_TOP_SMEM records; default: the library's defaults)"""
 import os, subprocess, sys
 HERE = os.path.dirname(os.path.abspath(__file__)); REPO = os.path.dirname(HERE)
 CHILD = r'''
@@ -8,9 +8,13 @@ import os, sys, torch
 sys.path.insert(0, %r)
 from raytracing_b200 import capi, scene_io
 from raytracing_b200.camera import default_camera
-name, worlds, fk, thr = sys.argv[1], [int(x) for x in sys.argv[2].split(",")], sys.argv[3], sys.argv[4]
+name, worlds, fk, thr, top = sys.argv[1], [int(x) for x in sys.argv[2].split(",")], sys.argv[3], sys.argv[4], sys.argv[5]
 w, h, mb = (3840, 2160, 16) if name == "CornellBox_Dragon" else (1920, 1080, 8)
-sc = scene_io.load_scene(name)
+if name == "Synthetic10M":
+    import bench
+    sc, _ = bench.load_workload_scene(name, w, h)          # cached per box
+else:
+    sc = scene_io.load_scene(name)
 out = []
 for world in worlds:
     ctx = capi.Context(w, h, device=0, rank=0, world=world)
@@ -18,7 +22,9 @@ for world in worlds:
         ctx.set_option(26, int(fk))
     if thr != "-":
         ctx.set_option(28, int(thr))
-    ctx.upload_scene(sc); ctx.set_camera(default_camera(w, h))
+    if top != "-":
+        ctx.set_option(29, int(top))
+    ctx.upload_scene(sc); ctx.set_camera(sc["camera_pose"] if "camera_pose" in sc else default_camera(w, h))
     stream = torch.cuda.ExternalStream(ctx.stream_handle())
     best = 1e9
     for rep in range(3):
@@ -39,8 +45,8 @@ print(" ".join(out))
 name, worlds = sys.argv[1], sys.argv[2]
 print(f"{name}: ms/frame (best of 3 x 20 frames) for world = {worlds}")
 for spec in sys.argv[3:]:
-    lib, fk, thr = (spec.split(":") + ["", ""])[:3]
+    lib, fk, thr, top = (spec.split(":") + ["", "", ""])[:4]
     path = lib if os.path.sep in lib else (os.path.join(REPO, "raytracing_b200", "librt_b200.so") if lib == "cur" else os.path.join(REPO, "raytracing_b200", "variants", f"librt_b200_{lib}.so"))
     env = dict(os.environ, RT_B200_LIB=path)
-    r = subprocess.run([sys.executable, "-c", CHILD, name, worlds, fk or "-", thr or "-"], capture_output=True, text=True, env=env)
+    r = subprocess.run([sys.executable, "-c", CHILD, name, worlds, fk or "-", thr or "-", top or "-"], capture_output=True, text=True, env=env)
     print(f"  {spec:24s} {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)
