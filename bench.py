@@ -172,7 +172,8 @@ def issue_roofline(name, world, ktimes, steps, sm_mhz, n_sms, peak_hbm, alg_of):
             inst, tinst, dram = c["inst_per_frame"] * scale, c["thread_inst_per_frame"] * scale, c["dram_bytes_per_frame"] * scale
             row.update({"issue_achieved_Ginst_s": inst / sec / 1e9, "issue_frac": inst / sec / issue_peak,
                         "lane_occupancy": tinst / (32.0 * inst), "hbm_achieved_GBs": dram / sec / 1e9, "hbm_frac": dram / sec / 1e9 / peak_hbm,
-                        "traffic_bytes_per_launch": dram / max(n / steps, 1), "warp_inst_per_frame": inst})
+                        "traffic_bytes_per_launch": dram / max(n / steps, 1), "warp_inst_per_frame": inst,
+                        "ncu_issue_active_pct": c.get("issue_active_pct"), "ncu_warps_active_pct": c.get("warps_active_pct")})
         rows[k] = row
     if not rows:
         return {"bound": None, "frac": None, "note": "no per-kernel times"}
@@ -183,7 +184,10 @@ def issue_roofline(name, world, ktimes, steps, sm_mhz, n_sms, peak_hbm, alg_of):
            "other_kernels": [v for k, v in rows.items() if k != dom]}
     if "issue_frac" in d:
         issue_bound = d["issue_frac"] >= d["hbm_frac"]
-        out.update({"bound": "issue" if issue_bound else "hbm",
+        # neither ceiling within a factor of two: the kernel waits — dependent L2/HBM fetches of the traversal and, for scenes with
+        # a long tail of ray lengths, resident warps that have run out of work while the slowest rays finish (ncu: warps active)
+        label = ("issue" if issue_bound else "hbm") if max(d["issue_frac"], d["hbm_frac"]) >= 0.5 else "latency"
+        out.update({"bound": label, "ncu_warps_active_pct": d.get("ncu_warps_active_pct"), "ncu_issue_active_pct": d.get("ncu_issue_active_pct"),
                     "achieved": d["issue_achieved_Ginst_s"] if issue_bound else d["hbm_achieved_GBs"],
                     "peak": issue_peak / 1e9 if issue_bound else peak_hbm,
                     "unit": "Gwarp-inst/s" if issue_bound else "GB/s",
