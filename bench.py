@@ -542,7 +542,8 @@ def main():
     # ---- the same end-to-end step through the C++ drop-in: librt_host.so's Render::RenderFrame() (SetCameraData + RequestReset +
     # Integrate(), which ends with ResolveRadiance into Render's page-locked host image) on ALL N devices behind one
     # CUDAPathTraceIntegrator (rt_create_multi: fan-out, partition and read-back inside the library, ONE caller thread).
-    # Rank 0 drives it; under torchrun the other ranks wait at the barrier (their contexts are idle).
+    # Rank 0 drives it; under torchrun the other ranks wait on the CPU (a key of the rendezvous store — an NCCL barrier would keep a
+    # spinning kernel on their GPUs, which rank 0's kernels would have to time-slice with).
     host_e2e = None
     barrier()
     if rank == 0 and not args.no_host_e2e:
@@ -569,6 +570,12 @@ def main():
             hr.close(); hs.close()
         except Exception as e:          # noqa: BLE001
             host_e2e = {"value": None, "error": repr(e)[:300]}
+    if world > 1:
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("rt_b200_host_leg_done", "1")
+        else:
+            store.wait(["rt_b200_host_leg_done"])
     barrier()
 
     # ---- second north_star scene (BASELINE configs[4]): device-timed on the same N GPUs, reported under "secondary"

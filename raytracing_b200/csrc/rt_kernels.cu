@@ -88,6 +88,9 @@ struct Queues
     uint32_t* shadow_flags;
     float4* hitq;
     uint32_t* missq;
+#ifdef RT_HITQ_CARRY
+    float4* hA; float4* hB; float4* hC;      // experiment: the hit queue carries its ray (coalesced reads in the shading kernel)
+#endif
 };
 
 // Per-frame constants that change from frame to frame (sample index, camera): kept in a small device buffer that a
@@ -320,9 +323,18 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
     // (measured, same results): with the records in shared memory the kernel is purely issue-bound and the packed
     // 64-bit stack entry + the sign-bit axis test win (CornellBox frame -2.7 %); with the records behind L1/L2 the two
     // 32-bit arrays (a discarded pop costs one load) and predicate selects are faster (ShaderBalls +1 %, Dragon +3.5 %).
-    int2 stack[SMEM == 1 ? 64 : 1];
-    int stack_ref[SMEM == 1 ? 1 : 64];
-    float stack_t[SMEM == 1 ? 1 : 64];
+#ifdef RT_SMEM_STACK
+    // experiment: the traversal stack in shared memory (entry i of thread t at [i * 256 + t]: conflict-free), per-phase kernels only
+    extern __shared__ __align__(128) float4 rt_dyn_smem[];
+    int2* const sstk = (int2*)((char*)rt_dyn_smem + sc.stack_off) + threadIdx.x;
+    constexpr bool SSTK = !PIN;
+#else
+    int2* const sstk = nullptr;
+    constexpr bool SSTK = false;
+#endif
+    int2 stack[(SMEM == 1 && !SSTK) ? 64 : 1];
+    int stack_ref[(SMEM == 1 || SSTK) ? 1 : 64];
+    float stack_t[(SMEM == 1 || SSTK) ? 1 : 64];
     if (cur < 0)
     {   // single-leaf tree: the root box is tested like any visited node
         float4 r0 = __ldg(sc.nodes_ref), r1 = __ldg(sc.nodes_ref + 1);
@@ -347,8 +359,17 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
             const float4* np = (SMEM == 2 && (uint32_t)cur >= sc.top_k) ? sc.wnodes + (size_t)cur * 4 : wnodes + (size_t)cur * 4;
             float4 a = ld_bvh<SMEM>(np), b = ld_bvh<SMEM>(np + 1), c = ld_bvh<SMEM>(np + 2), m = ld_bvh<SMEM>(np + 3);
             // child 0 box: min (a.x,a.y,a.z) max (a.w,b.x,b.y); child 1 box: min (b.z,b.w,c.x) max (c.y,c.z,c.w)
+#ifdef RT_FMA_TRAVERSAL
+            // experiment (NOT bit-exact): contracted slab test, plane * inv - origin * inv in one FFMA per plane
+            const f3 noi = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
+            f3 t00 = mk3(__fmaf_rn(a.x, inv.x, noi.x), __fmaf_rn(a.y, inv.y, noi.y), __fmaf_rn(a.z, inv.z, noi.z));
+            f3 t01 = mk3(__fmaf_rn(a.w, inv.x, noi.x), __fmaf_rn(b.x, inv.y, noi.y), __fmaf_rn(b.y, inv.z, noi.z));
+            f3 t10 = mk3(__fmaf_rn(b.z, inv.x, noi.x), __fmaf_rn(b.w, inv.y, noi.y), __fmaf_rn(c.x, inv.z, noi.z));
+            f3 t11 = mk3(__fmaf_rn(c.y, inv.x, noi.x), __fmaf_rn(c.z, inv.y, noi.y), __fmaf_rn(c.w, inv.z, noi.z));
+#else
             f3 t00 = (mk3(a.x, a.y, a.z) - o) * inv, t01 = (mk3(a.w, b.x, b.y) - o) * inv;
             f3 t10 = (mk3(b.z, b.w, c.x) - o) * inv, t11 = (mk3(c.y, c.z, c.w) - o) * inv;
+#endif
             float lo0 = fmaxf(fmaxf(fmaxf(fminf(t00.x, t01.x), fminf(t00.y, t01.y)), fminf(t00.z, t01.z)), t_min);
             float hi0 = fminf(fminf(fmaxf(t00.x, t01.x), fmaxf(t00.y, t01.y)), fmaxf(t00.z, t01.z));
             float lo1 = fmaxf(fmaxf(fmaxf(fminf(t10.x, t11.x), fminf(t10.y, t11.y)), fminf(t10.z, t11.z)), t_min);
@@ -364,7 +385,8 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
             {
                 if (far_hit)
                 {
-                    if (SMEM == 1) stack[sp] = make_int2(far_ref, __float_as_int(far_lo));
+                    if (SSTK) sstk[sp * 256] = make_int2(far_ref, __float_as_int(far_lo));
+                    else if (SMEM == 1) stack[sp] = make_int2(far_ref, __float_as_int(far_lo));
                     else { stack_ref[sp] = far_ref; stack_t[sp] = far_lo; }
                     ++sp;
                 }
@@ -378,7 +400,8 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
                 while (sp > 0)
                 {
                     --sp;
-                    if (SMEM == 1) { int2 e = stack[sp]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
+                    if (SSTK) { int2 e = sstk[sp * 256]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
+                    else if (SMEM == 1) { int2 e = stack[sp]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
                     else if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; }
                 }
                 if (!found) return prim;
@@ -392,21 +415,28 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
             float4 q0 = ld_bvh<(SMEM == 1)>(tp), q1 = ld_bvh<(SMEM == 1)>(tp + 1), q2 = ld_bvh<(SMEM == 1)>(tp + 2);
             f3 p1 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
             bool last = __float_as_uint(q2.y) != 0u;
-            f3 pvec = cross(d, e2);
-            float det = dot(e1, pvec);
+#ifdef RT_FMA_TRAVERSAL
+#define RT_CROSS(a, b) mk3(__fmaf_rn((a).y, (b).z, -((a).z * (b).y)), __fmaf_rn((a).z, (b).x, -((a).x * (b).z)), __fmaf_rn((a).x, (b).y, -((a).y * (b).x)))
+#define RT_DOT(a, b) __fmaf_rn((a).x, (b).x, __fmaf_rn((a).y, (b).y, (a).z * (b).z))
+#else
+#define RT_CROSS(a, b) cross(a, b)
+#define RT_DOT(a, b) dot(a, b)
+#endif
+            f3 pvec = RT_CROSS(d, e2);
+            float det = RT_DOT(e1, pvec);
             if (PIN) asm volatile("" : "+f"(det));
             if (!(det < 1e-8f || -det > 1e-8f))
             {
                 float inv_det = 1.0f / det;
                 f3 tvec = o - p1;
-                float u = dot(tvec, pvec) * inv_det;
+                float u = RT_DOT(tvec, pvec) * inv_det;
                 if (!(u < 0.0f || u > 1.0f))
                 {
-                    f3 qvec = cross(tvec, e1);
-                    float v = dot(d, qvec) * inv_det;
+                    f3 qvec = RT_CROSS(tvec, e1);
+                    float v = RT_DOT(d, qvec) * inv_det;
                     if (!(v < 0.0f || u + v > 1.0f))
                     {
-                        float t = dot(e2, qvec) * inv_det;
+                        float t = RT_DOT(e2, qvec) * inv_det;
                         if (!(t < t_min || t > t_max))
                         {
                             bu = u; bv = v; bt = t; prim = ti; t_max = t;
@@ -422,7 +452,8 @@ __device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4*
         while (sp > 0)
                 {
                     --sp;
-                    if (SMEM == 1) { int2 e = stack[sp]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
+                    if (SSTK) { int2 e = sstk[sp * 256]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
+                    else if (SMEM == 1) { int2 e = stack[sp]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
                     else if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; }
                 }
         if (!found) return prim;
@@ -808,7 +839,16 @@ __device__ __forceinline__ void closest_phase(const FrameParams& p, const DevSce
             if (lane == 0)
                 slot = atomicAdd((unsigned long long*)&ctr->hm[bounce], (unsigned long long)__popc(hmask) | ((unsigned long long)__popc(mmask) << 32));
             slot = __shfl_sync(0xffffffffu, slot, 0);
+#ifdef RT_HITQ_CARRY
+            if (hit)
+            {
+                const uint32_t k = (uint32_t)slot + __popc(hmask & lt_mask);
+                q.hitq[k] = make_float4(bu, bv, __uint_as_float(prim), __uint_as_float(i));
+                q.hA[k] = q.A[in][i]; q.hB[k] = q.B[in][i]; q.hC[k] = q.C[in][i];
+            }
+#else
             if (hit) q.hitq[(uint32_t)slot + __popc(hmask & lt_mask)] = make_float4(bu, bv, __uint_as_float(prim), __uint_as_float(i));
+#endif
             else if (live) q.missq[(uint32_t)(slot >> 32) + __popc(mmask & lt_mask)] = i;
         }
     }
@@ -869,8 +909,12 @@ __global__ void __launch_bounds__(256, RT_MINB_SHADE) k_shade_queues(FrameParams
             if (hit)
             {
                 float4 h = q.hitq[k];
+#ifdef RT_HITQ_CARRY
+                float4 a = q.hA[k], b = q.hB[k], c = q.hC[k];
+#else
                 uint32_t i = __float_as_uint(h.w);
                 float4 a = q.A[in][i], b = q.B[in][i], c = q.C[in][i];
+#endif
                 pixel = __float_as_uint(a.w);
                 shade_hit(sc, p, aov, bounce, pixel, mk3(a), mk3(b), mk3(c), __float_as_uint(h.z), h.x, h.y, so);
             }
@@ -1243,6 +1287,7 @@ struct rt_ctx
     // options
     int white_furnace = 0, sampler = 0, aov = 0, denoiser = 0, count_traversal = 0, kernel_timing = 0, traversal = 1, smem_bvh = 1;
     uint32_t top_smem_records = 0;                 // RT_OPT_TOP_SMEM
+    int bvh_depth = 0;
 
     // per-pixel buffers
     Queues q = {};
@@ -1377,6 +1422,9 @@ inline dim3 grid_for(uint32_t n, uint32_t block = 256) { uint32_t g = (n + block
 // buffer, the shadow queue or the counters again.
 int join_shadow(rt_ctx* c)
 {
+    // callers reach this before their own cudaSetDevice; with several devices in one process (rt_create_multi) the current device
+    // may be another context's
+    if (c->shadow_deferred || c->shadow_pending) RT_CUDA(c, cudaSetDevice(c->device));
     if (c->shadow_deferred)
     {   // nobody merged the deferred shadow pass into a traversal kernel: it runs on its own, in stream order
         c->shadow_deferred = false;
@@ -1432,7 +1480,7 @@ int alloc_frame_buffers(rt_ctx* c)
     c->local_rows = (c->height > c->rank) ? (c->height - c->rank + c->world - 1) / c->world : 0;
     c->n_local = c->local_rows * c->width;
     // k_frame gives every resident CTA its own region of each queue, rounded up to whole groups of 32 slots
-    size_t n = (size_t)c->n_local + 32u + (size_t)c->num_sms * 8u * 32u;
+    size_t n = (size_t)c->n_local + 32u + (size_t)c->num_sms * 32u * 32u;       // up to 32 resident CTAs per SM
     c->n_alloc = n;
     for (int i = 0; i < 2; ++i)
     {
@@ -1441,6 +1489,9 @@ int alloc_frame_buffers(rt_ctx* c)
     RT_CUDA(c, cudaMalloc(&c->q.sA, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.sB, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.sC, n * 16));
     RT_CUDA(c, cudaMalloc(&c->q.hits, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.shadow_flags, n * 4));
     RT_CUDA(c, cudaMalloc(&c->q.hitq, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.missq, n * 4));
+#ifdef RT_HITQ_CARRY
+    RT_CUDA(c, cudaMalloc(&c->q.hA, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.hB, n * 16)); RT_CUDA(c, cudaMalloc(&c->q.hC, n * 16));
+#endif
     RT_CUDA(c, cudaMalloc(&c->radiance, n * 16)); RT_CUDA(c, cudaMalloc(&c->resolved, n * 16));
     RT_CUDA(c, cudaMemsetAsync(c->radiance, 0, n * 16, c->stream));
     c->copy_pending[0] = c->copy_pending[1] = false;          // both streams were drained above
@@ -1501,7 +1552,15 @@ Stage bvh_stage(const rt_ctx* c)
     return st;
 }
 size_t smem_stage_bytes(const rt_ctx* c) { return bvh_stage(c).bytes; }
-DevScene staged_scene(const rt_ctx* c, const Stage& st) { DevScene sc = c->scene; sc.top_k = st.top_k; return sc; }
+DevScene staged_scene(const rt_ctx* c, const Stage& st) { DevScene sc = c->scene; sc.top_k = st.top_k; sc.stack_off = (uint32_t)((st.bytes + 127) & ~(size_t)127); return sc; }
+// kernels that ask for more than 48 KB of dynamic shared memory need the limit raised first
+void set_smem_limit(const void* kernel, size_t bytes) { if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
+#ifdef RT_SMEM_STACK
+// experiment: dynamic shared memory of the per-phase traversal kernels = staged BVH + one stack column per thread
+size_t with_stack(const rt_ctx* c, size_t stage) { return ((stage + 127) & ~(size_t)127) + (size_t)c->bvh_depth * 256 * 8; }
+#else
+size_t with_stack(const rt_ctx*, size_t stage) { return stage; }
+#endif
 
 AovCam aov_cam(const RtCamera& cam);
 
@@ -1727,7 +1786,8 @@ int rt_upload_scene(rt_ctx* c, const RtSceneDesc* s)
         if ((rc = upload(wl.tris.data(), wl.tris.size() * 16, (const void**)&ds.wtris))) return rc;
         ds.root_ref = wl.root_ref;
         ds.wnodes_f4 = (uint32_t)wl.nodes.size(); ds.wtris_f4 = (uint32_t)wl.tris.size();
-        ds.top_n = wl.top_n; ds.top_k = 0;
+        ds.top_n = wl.top_n; ds.top_k = 0; ds.stack_off = 0;
+        c->bvh_depth = wl.max_depth;
     }
     c->scene_ready = true;
     ++c->config_gen;
@@ -1978,9 +2038,11 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
         TimedLaunch t(c, RT_K_TRACE_BOTH);
         const Stage sg = bvh_stage(c);
         const DevScene sc = staged_scene(c, sg);
-        if (sg.mode == 1) launch_chain(c, k_trace_both<1>, RT_PGRID(c, k_trace_both<1>, sg.bytes), sg.bytes, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
-        else if (sg.mode == 2) launch_chain(c, k_trace_both<2>, RT_PGRID(c, k_trace_both<2>, sg.bytes), sg.bytes, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
-        else launch_chain(c, k_trace_both<0>, RT_PGRID(c, k_trace_both<0>, 0), 0, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
+        const size_t sm = with_stack(c, sg.bytes);
+        set_smem_limit((const void*)k_trace_both<0>, sm); set_smem_limit((const void*)k_trace_both<1>, sm); set_smem_limit((const void*)k_trace_both<2>, sm);
+        if (sg.mode == 1) launch_chain(c, k_trace_both<1>, RT_PGRID(c, k_trace_both<1>, sm), sm, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
+        else if (sg.mode == 2) launch_chain(c, k_trace_both<2>, RT_PGRID(c, k_trace_both<2>, sm), sm, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
+        else launch_chain(c, k_trace_both<0>, RT_PGRID(c, k_trace_both<0>, sm), sm, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce, c->shadow_deferred_bounce);
         int rc = post_launch(c, "k_trace_both"); if (rc) return rc;
     }
     else
@@ -1988,10 +2050,12 @@ int rt_extend_shade(rt_ctx* c, uint32_t bounce)
         TimedLaunch t(c, RT_K_TRACE_CLOSEST);
         const Stage sg = bvh_stage(c);
         const DevScene sc = staged_scene(c, sg);
+        const size_t sm = with_stack(c, sg.bytes);
+        set_smem_limit((const void*)k_trace_closest<false, 0>, sm); set_smem_limit((const void*)k_trace_closest<false, 1>, sm); set_smem_limit((const void*)k_trace_closest<false, 2>, sm);
         if (c->count_traversal) k_trace_closest<true, 0><<<RT_PGRID(c, (k_trace_closest<true, 0>), 0), 256, 0, c->stream>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, bounce);
-        else if (sg.mode == 1) launch_chain(c, k_trace_closest<false, 1>, RT_PGRID(c, (k_trace_closest<false, 1>), sg.bytes), sg.bytes, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, bounce);
-        else if (sg.mode == 2) launch_chain(c, k_trace_closest<false, 2>, RT_PGRID(c, (k_trace_closest<false, 2>), sg.bytes), sg.bytes, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, bounce);
-        else launch_chain(c, k_trace_closest<false, 0>, RT_PGRID(c, (k_trace_closest<false, 0>), 0), 0, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, bounce);
+        else if (sg.mode == 1) launch_chain(c, k_trace_closest<false, 1>, RT_PGRID(c, (k_trace_closest<false, 1>), sm), sm, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, bounce);
+        else if (sg.mode == 2) launch_chain(c, k_trace_closest<false, 2>, RT_PGRID(c, (k_trace_closest<false, 2>), sm), sm, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, bounce);
+        else launch_chain(c, k_trace_closest<false, 0>, RT_PGRID(c, (k_trace_closest<false, 0>), sm), sm, c->stream, frame_params(c), sc, c->traversal, c->q, c->counters, bounce);
         int rc = post_launch(c, "k_trace_closest"); if (rc) return rc;
     }
     { int rc = join_shadow(c); if (rc) return rc; }     // the shading pass accumulates into radiance and refills the shadow queue
@@ -2005,10 +2069,12 @@ static int launch_shadow_pass(rt_ctx* c, uint32_t bounce, cudaStream_t st)
     TimedLaunch t(c, RT_K_SHADOW_ACCUMULATE, st);
     const Stage sg = bvh_stage(c);
     const DevScene sc = staged_scene(c, sg);
+    const size_t sm = with_stack(c, sg.bytes);
+    set_smem_limit((const void*)k_shadow_accumulate<false, 0>, sm); set_smem_limit((const void*)k_shadow_accumulate<false, 1>, sm); set_smem_limit((const void*)k_shadow_accumulate<false, 2>, sm);
     if (c->count_traversal) k_shadow_accumulate<true, 0><<<RT_PGRID(c, (k_shadow_accumulate<true, 0>), 0), 256, 0, st>>>(frame_params(c), c->scene, c->traversal, c->q, c->counters, c->radiance, bounce);
-    else if (sg.mode == 1) k_shadow_accumulate<false, 1><<<RT_PGRID(c, (k_shadow_accumulate<false, 1>), sg.bytes), 256, sg.bytes, st>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce);
-    else if (sg.mode == 2) k_shadow_accumulate<false, 2><<<RT_PGRID(c, (k_shadow_accumulate<false, 2>), sg.bytes), 256, sg.bytes, st>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce);
-    else k_shadow_accumulate<false, 0><<<RT_PGRID(c, (k_shadow_accumulate<false, 0>), 0), 256, 0, st>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce);
+    else if (sg.mode == 1) k_shadow_accumulate<false, 1><<<RT_PGRID(c, (k_shadow_accumulate<false, 1>), sm), 256, sm, st>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce);
+    else if (sg.mode == 2) k_shadow_accumulate<false, 2><<<RT_PGRID(c, (k_shadow_accumulate<false, 2>), sm), 256, sm, st>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce);
+    else k_shadow_accumulate<false, 0><<<RT_PGRID(c, (k_shadow_accumulate<false, 0>), sm), 256, sm, st>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, bounce);
     return post_launch(c, "k_shadow_accumulate");
 }
 
@@ -2149,7 +2215,7 @@ static int integrate_frame_kernel(rt_ctx* c, uint32_t max_bounces)
     if (!per_sm)
     {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, stage) != cudaSuccess || per_sm < 1) per_sm = 1;
-        if (per_sm > 8) per_sm = 8;
+        if (per_sm > 32) per_sm = 32;
         c->occupancy.push_back({ kern, stage + ((size_t)threads << 32), per_sm });
     }
     const uint32_t n_groups = (c->n_local + 31u) / 32u;
