@@ -189,13 +189,15 @@ def test_fuzzed_frames_bit_exact_vs_reference_kernels(cfg):
     r.close()
 
 
-def test_math_library_sensitivity_is_small():
+@pytest.mark.parametrize("name,w,h,mb,limit", [("CornellBox", 160, 90, 8, 0.02), ("ShaderBalls", 160, 90, 8, 0.02), ("CornellBox_Dragon", 160, 90, 16, 0.04)])
+def test_math_library_sensitivity_is_small(name, w, h, mb, limit):
     """The OpenCL driver's libm is unpinned.  Swapping include/rt_math.h for glibc's libm inside the
-    reference kernels must leave all but a small fraction of pixels within 1e-4 relative."""
+    reference kernels must leave all but a small fraction of pixels within 1e-4 relative — on all three shipped scenes (the
+    mirror / metal paths of the Dragon scene at 16 bounces are the most sensitive).  include/rt_math.h itself is pinned against
+    double-precision libm in tests/test_rt_math.py."""
     if not refbind.available(libm=True):
         pytest.skip("libref_libm.so not built")
-    sc = scene("ShaderBalls")
-    w, h, mb = 160, 90, 8
+    sc = scene(name)
     cam = default_camera(w, h)
     imgs = []
     for libm in (False, True):
@@ -205,4 +207,4 @@ def test_math_library_sensitivity_is_small():
     a, b = imgs
     rel = np.abs(a - b) / np.maximum(np.abs(a), 1e-6)
     frac_bad = (rel.max(axis=-1) > 1e-4).mean()
-    assert frac_bad < 0.02, frac_bad
+    assert frac_bad < limit, frac_bad
