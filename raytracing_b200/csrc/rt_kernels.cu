@@ -1326,6 +1326,7 @@ struct rt_ctx
     FrameDyn* d_dyn = nullptr;
     bool pdl = true;               // RT_OPT_PDL
     int frame_kernel = 2;          // RT_OPT_FRAME_KERNEL: 1 rt_integrate launches ONE persistent kernel per frame (k_frame), 0 one kernel per phase, 2 by partition size
+    int grid_div = 1;              // contexts that share this device (rt_create_multi lists a device k times): each launches 1/k of the resident CTAs
     int frame_threads = 0;         // RT_OPT_FRAME_THREADS: threads per CTA of k_frame (0 = by partition size)
     size_t n_alloc = 0;            // entries of every per-pixel queue: n_local + one group of 32 per CTA that can be resident (k_frame's regions)
     int* d_bn = nullptr;           // sobol | scrambling | ranking (rt_upload_sampler_tables)
@@ -1511,7 +1512,8 @@ int persistent_grid(rt_ctx* c, const void* kernel, size_t dyn_smem)
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         c->occupancy.push_back({ kernel, dyn_smem, per_sm });
     }
-    int g = c->num_sms * per_sm;
+    int g = c->num_sms * per_sm / c->grid_div;
+    if (g < c->num_sms) g = c->num_sms;
     int need = (int)((c->n_local + 255u) / 256u);
     if (need < 1) need = 1;
     return g < need ? g : need;
@@ -2219,7 +2221,8 @@ static int integrate_frame_kernel(rt_ctx* c, uint32_t max_bounces)
         c->occupancy.push_back({ kern, stage + ((size_t)threads << 32), per_sm });
     }
     const uint32_t n_groups = (c->n_local + 31u) / 32u;
-    uint32_t grid = (uint32_t)(c->num_sms * per_sm);
+    uint32_t grid = (uint32_t)(c->num_sms * per_sm / c->grid_div);
+    if (grid < (uint32_t)c->num_sms) grid = (uint32_t)c->num_sms;
     if (grid > n_groups) grid = n_groups;
     if (grid < 1) grid = 1;
     const uint32_t slots_per_cta = ((n_groups + grid - 1u) / grid) * 32u;
@@ -2619,6 +2622,13 @@ int rt_create_multi(uint32_t width, uint32_t height, const int* devices, uint32_
         if (rc == RT_OK) { rc = rt_set_partition(k, i, n_devices); if (rc != RT_OK) { g_create_error = k->error; rt_destroy(k); } }
         if (rc != RT_OK) { for (rt_ctx* o : g->children) rt_destroy(o); delete g; return rc; }
         g->children.push_back(k);
+    }
+    // contexts that time-share one device split its resident CTA slots, so that their persistent kernels run side by side
+    for (rt_ctx* k : g->children)
+    {
+        int same = 0;
+        for (rt_ctx* o : g->children) same += o->device == k->device;
+        k->grid_div = same;
     }
     // peer access towards the first device for the NVLink gather (ignored where it is already on / not available:
     // cudaMemcpyPeerAsync then stages through the host)
