@@ -185,6 +185,21 @@ int rt_gather_radiance(rt_ctx* ctx);
 int rt_host_register(void* ptr, uint64_t bytes);
 int rt_host_unregister(void* ptr);
 
+/* Fused gather over peer memory — the frame's one collective done by the frame kernel itself (new capability).  The presenting
+ * rank allocates a buffer of `world` slabs (stride = rows_max * width * 16 bytes, the layout rt_resolve_gathered reads) followed
+ * by one completion flag per rank (rt_gather_buffer); every rank points its context at it (rt_set_gather_target: the owner with
+ * its own pointer, ranks in other processes with the mapping rt_ipc_open returns for the 64-byte handle of rt_ipc_export, contexts
+ * of a multi-device context through peer access — RT_OPT_PRESENT 1 does all of this).  From then on rt_integrate also delivers the
+ * frame: the one-kernel frame stores a pixel's radiance into its rank's slab over NVLink the moment the pixel's path ends (the
+ * transfer is spread over the frame), the per-phase schedule copies its slab at the end; then the rank's flag is set to its frame
+ * number.  rt_gather_wait on the presenting context makes its stream wait for all flags; rt_resolve_gathered(buffer, stride)
+ * presents. */
+int rt_gather_buffer(rt_ctx* ctx, void** dev_ptr, uint64_t* stride_bytes, uint64_t* total_bytes);
+int rt_ipc_export(const void* dev_ptr, void* handle64);
+int rt_ipc_open(rt_ctx* ctx, const void* handle64, void** dev_ptr);
+int rt_set_gather_target(rt_ctx* ctx, void* base, uint64_t stride_bytes);
+int rt_gather_wait(rt_ctx* ctx);
+
 /* Parity tap for include/rt_math.h (the elementary functions shared with the oracle): out[i] = f(a[i], b[i]) evaluated on
  * `device`; host pointers, blocking.  fn: 0 sin, 1 cos, 2 tan, 3 atan2(a, b), 4 acos, 5 pow(a, b), 6 fmin, 7 fmax,
  * 8 1 / sqrt(a), 9 a / b. */

@@ -31,7 +31,8 @@ SYMBOLS = ["rt_create", "rt_destroy", "rt_last_error", "rt_set_partition", "rt_u
            "rt_integrate", "rt_sync", "rt_read_hits", "rt_read_rays", "rt_read_radiance", "rt_read_frame_stats",
            "rt_read_sample_count", "rt_read_aovs", "rt_kernel_times", "rt_launch_count", "rt_local_pixel_count",
            "rt_radiance_device_ptr", "rt_stream_handle",
-           "rt_create_multi", "rt_device_count", "rt_gather_radiance", "rt_host_register", "rt_host_unregister", "rt_math_eval"]
+           "rt_create_multi", "rt_device_count", "rt_gather_radiance", "rt_host_register", "rt_host_unregister", "rt_math_eval",
+           "rt_gather_buffer", "rt_ipc_export", "rt_ipc_open", "rt_set_gather_target", "rt_gather_wait"]
 
 
 class RtSceneDesc(C.Structure):
@@ -104,6 +105,11 @@ def load_library():
     L.rt_host_register.argtypes = [C.c_void_p, C.c_uint64]
     L.rt_host_unregister.argtypes = [C.c_void_p]
     L.rt_math_eval.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.rt_gather_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.rt_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.rt_ipc_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.rt_set_gather_target.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.rt_gather_wait.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -134,6 +140,25 @@ class Context:
 
     def gather_radiance(self):
         self._ck(self.lib.rt_gather_radiance(self.h))
+
+    # ---- fused gather over peer memory (rt_gather_buffer .. rt_gather_wait)
+    def gather_buffer(self):
+        """-> (device pointer, slab stride in bytes, total bytes) of the gathered-radiance buffer this context owns."""
+        p, st, tot = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.rt_gather_buffer(self.h, C.byref(p), C.byref(st), C.byref(tot)))
+        return p.value, st.value, tot.value
+
+    def ipc_open(self, handle: bytes):
+        buf = C.create_string_buffer(bytes(handle), 64)
+        p = C.c_void_p()
+        self._ck(self.lib.rt_ipc_open(self.h, buf, C.byref(p)))
+        return p.value
+
+    def set_gather_target(self, base, stride_bytes=0):
+        self._ck(self.lib.rt_set_gather_target(self.h, C.c_void_p(base) if base else None, stride_bytes))
+
+    def gather_wait(self):
+        self._ck(self.lib.rt_gather_wait(self.h))
 
     def _ck(self, rc):
         if rc != 0:
@@ -340,3 +365,12 @@ def math_eval(fn: str, a, b=None, device: int = 0):
     if rc != 0:
         raise RtError(rc, load_library().rt_last_error(None).decode())
     return out
+
+
+def ipc_export(dev_ptr: int) -> bytes:
+    """64-byte CUDA IPC handle of a device allocation (rt_ipc_export)."""
+    buf = C.create_string_buffer(64)
+    rc = load_library().rt_ipc_export(C.c_void_p(dev_ptr), buf)
+    if rc != 0:
+        raise RtError(rc, load_library().rt_last_error(None).decode())
+    return buf.raw

@@ -104,6 +104,8 @@ struct FrameParams
     int white_furnace;
     const int* bn;                 // blue-noise sampler tables (kBlueNoise) or nullptr (kRandom)
     const FrameDyn* dyn;
+    float4* gather;                // k_frame only: this rank's slab of the gathered radiance on the presenting device (peer memory,
+                                   // rt_set_gather_target) — a pixel's radiance is pushed there the moment its path ends; else nullptr
 };
 
 // AOV outputs of bounce 0 (kernels/cl/aov.cl:44-110), written by the bounce-0 shading pass when enabled
@@ -486,6 +488,7 @@ __device__ __forceinline__ void shade_miss(const DevScene& sc, const FrameParams
     float4 r = radiance[li];
     r.x += add.x; r.y += add.y; r.z += add.z;
     radiance[li] = r;
+    if (p.gather) p.gather[li] = r;        // the path ends here: its pixel is final (its last shadow ray was accumulated a phase ago)
 }
 
 // kernels/cl/hit_surface.cl:30-186
@@ -953,6 +956,7 @@ struct CtaFrame
     unsigned long long hm[2];                // hits (low word) and misses (high word) of T(b), parity b & 1
     unsigned long long emit[2];              // shadow rays (low word) and continuation rays (high word) spawned by S(b): slot reservation
     uint32_t n_emissive, n_unoccluded;
+    uint32_t ended_n[2];                     // fused gather: pixels whose path ended at a hit in S(b) (no continuation), parity b & 1
 };
 
 template <int SMEM>
@@ -977,7 +981,7 @@ __global__ void __launch_bounds__(RT_FRAME_MAX_THREADS, 1) k_frame(FrameParams p
         const uint32_t cta = blockIdx.x, n_cta = gridDim.x;
         const uint32_t my_groups = cta < n_groups ? (n_groups - cta + n_cta - 1u) / n_cta : 0u;
         s.cur_trace = 0; s.cur_shade = 0; s.ext_n[0] = my_groups * 32u; s.ext_n[1] = 0; s.shadow_n[0] = s.shadow_n[1] = 0;
-        s.hm[0] = s.hm[1] = 0ull; s.emit[0] = s.emit[1] = 0ull; s.n_emissive = 0; s.n_unoccluded = 0;
+        s.hm[0] = s.hm[1] = 0ull; s.emit[0] = s.emit[1] = 0ull; s.n_emissive = 0; s.n_unoccluded = 0; s.ended_n[0] = s.ended_n[1] = 0;
         if (blockIdx.x == 0) ctr->n_primary = p.n_local;
     }
     __syncthreads();
@@ -995,7 +999,7 @@ __global__ void __launch_bounds__(RT_FRAME_MAX_THREADS, 1) k_frame(FrameParams p
             const uint32_t total = ext_span + n_sh;
             if (threadIdx.x == 0)
             {   // state of the NEXT phases that nobody reads during this one
-                s.cur_shade = 0; s.ext_n[(b + 1u) & 1] = 0; s.shadow_n[in] = 0; s.emit[in] = 0ull;
+                s.cur_shade = 0; s.ext_n[(b + 1u) & 1] = 0; s.shadow_n[in] = 0; s.emit[in] = 0ull; s.ended_n[in] = 0;
             }
             for (;;)
             {
@@ -1074,6 +1078,23 @@ __global__ void __launch_bounds__(RT_FRAME_MAX_THREADS, 1) k_frame(FrameParams p
                 }
             }
             __syncthreads();
+            if (p.gather && b > 0)
+            {   // fused gather: the shadow rays of bounce b-1 are accumulated, so the pixels whose path ended at a hit of S(b-1) are
+                // final; after the last round so are the paths that were still alive (their rays sit in the queue S(max) filled)
+                const int pin = (b - 1u) & 1;
+                const uint32_t n_end = s.ended_n[pin];
+                const uint32_t* list = pin ? (const uint32_t*)q.hits + base : q.shadow_flags + base;
+                for (uint32_t k = threadIdx.x; k < n_end; k += blockDim.x) { const uint32_t li = list[k]; p.gather[li] = radiance[li]; }
+                if (b > max_bounces)
+                {
+                    const uint32_t n_alive = s.ext_n[in];
+                    for (uint32_t k = threadIdx.x; k < n_alive; k += blockDim.x)
+                    {
+                        const uint32_t li = local_index(p, __float_as_uint(FQ(A[in], k).w));
+                        p.gather[li] = radiance[li];
+                    }
+                }
+            }
             if (threadIdx.x == 0)
             {   // per-bounce statistics (rt_read_frame_stats): one fire-and-forget global add per CTA and counter
                 const unsigned long long hm = s.hm[in];
@@ -1133,6 +1154,21 @@ __global__ void __launch_bounds__(RT_FRAME_MAX_THREADS, 1) k_frame(FrameParams p
                         slot = __shfl_sync(0xffffffffu, slot, 0);
                     }
                     const unsigned lt_mask = (1u << lane) - 1u;
+                    if (p.gather)
+                    {   // paths that end at this hit (no continuation ray): final once their shadow ray is accumulated in T(b+1)
+                        const unsigned dmask = __ballot_sync(0xffffffffu, hit && !so.spawn_next);
+                        if (dmask)
+                        {
+                            uint32_t at0 = 0;
+                            if (lane == 0) at0 = atomicAdd(&s.ended_n[in], (uint32_t)__popc(dmask));
+                            at0 = __shfl_sync(0xffffffffu, at0, 0);
+                            if (hit && !so.spawn_next)
+                            {
+                                uint32_t* list = in ? (uint32_t*)q.hits + base : q.shadow_flags + base;
+                                list[at0 + __popc(dmask & lt_mask)] = local_index(p, pixel);
+                            }
+                        }
+                    }
                     if (ss)
                     {
                         const uint32_t si = (uint32_t)slot + __popc(smask & lt_mask);
@@ -1232,6 +1268,22 @@ __global__ void __launch_bounds__(256) k_temporal(uint32_t width, uint32_t heigh
     radiance[idx] = cur;
 }
 
+// Completion flags of the fused gather (one uint32 per rank, in the presenting device's memory, behind the slabs): a rank stores its
+// frame number after its frame kernel has completed (stream order) — everything it pushed is then visible system-wide — and the
+// presenting rank's stream waits until every flag has reached its own frame number.
+__global__ void k_gather_signal(uint32_t* flag, uint32_t frame)
+{
+    __threadfence_system();
+    *(volatile uint32_t*)flag = frame;
+    __threadfence_system();
+}
+__global__ void k_gather_wait(const uint32_t* flags, uint32_t world, uint32_t frame)
+{
+    if (threadIdx.x < world)
+        while ((int32_t)(*(volatile const uint32_t*)(flags + threadIdx.x) - frame) < 0) __nanosleep(200);
+    __threadfence_system();
+}
+
 // rt_math_eval: the functions of include/rt_math.h evaluated on the device (parity tap: tests compare them bitwise with the
 // same header compiled for the host)
 __global__ void k_math_eval(int fn, const float* a, const float* b, float* out, uint64_t n)
@@ -1326,6 +1378,11 @@ struct rt_ctx
     FrameDyn* d_dyn = nullptr;
     bool pdl = true;               // RT_OPT_PDL
     int frame_kernel = 2;          // RT_OPT_FRAME_KERNEL: 1 rt_integrate launches ONE persistent kernel per frame (k_frame), 0 one kernel per phase, 2 by partition size
+    // fused gather (rt_set_gather_target): this rank's slab and flag in the presenting device's memory, frames signalled so far
+    float4* gather_slab = nullptr; uint32_t* gather_flag = nullptr; uint32_t gather_frame = 0;
+    uint32_t gather_sample = 0xFFFFFFFFu;          // sample_count after the last frame that was pushed
+    void* own_gather = nullptr; size_t own_gather_stride = 0;      // the buffer this context allocated (rt_gather_buffer)
+    std::vector<void*> ipc_opened;
     int grid_div = 1;              // contexts that share this device (rt_create_multi lists a device k times): each launches 1/k of the resident CTAs
     int frame_threads = 0;         // RT_OPT_FRAME_THREADS: threads per CTA of k_frame (0 = by partition size)
     size_t n_alloc = 0;            // entries of every per-pixel queue: n_local + one group of 32 per CTA that can be resident (k_frame's regions)
@@ -1451,6 +1508,7 @@ FrameParams frame_params(const rt_ctx* c)
     FrameParams p;
     p.width = c->width; p.height = c->height; p.rank = c->rank; p.world = c->world; p.n_local = c->n_local;
     p.white_furnace = c->white_furnace; p.bn = c->sampler ? c->d_bn : nullptr; p.dyn = c->d_dyn;
+    p.gather = nullptr;            // set by the one-kernel frame's launch only
     return p;
 }
 
@@ -1687,6 +1745,8 @@ int rt_destroy(rt_ctx* c)
     for (int i = 0; i < 2; ++i) { if (c->resolve_done[i]) cudaEventDestroy(c->resolve_done[i]); if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]); }
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     free_aov_buffers(c);
+    cudaFree(c->own_gather);
+    for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void* p : c->scene_allocs) cudaFree(p);
     for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
@@ -1824,7 +1884,15 @@ int rt_set_option(rt_ctx* c, int key, uint32_t value)
     if (key == RT_OPT_PRESENT)
     {
         if (value > 1) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "present mode must be 0 (parallel read-back) or 1 (gather to the first device)");
-        c->present = (int)value; return RT_OK;
+        c->present = (int)value;
+        if (!c->children.empty())
+        {   // gather presentation: the children push their pixels into a buffer on the first device while they render (fused gather)
+            rt_ctx* k0 = c->children[0];
+            void* buf = nullptr; uint64_t stride = 0;
+            if (value == 1) { int rc = rt_gather_buffer(k0, &buf, &stride, nullptr); if (rc) { c->error = k0->error; return rc; } }
+            for (rt_ctx* k : c->children) { int rc = rt_set_gather_target(k, value == 1 ? buf : nullptr, stride); if (rc) { c->error = k->error; return rc; } }
+        }
+        return RT_OK;
     }
     RT_FANOUT(c, rt_set_option(k, key, value));
     ++c->config_gen;
@@ -2200,6 +2268,20 @@ static int frame_kernel_threads(const rt_ctx* c)
     return (size_t)c->n_local > (size_t)c->num_sms * 4096u ? 1024 : 256;
 }
 
+// Fused gather, end of a frame: k_frame has pushed every pixel already (copy_slab false); the per-phase schedule pushes its whole
+// slab with one device-to-device copy.  Then the completion flag.
+static int gather_signal(rt_ctx* c, bool copy_slab)
+{
+    if (!c->gather_slab) return RT_OK;
+    if (copy_slab && c->n_local)
+        RT_CUDA(c, cudaMemcpyAsync(c->gather_slab, c->radiance, (size_t)c->n_local * 16, cudaMemcpyDefault, c->stream));
+    ++c->gather_frame;
+    c->gather_sample = c->sample_count;
+    k_gather_signal<<<1, 1, 0, c->stream>>>(c->gather_flag, c->gather_frame);
+    ++c->launches;
+    return post_launch(c, "k_gather_signal");
+}
+
 // The whole frame as ONE persistent kernel (k_frame): a counter clear and a launch.
 static int integrate_frame_kernel(rt_ctx* c, uint32_t max_bounces)
 {
@@ -2228,16 +2310,18 @@ static int integrate_frame_kernel(rt_ctx* c, uint32_t max_bounces)
     const uint32_t slots_per_cta = ((n_groups + grid - 1u) / grid) * 32u;
     if ((size_t)grid * slots_per_cta > c->n_alloc) RT_FAIL(c, RT_ERR_CUDA, "frame kernel: queue regions exceed the allocation");
     const FrameDyn dyn = frame_dyn(c);
+    FrameParams fp = frame_params(c);
+    fp.gather = c->gather_slab;
     {
         TimedLaunch t(c, RT_K_MISC);
-        if (sg.mode == 1) k_frame<1><<<grid, threads, stage, c->stream>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
-        else if (sg.mode == 2) k_frame<2><<<grid, threads, stage, c->stream>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
-        else k_frame<0><<<grid, threads, 0, c->stream>>>(frame_params(c), sc, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
+        if (sg.mode == 1) k_frame<1><<<grid, threads, stage, c->stream>>>(fp, sc, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
+        else if (sg.mode == 2) k_frame<2><<<grid, threads, stage, c->stream>>>(fp, sc, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
+        else k_frame<0><<<grid, threads, 0, c->stream>>>(fp, sc, c->traversal, c->q, c->counters, c->radiance, aov_params(c), max_bounces, slots_per_cta, dyn);
     }
     if ((rc = post_launch(c, "k_frame"))) return rc;
     c->frame_started = true; c->cur_bounce = max_bounces;
     ++c->sample_count;
-    return RT_OK;
+    return gather_signal(c, false);
 }
 
 int rt_integrate(rt_ctx* c, uint32_t max_bounces)
@@ -2245,7 +2329,11 @@ int rt_integrate(rt_ctx* c, uint32_t max_bounces)
     RT_CHECK_CTX(c); RT_FANOUT(c, rt_integrate(k, max_bounces));
     if (max_bounces > RT_MAX_BOUNCES) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "max_bounces %u exceeds RT_MAX_BOUNCES", max_bounces);
     if (frame_kernel_selected(c) && !c->kernel_timing && !c->count_traversal) return integrate_frame_kernel(c, max_bounces);
-    if (!c->use_graph || c->kernel_timing || c->count_traversal) return integrate_body(c, max_bounces);
+    if (!c->use_graph || c->kernel_timing || c->count_traversal)
+    {
+        int rc = integrate_body(c, max_bounces); if (rc) return rc;
+        return gather_signal(c, true);
+    }
     int rc = require_ready(c); if (rc) return rc;
     RT_CUDA(c, cudaSetDevice(c->device));
     if (!c->graph_exec || c->graph_gen != c->config_gen || c->graph_max_bounces != max_bounces)
@@ -2263,7 +2351,7 @@ int rt_integrate(rt_ctx* c, uint32_t max_bounces)
     c->launches += c->graph_launches;
     c->frame_started = true; c->cur_bounce = max_bounces;
     ++c->sample_count;
-    return RT_OK;
+    return gather_signal(c, true);
 }
 
 // resolve kernel + device->host copy of this context's rows, enqueued on its stream (no synchronisation)
@@ -2291,9 +2379,20 @@ int rt_resolve(rt_ctx* c, float* dst)
     {
         if (c->present == 1)
         {   // the frame's ONE collective: radiance slabs -> first device over NVLink, resolved and read back there
-            int rc = rt_gather_radiance(c); if (rc) return rc;
             rt_ctx* k0 = c->children[0];
-            rc = rt_resolve_gathered(k0, c->gather_buf, (uint64_t)c->gather_stride_f4 * 16, dst);
+            bool pushed = true;              // did the frame kernels push this frame already (fused gather)?
+            for (rt_ctx* k : c->children) pushed = pushed && k->gather_slab && k->gather_sample == k->sample_count;
+            int rc;
+            if (pushed)
+            {
+                rc = rt_gather_wait(k0);
+                if (!rc) rc = rt_resolve_gathered(k0, k0->own_gather, (uint64_t)k0->own_gather_stride, dst);
+            }
+            else
+            {   // frames rendered before the option was set: explicit peer copies
+                rc = rt_gather_radiance(c); if (rc) return rc;
+                rc = rt_resolve_gathered(k0, c->gather_buf, (uint64_t)c->gather_stride_f4 * 16, dst);
+            }
             if (rc) c->error = k0->error;
             return rc;
         }
@@ -2705,6 +2804,83 @@ int rt_host_unregister(void* ptr)
     cudaError_t e = cudaHostUnregister(ptr);
     if (e != cudaSuccess) { cudaGetLastError(); g_create_error = std::string("rt_host_unregister: ") + cudaGetErrorString(e); return RT_ERR_CUDA; }
     return RT_OK;
+}
+
+/* ---- fused gather over peer memory ------------------------------------------------------------------------------------------
+ * The frame's one collective done by the frame kernel itself: every rank pushes the radiance of a pixel into its slab of a buffer
+ * on the presenting device (NVLink peer stores) the moment the pixel's path ends, so the transfer is spread over the whole frame
+ * instead of following it; a per-rank flag signals completion.  The buffer holds world slabs of rows_max * width float4 (the layout
+ * rt_resolve_gathered reads) followed by the flags.  One process per GPU: the owner exports the buffer with rt_ipc_export, the
+ * other ranks map it with rt_ipc_open; one process over several devices (rt_create_multi): peer access, no handles needed. */
+int rt_gather_buffer(rt_ctx* c, void** dev_ptr, uint64_t* stride_bytes, uint64_t* total_bytes)
+{
+    RT_CHECK_CTX(c); RT_NOT_ON_GROUP(c, "rt_gather_buffer");
+    if (!dev_ptr || !stride_bytes) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_gather_buffer: null output");
+    const size_t rows_max = ((size_t)c->height + c->world - 1) / c->world;
+    const size_t stride = rows_max * c->width * 16;
+    const size_t total = stride * c->world + 256;
+    RT_CUDA(c, cudaSetDevice(c->device));
+    if (c->own_gather && c->own_gather_stride != stride) { cudaFree(c->own_gather); c->own_gather = nullptr; }
+    if (!c->own_gather)
+    {
+        RT_CUDA(c, cudaMalloc(&c->own_gather, total));
+        RT_CUDA(c, cudaMemset(c->own_gather, 0, total));
+        c->own_gather_stride = stride;
+    }
+    *dev_ptr = c->own_gather; *stride_bytes = stride;
+    if (total_bytes) *total_bytes = total;
+    return RT_OK;
+}
+
+int rt_ipc_export(const void* dev_ptr, void* handle64)
+{
+    if (!dev_ptr || !handle64) return RT_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr));
+    if (e != cudaSuccess) { cudaGetLastError(); g_create_error = std::string("rt_ipc_export: ") + cudaGetErrorString(e); return RT_ERR_CUDA; }
+    memcpy(handle64, &h, 64);
+    return RT_OK;
+}
+
+int rt_ipc_open(rt_ctx* c, const void* handle64, void** dev_ptr)
+{
+    RT_CHECK_CTX(c); RT_NOT_ON_GROUP(c, "rt_ipc_open");
+    if (!handle64 || !dev_ptr) RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_ipc_open: null argument");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h; memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    RT_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->ipc_opened.push_back(p);
+    *dev_ptr = p;
+    return RT_OK;
+}
+
+/* base = the buffer of rt_gather_buffer as THIS process addresses it (own pointer, peer pointer or rt_ipc_open mapping);
+ * NULL turns the fused gather off.  Takes effect with the next frame. */
+int rt_set_gather_target(rt_ctx* c, void* base, uint64_t stride_bytes)
+{
+    RT_CHECK_CTX(c); RT_NOT_ON_GROUP(c, "rt_set_gather_target");
+    { int rc = join_shadow(c); if (rc) return rc; }
+    if (!base) { c->gather_slab = nullptr; c->gather_flag = nullptr; return RT_OK; }
+    const size_t rows_max = ((size_t)c->height + c->world - 1) / c->world;
+    if (stride_bytes % 16 != 0 || stride_bytes < rows_max * c->width * 16)
+        RT_FAIL(c, RT_ERR_INVALID_ARGUMENT, "rt_set_gather_target: slab stride must be a multiple of 16 and hold %zu rows", rows_max);
+    c->gather_slab = (float4*)((char*)base + (size_t)c->rank * stride_bytes);
+    c->gather_flag = (uint32_t*)((char*)base + (size_t)c->world * stride_bytes) + c->rank;
+    return RT_OK;
+}
+
+/* On the context that presents (it must have a gather target itself, i.e. take part in the frames): makes its stream wait until
+ * every rank has signalled the frame this context rendered last. */
+int rt_gather_wait(rt_ctx* c)
+{
+    RT_CHECK_CTX(c); RT_NOT_ON_GROUP(c, "rt_gather_wait");
+    if (!c->gather_flag) RT_FAIL(c, RT_ERR_NOT_READY, "rt_gather_wait: no gather target set");
+    RT_CUDA(c, cudaSetDevice(c->device));
+    k_gather_wait<<<1, 64, 0, c->stream>>>(c->gather_flag - c->rank, c->world, c->gather_frame);
+    ++c->launches;
+    return post_launch(c, "k_gather_wait");
 }
 
 /* Parity tap: out[i] = f(a[i], b[i]) for a function of include/rt_math.h, evaluated on `device` (host pointers; blocking).

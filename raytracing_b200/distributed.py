@@ -124,3 +124,59 @@ class SharedHostImage:
             torch.cuda.cudart().cudaHostUnregister(self.image.ctypes.data)
             self.pinned = False
         self._release()
+
+
+class FusedGather:
+    """The frame's one collective done by the frame kernels themselves (include/rt_b200.h, rt_set_gather_target): rank 0 owns a
+    buffer of `world` radiance slabs + completion flags on its GPU, every other rank maps it through CUDA IPC (NVLink peer
+    memory) and its frame kernel stores a pixel's radiance there the moment the pixel's path ends.  torch.distributed only
+    carries the 64-byte IPC handle at set-up; no collective runs per frame.  `ok` is False (on every rank) when the mapping could
+    not be set up on some rank — callers then fall back to RadianceGather (NCCL)."""
+
+    def __init__(self, ctx, rank: int, world: int):
+        from . import capi
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.ptr = self.stride = None
+        err = None
+        handle = [None]
+        try:
+            if rank == 0:
+                self.ptr, self.stride, _ = ctx.gather_buffer()
+                handle = [(capi.ipc_export(self.ptr), self.stride)]
+        except Exception as e:          # noqa: BLE001
+            err = repr(e)
+        if world > 1:
+            dist.broadcast_object_list(handle, src=0)
+        try:
+            if err is None and rank != 0:
+                if handle[0] is None:
+                    raise RuntimeError("rank 0 could not export the buffer")
+                self.stride = handle[0][1]
+                self.ptr = ctx.ipc_open(handle[0][0])
+            if err is None:
+                ctx.set_gather_target(self.ptr, self.stride)
+        except Exception as e:          # noqa: BLE001
+            err = repr(e)
+        flags = [err]
+        if world > 1:
+            all_err = [None] * world
+            dist.all_gather_object(all_err, err)
+            flags = all_err
+        self.errors = [e for e in flags if e]
+        self.ok = not self.errors
+        if not self.ok:
+            try:
+                ctx.set_gather_target(None)
+            except Exception:           # noqa: BLE001
+                pass
+
+    def wait(self):
+        """Rank 0: the render stream waits until every rank has delivered the frame rendered last."""
+        if self.rank == 0:
+            self.ctx.gather_wait()
+
+    def close(self):
+        try:
+            self.ctx.set_gather_target(None)
+        except Exception:               # noqa: BLE001
+            pass

@@ -558,6 +558,41 @@ def test_top_of_tree_staging_is_bit_identical(name, w, h, mb):
     c.destroy()
 
 
+@pytest.mark.parametrize("name,w,h,mb,fk", [("CornellBox", 203, 117, 6, 1), ("ShaderBalls", 320, 180, 5, 1), ("ShaderBalls", 257, 131, 7, 0)])
+def test_fused_gather_delivers_the_frame(name, w, h, mb, fk):
+    """rt_set_gather_target: the ranks' frame kernels push every pixel into rank 0's gather buffer the moment its path ends
+    (misses in the shading phase, paths that end at a hit after their last shadow ray, survivors after the last round; the
+    per-phase schedule copies its slab at the end).  Three ranks in one process share the buffer directly; after rt_gather_wait
+    the buffer resolved through rt_resolve_gathered equals the single-context image, over three progressive samples."""
+    sc = scene(name); cam = default_camera(w, h)
+    world = 3
+    one = capi.Context(w, h); one.upload_scene(sc); one.set_camera(cam); one.reset()
+    parts = []
+    for rank in range(world):
+        c = capi.Context(w, h, rank=rank, world=world)
+        c.set_option(capi.OPT_FRAME_KERNEL, fk)
+        c.upload_scene(sc); c.set_camera(cam); c.reset()
+        parts.append(c)
+    buf, stride, total = parts[0].gather_buffer()
+    assert total >= world * stride + 4 * world
+    for c in parts:
+        c.set_gather_target(buf, stride)
+    for sample in range(3):
+        one.integrate(mb)
+        for c in reversed(parts):                # rank 0 last: its wait really waits for flags set on other streams
+            c.integrate(mb)
+        parts[0].gather_wait()
+        got = parts[0].resolve_gathered(buf, stride)
+        assert np.array_equal(bits(got), bits(one.resolve())), sample
+    # turning it off again stops the pushes
+    for c in parts:
+        c.set_gather_target(None)
+    with pytest.raises(capi.RtError):
+        parts[0].gather_wait()
+    for c in parts + [one]:
+        c.destroy()
+
+
 @pytest.mark.parametrize("name,w,h,mb", [("CornellBox", 203, 117, 6), ("ShaderBalls", 320, 180, 5)])
 def test_multi_device_context_matches_single_device(name, w, h, mb):
     """rt_create_multi: ONE context over several devices (here the devices of the box, or device 0 listed three times when it has
@@ -581,7 +616,11 @@ def test_multi_device_context_matches_single_device(name, w, h, mb):
         assert np.array_equal(bits(want), bits(many.resolve(host)))               # parallel read-back into a page-locked image
         many.set_option(capi.OPT_PRESENT, 1)
         host[:] = 0
-        assert np.array_equal(bits(want), bits(many.resolve(host)))               # gather to devices[0] (peer copies) + resolve there
+        assert np.array_equal(bits(want), bits(many.resolve(host)))               # frames rendered before the option: peer copies to devices[0], resolve there
+        one.integrate(mb); many.integrate(mb)                                      # a frame rendered WITH the option: pushed by the frame kernels (fused gather)
+        want = one.resolve()
+        host[:] = 0
+        assert np.array_equal(bits(want), bits(many.resolve(host)))
         many.set_option(capi.OPT_PRESENT, 0)
         host[:] = 0
         many.resolve_async(host); many.resolve_wait()
