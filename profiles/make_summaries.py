@@ -126,4 +126,24 @@ for rep in sorted(glob.glob(os.path.join(src, f"prof_*_{tag}.csv")) + glob.glob(
     print(w, json.dumps({c: {"Minst": round(k["inst_per_frame"] / 1e6, 1), "lanes": round(k["lane_occupancy"] * 32, 1), "dramMB": round(k["dram_bytes_per_frame"] / 1e6, 1)}
                          for c, k in entry["kernels"].items()}))
 
+# launch list of the bench command itself (ncu --metrics gpu__time_duration.sum, profiles/run_ncu.sh launches): per-kernel shares
+import collections
+lc = os.path.join(src, f"launches_{tag}.csv")
+if os.path.exists(lc):
+    lines = [l for l in open(lc) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        v = fnum(row["Metric Value"]); u = row["Metric Unit"]
+        v = v / 1e3 if u in ("ns", "nsecond") else (v * 1e3 if u in ("ms", "msecond") else v)
+        agg.setdefault(row["Kernel Name"].split("(")[0][-44:], []).append(v)
+    tot = sum(sum(v) for v in agg.values()) or 1.0
+    with open(os.path.join(HERE, f"{tag}_launch_shares.txt"), "w") as f:
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 2 --warmup 3 --no-cpu-baseline --secondary none --no-host-e2e, tag {tag}\n")
+        f.write("# (counter frame + warm-up + 2 timed steps + per-kernel-timing steps + e2e frames); per-launch times are cold-cache and serialised:\n"
+                "# the SHARES are what must agree with bench.py's CUDA-event split\n")
+        for k, v in agg.items():
+            f.write(f"{k:46s} launches {len(v):4d}  total {sum(v):10.1f} us  share {100 * sum(v) / tot:5.1f}%\n")
+    with open(os.path.join(HERE, f"{tag}_launches.csv"), "w") as f:
+        f.writelines(lines)
+
 json.dump(tj, open(tj_path, "w"), indent=1)
