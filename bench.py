@@ -478,6 +478,20 @@ def main():
 
         return types.SimpleNamespace(**{k: v for k, v in locals().items() if k not in ("workload",)})
 
+    def destroy_context(c):
+        """Rank 0's context owns the fused-gather buffer that the other ranks have mapped through CUDA IPC: they unmap (destroy
+        their context) first, rank 0 frees after the barrier."""
+        if c is None:
+            return
+        if world > 1:
+            if rank != 0:
+                c.destroy()
+            torch.cuda.synchronize(); dist.barrier()
+            if rank == 0:
+                c.destroy()
+        else:
+            c.destroy()
+
     R = device_run(workload, args.steps)
     name, w, h, mb = workload
     ctx, frame, barrier, gather, slab, stream, scene, cam = R.ctx, R.frame, R.barrier, R.gather, R.slab, R.stream, R.scene, R.cam
@@ -612,7 +626,7 @@ def main():
     secondary = None
     sec_name = args.secondary if args.secondary in WORKLOADS and args.secondary != args.scene else None
     if sec_name:
-        ctx.destroy()                                    # the primary context is finished: free its queues before the 3 GB scene
+        destroy_context(ctx)                             # the primary context is finished: free its queues before the 3 GB scene
         ctx = None
         S = device_run(WORKLOADS[sec_name], args.secondary_steps)
         sclk = S.sampler.summary()
@@ -627,7 +641,7 @@ def main():
                          "collective_ms": S.collective_ms, "collective": {"kind": S.collective_kind, "nccl_gather_alone_ms": S.collective_ms}, "gpu_launches": int(S.launches),
                          "roofline": issue_roofline(sec_name, world, S.ktimes, args.secondary_steps, s_mhz, S.n_sms, s_peak, S.alg_of),
                          "kernel_ms_per_step": {k: v[0] / args.secondary_steps for k, v in S.ktimes.items() if v[1]}, "clocks": sclk}
-        S.ctx.destroy()
+        destroy_context(S.ctx)
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
@@ -685,8 +699,7 @@ def main():
         print(json.dumps(line))
     if shared is not None:
         shared.close()
-    if ctx is not None:
-        ctx.destroy()
+    destroy_context(ctx)
     if world > 1:
         dist.destroy_process_group()
 
