@@ -55,420 +55,8 @@ using namespace rt;
 namespace
 {
 
-// ------------------------------------------------------------------------------------ device state
-struct DevCounters
-{
-    uint32_t n_primary;                          // rays entering bounce 0
-    uint32_t pad0;
-    // rays spawned by the shading pass of bounce b: shadow rays and continuation rays (= the rays entering bounce b+1).
-    // Adjacent + 8-byte aligned so that ONE 64-bit atomic reserves slots in both output queues.
-    struct alignas(8) Emit { uint32_t shadow, next; };
-    Emit emit[RT_MAX_BOUNCES + 1];
-    struct alignas(8) HitMiss { uint32_t hit, miss; };   // adjacent + 8-byte aligned: one 64-bit atomic advances both
-    HitMiss hm[RT_MAX_BOUNCES + 1];              // hit-queue entries / misses of bounce b
-    uint32_t n_emissive[RT_MAX_BOUNCES + 1];
-    uint32_t n_unoccluded[RT_MAX_BOUNCES + 1];
-    uint32_t work_ext[RT_MAX_BOUNCES + 1];       // persistent-kernel work cursors
-    uint32_t work_shade[RT_MAX_BOUNCES + 1];
-    uint32_t work_shadow[RT_MAX_BOUNCES + 1];
-    unsigned long long nodes_ext[RT_MAX_BOUNCES + 1], tris_ext[RT_MAX_BOUNCES + 1];
-    unsigned long long nodes_shadow[RT_MAX_BOUNCES + 1], tris_shadow[RT_MAX_BOUNCES + 1];
-};
-
-__host__ __device__ __forceinline__ const uint32_t* in_count_ptr(const DevCounters* c, uint32_t bounce)
-{
-    return bounce == 0 ? &c->n_primary : &c->emit[bounce - 1].next;
-}
-
-struct Queues
-{
-    float4* A[2]; float4* B[2]; float4* C[2];
-    float4* sA; float4* sB; float4* sC;
-    float4* hits;
-    uint32_t* shadow_flags;
-    float4* hitq;
-    uint32_t* missq;
-#ifdef RT_HITQ_CARRY
-    float4* hA; float4* hB; float4* hC;      // experiment: the hit queue carries its ray (coalesced reads in the shading kernel)
-#endif
-};
-
-// Per-frame constants that change from frame to frame (sample index, camera): kept in a small device buffer that a
-// 1-thread kernel refreshes at the start of every frame, so that the rest of the frame's launches have frame-invariant
-// arguments and the whole frame can be replayed as ONE CUDA graph (rt_integrate) with a single node-parameter update.
-struct FrameDyn;
-
-struct FrameParams
-{
-    uint32_t width, height, rank, world, n_local;
-    int white_furnace;
-    const int* bn;                 // blue-noise sampler tables (kBlueNoise) or nullptr (kRandom)
-    const FrameDyn* dyn;
-    float4* gather;                // k_frame only: this rank's slab of the gathered radiance on the presenting device (peer memory,
-                                   // rt_set_gather_target) — a pixel's radiance is pushed there the moment its path ends; else nullptr
-};
-
-// AOV outputs of bounce 0 (kernels/cl/aov.cl:44-110), written by the bounce-0 shading pass when enabled
-struct AovCam { f3 position, front, up, right; float angle, aspect_ratio; };
-struct AovParams
-{
-    int enabled;
-    float4* albedo; float* depth; float4* normal; float2* velocity;
-};
-
-struct FrameDyn
-{
-    uint32_t sample_idx, pad[3];
-    RayGenConsts raygen;
-    AovCam cam, prev;
-};
-
-__global__ void k_set_frame(FrameDyn* dst, FrameDyn value) { *dst = value; }
-
-// kernels/cl/aov.cl:30-42
-__device__ __forceinline__ f2 project_screen(f3 position, const AovCam& c)
-{
-    f3 d = normalize(position - c.position);
-    f3 ipd = d / dot(c.front, d);
-    float u = dot(c.right, ipd) / (c.angle * c.aspect_ratio);
-    float v = dot(c.up, ipd) / (c.angle);
-    f2 r; r.x = u * 0.5f + 0.5f; r.y = v * 0.5f + 0.5f;
-    return r;
-}
-
-__device__ __forceinline__ uint32_t pack_pixel(uint32_t px, uint32_t py) { return px | (py << 16); }
-__device__ __forceinline__ uint32_t local_index(const FrameParams& p, uint32_t pxy)
-{
-    uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
-    return (p.world == 1 ? py : py / p.world) * p.width + px;
-}
-
-__device__ __forceinline__ void warp_count(uint32_t* counter, bool pred)
-{
-    unsigned mask = __ballot_sync(0xffffffffu, pred);
-    if (mask != 0 && (threadIdx.x & 31) == __ffs(mask) - 1) atomicAdd(counter, (uint32_t)__popc(mask));
-}
-
-__device__ __forceinline__ void warp_sum64(unsigned long long* counter, uint32_t v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(counter, (unsigned long long)v);
-}
-
-// ------------------------------------------------------------------------------------ TMA staging of a small BVH
-// When the whole traversal structure (interior records + triangle records) is small enough, every CTA of a
-// traversal kernel copies it ONCE into shared memory with two TMA bulk copies (cp.async.bulk, completion signalled
-// through an mbarrier transaction count) issued by one elected thread, and all node / triangle fetches of the
-// kernel become shared-memory loads: the L1 data pipe is the second-busiest unit of the traversal kernels (ncu:
-// l1tex data-pipe wavefronts ~58 % of peak, a divergent LDG.128 touches one 128-byte line per active lane), while a
-// 16-byte LDS from 32 different records needs 4 conflict-free wavefronts.  The kernels are persistent, so the copy
-// is amortised over every ray the CTA traces.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void tma_stage_bvh(float4* dst, const DevScene& sc, uint64_t* mbar)
-{
-    const uint32_t bar = smem_u32(mbar);
-    const uint32_t nodes_bytes = sc.wnodes_f4 * 16u, tris_bytes = sc.wtris_f4 * 16u;
-    if (threadIdx.x == 0)
-    {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nodes_bytes + tris_bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(dst)), "l"(sc.wnodes), "r"(nodes_bytes), "r"(bar) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(dst + sc.wnodes_f4)), "l"(sc.wtris), "r"(tris_bytes), "r"(bar) : "memory");
-    }
-    uint32_t done = 0;
-    while (!done)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(bar), "r"(0) : "memory");
-}
-
-// Scenes that do not fit: only the top of the tree — the first `n_records` interior records, breadth-first (rt_bvh_layout.h) — is
-// staged, with one TMA bulk copy per CTA; deeper records and all triangles stay behind L1/L2 (RT_OPT_TOP_SMEM).
-__device__ __forceinline__ void tma_stage_top(float4* dst, const float4* wnodes, uint32_t n_records, uint64_t* mbar)
-{
-    const uint32_t bar = smem_u32(mbar);
-    const uint32_t bytes = n_records * 64u;
-    if (threadIdx.x == 0)
-    {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(dst)), "l"(wnodes), "r"(bytes), "r"(bar) : "memory");
-    }
-    uint32_t done = 0;
-    while (!done)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(bar), "r"(0) : "memory");
-}
-
-// Programmatic dependent launch (RT_OPT_PDL): a kernel launched with the programmatic-stream-serialization attribute may
-// start (launch its CTAs, stage the BVH) while the previous kernel of the stream is still draining; pdl_wait() blocks
-// until that kernel has completed and its memory is visible, and is a no-op for a normal launch.  Every persistent
-// kernel lets ITS dependent start as early as possible: its CTAs are all resident by then (persistent_grid), so
-// the dependent's CTAs only take the slots that exiting CTAs free.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-// SMEM: 0 records behind L1/L2 (ld.global.nc), 1 all records in shared memory, 2 the first sc.top_k interior records in shared
-// memory and the rest in global memory (one generic load serves both)
-template <int SMEM>
-__device__ __forceinline__ float4 ld_bvh(const float4* p) { return SMEM ? *p : __ldg(p); }
-
-// ------------------------------------------------------------------------------------ traversal
-// Literal restatement of kernels/cl/trace_bvh.cl:99-211 on the reference node layout: per-ray
-// DFS, 64-entry private stack, far child pushed unconditionally and box-tested when popped,
-// near child chosen by ray_sign[axis], inclusive tests, later equal-t hit overwrites, back-face
-// culling (det < 1e-8 rejects).  ANY = the -D SHADOW_RAYS variant (returns 0 on first hit).
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ uint32_t trace_literal(const DevScene& sc, f3 o, f3 d, float t_min, float t_max,
-                                                  float& bu, float& bv, float& bt, uint32_t& nv, uint32_t& nt)
-{
-    f3 inv = splat(1.0f) / d;
-    int sx = inv.x < 0, sy = inv.y < 0, sz = inv.z < 0;
-    uint32_t prim = RT_INVALID_ID;
-    int to_visit = 0, cur = 0;
-    int stack[64];
-    for (;;)
-    {
-        float4 n0 = __ldg(sc.nodes_ref + (size_t)cur * 3), n1 = __ldg(sc.nodes_ref + (size_t)cur * 3 + 1), n2 = __ldg(sc.nodes_ref + (size_t)cur * 3 + 2);
-        if (COUNT) ++nv;
-        f3 t0 = (mk3(n0) - o) * inv, t1 = (mk3(n1) - o) * inv;
-        float lo = fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z));
-        float hi = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
-        bool box = fminf(hi, t_max) >= fmaxf(lo, t_min);
-        uint32_t offset = __float_as_uint(n2.x), npa = __float_as_uint(n2.y);
-        if (box)
-        {
-            int nprims = (int)(npa >> 16);
-            if (nprims > 0)
-            {
-                for (int i = 0; i < nprims; ++i)
-                {
-                    const float4* tp = sc.tris_ref + (size_t)(offset + i) * 3;
-                    f3 p1 = mk3(__ldg(tp)), p2 = mk3(__ldg(tp + 1)), p3 = mk3(__ldg(tp + 2));
-                    if (COUNT) ++nt;
-                    f3 e1 = p2 - p1, e2 = p3 - p1;
-                    f3 pvec = cross(d, e2);
-                    float det = dot(e1, pvec);
-                    if (det < 1e-8f || -det > 1e-8f) continue;
-                    float inv_det = 1.0f / det;
-                    f3 tvec = o - p1;
-                    float u = dot(tvec, pvec) * inv_det;
-                    if (u < 0.0f || u > 1.0f) continue;
-                    f3 qvec = cross(tvec, e1);
-                    float v = dot(d, qvec) * inv_det;
-                    if (v < 0.0f || u + v > 1.0f) continue;
-                    float t = dot(e2, qvec) * inv_det;
-                    if (t < t_min || t > t_max) continue;
-                    bu = u; bv = v; bt = t;
-                    prim = offset + i;
-                    t_max = t;
-                    if (ANY) return 0u;
-                }
-                if (to_visit == 0) break;
-                cur = stack[--to_visit];
-            }
-            else
-            {
-                uint32_t axis = npa & 0xFFFFu;
-                int s = axis == 0 ? sx : (axis == 1 ? sy : sz);
-                if (s) { stack[to_visit++] = cur + 1; cur = (int)offset; }
-                else   { stack[to_visit++] = (int)offset; cur = cur + 1; }
-            }
-        }
-        else
-        {
-            if (to_visit == 0) break;
-            cur = stack[--to_visit];
-        }
-    }
-    return prim;
-}
-
-// Optimised traversal on the child-box node layout (rt_bvh_layout.h).  Same visiting order and
-// the same arithmetic per box / triangle test as trace_literal, so results are bit-identical
-// for finite rays; non-finite rays (NaN/inf components; their traversal is garbage-in but must
-// still match) take the literal path.
-// PIN: the whole-frame kernel shares its register budget with the shading code and ptxas then re-derives the sign bits on
-// every step and recomputes the determinant after its branch; an empty asm makes both values opaque (kept in registers).
-template <bool ANY, bool COUNT, int SMEM, bool PIN = false>
-__device__ __forceinline__ uint32_t trace_fast(const DevScene& sc, const float4* wnodes, const float4* wtris, f3 o, f3 d, float t_min, float t_max,
-                                               float& bu, float& bv, float& bt, uint32_t& nv, uint32_t& nt)
-{
-    float fin = ((o.x + o.y) + o.z) + ((d.x + d.y) + d.z);
-    if (!(fabsf(fin) <= 3.0e38f) || COUNT)
-        return trace_literal<ANY, COUNT>(sc, o, d, t_min, t_max, bu, bv, bt, nv, nt);
-
-    f3 inv = splat(1.0f) / d;
-    const bool sx = inv.x < 0, sy = inv.y < 0, sz = inv.z < 0;
-    uint32_t sign_bits = (sx ? 1u : 0u) | (sy ? 2u : 0u) | (sz ? 4u : 0u);
-    if (PIN) asm volatile("" : "+r"(sign_bits));
-    uint32_t prim = RT_INVALID_ID;
-    int sp = 0;
-    int cur = sc.root_ref;
-    // Deferred far children: (node reference, entry distance).  Two code shapes, chosen by where the BVH records live
-    // (measured, same results): with the records in shared memory the kernel is purely issue-bound and the packed
-    // 64-bit stack entry + the sign-bit axis test win (CornellBox frame -2.7 %); with the records behind L1/L2 the two
-    // 32-bit arrays (a discarded pop costs one load) and predicate selects are faster (ShaderBalls +1 %, Dragon +3.5 %).
-#ifdef RT_SMEM_STACK
-    // experiment: the traversal stack in shared memory (entry i of thread t at [i * 256 + t]: conflict-free), per-phase kernels only
-    extern __shared__ __align__(128) float4 rt_dyn_smem[];
-    int2* const sstk = (int2*)((char*)rt_dyn_smem + sc.stack_off) + threadIdx.x;
-    constexpr bool SSTK = !PIN;
-#else
-    int2* const sstk = nullptr;
-    constexpr bool SSTK = false;
-#endif
-    int2 stack[(SMEM == 1 && !SSTK) ? 64 : 1];
-    int stack_ref[(SMEM == 1 || SSTK) ? 1 : 64];
-    float stack_t[(SMEM == 1 || SSTK) ? 1 : 64];
-    if (cur < 0)
-    {   // single-leaf tree: the root box is tested like any visited node
-        float4 r0 = __ldg(sc.nodes_ref), r1 = __ldg(sc.nodes_ref + 1);
-        f3 t0 = (mk3(r0) - o) * inv, t1 = (mk3(r1) - o) * inv;
-        float lo = fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z));
-        float hi = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
-        if (!(fminf(hi, t_max) >= fmaxf(lo, t_min))) return prim;
-    }
-    else
-    {   // root box test (the reference tests every node it visits, including the root)
-        float4 r0 = __ldg(sc.nodes_ref), r1 = __ldg(sc.nodes_ref + 1);
-        f3 t0 = (mk3(r0) - o) * inv, t1 = (mk3(r1) - o) * inv;
-        float lo = fmaxf(fmaxf(fminf(t0.x, t1.x), fminf(t0.y, t1.y)), fminf(t0.z, t1.z));
-        float hi = fminf(fminf(fmaxf(t0.x, t1.x), fmaxf(t0.y, t1.y)), fmaxf(t0.z, t1.z));
-        if (!(fminf(hi, t_max) >= fmaxf(lo, t_min))) return prim;
-    }
-    for (;;)
-    {
-        while (cur >= 0)
-        {
-            // SMEM == 2: `wnodes` is the staged top of the tree (records [0, sc.top_k)), deeper records come from sc.wnodes
-            const float4* np = (SMEM == 2 && (uint32_t)cur >= sc.top_k) ? sc.wnodes + (size_t)cur * 4 : wnodes + (size_t)cur * 4;
-            float4 a = ld_bvh<SMEM>(np), b = ld_bvh<SMEM>(np + 1), c = ld_bvh<SMEM>(np + 2), m = ld_bvh<SMEM>(np + 3);
-            // child 0 box: min (a.x,a.y,a.z) max (a.w,b.x,b.y); child 1 box: min (b.z,b.w,c.x) max (c.y,c.z,c.w)
-#ifdef RT_FMA_TRAVERSAL
-            // experiment (NOT bit-exact): contracted slab test, plane * inv - origin * inv in one FFMA per plane
-            const f3 noi = mk3(-(o.x * inv.x), -(o.y * inv.y), -(o.z * inv.z));
-            f3 t00 = mk3(__fmaf_rn(a.x, inv.x, noi.x), __fmaf_rn(a.y, inv.y, noi.y), __fmaf_rn(a.z, inv.z, noi.z));
-            f3 t01 = mk3(__fmaf_rn(a.w, inv.x, noi.x), __fmaf_rn(b.x, inv.y, noi.y), __fmaf_rn(b.y, inv.z, noi.z));
-            f3 t10 = mk3(__fmaf_rn(b.z, inv.x, noi.x), __fmaf_rn(b.w, inv.y, noi.y), __fmaf_rn(c.x, inv.z, noi.z));
-            f3 t11 = mk3(__fmaf_rn(c.y, inv.x, noi.x), __fmaf_rn(c.z, inv.y, noi.y), __fmaf_rn(c.w, inv.z, noi.z));
-#else
-            f3 t00 = (mk3(a.x, a.y, a.z) - o) * inv, t01 = (mk3(a.w, b.x, b.y) - o) * inv;
-            f3 t10 = (mk3(b.z, b.w, c.x) - o) * inv, t11 = (mk3(c.y, c.z, c.w) - o) * inv;
-#endif
-            float lo0 = fmaxf(fmaxf(fmaxf(fminf(t00.x, t01.x), fminf(t00.y, t01.y)), fminf(t00.z, t01.z)), t_min);
-            float hi0 = fminf(fminf(fmaxf(t00.x, t01.x), fmaxf(t00.y, t01.y)), fmaxf(t00.z, t01.z));
-            float lo1 = fmaxf(fmaxf(fmaxf(fminf(t10.x, t11.x), fminf(t10.y, t11.y)), fminf(t10.z, t11.z)), t_min);
-            float hi1 = fminf(fminf(fmaxf(t10.x, t11.x), fmaxf(t10.y, t11.y)), fmaxf(t10.z, t11.z));
-            bool h0 = fminf(hi0, t_max) >= lo0, h1 = fminf(hi1, t_max) >= lo1;
-            int r0 = __float_as_int(m.x), r1 = __float_as_int(m.y);
-            uint32_t axis = __float_as_uint(m.z);
-            bool swap = SMEM == 1 ? ((sign_bits >> axis) & 1u) != 0u : (axis == 0 ? sx : (axis == 1 ? sy : sz));   // near child = second iff inv_dir[axis] < 0
-            int near_ref = swap ? r1 : r0, far_ref = swap ? r0 : r1;
-            bool near_hit = swap ? h1 : h0, far_hit = swap ? h0 : h1;
-            float far_lo = swap ? lo0 : lo1;
-            if (near_hit)
-            {
-                if (far_hit)
-                {
-                    if (SSTK) sstk[sp * 256] = make_int2(far_ref, __float_as_int(far_lo));
-                    else if (SMEM == 1) stack[sp] = make_int2(far_ref, __float_as_int(far_lo));
-                    else { stack_ref[sp] = far_ref; stack_t[sp] = far_lo; }
-                    ++sp;
-                }
-                cur = near_ref;
-            }
-            else if (far_hit) cur = far_ref;
-            else
-            {   // pop: a pushed far child is re-tested against the (possibly shrunk) t_max, as the
-                // reference does when it pops it; its slab interval was already valid at push time
-                bool found = false;
-                while (sp > 0)
-                {
-                    --sp;
-                    if (SSTK) { int2 e = sstk[sp * 256]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
-                    else if (SMEM == 1) { int2 e = stack[sp]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
-                    else if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; }
-                }
-                if (!found) return prim;
-            }
-        }
-        // leaf: triangles [~cur ...] until the end-of-leaf flag
-        uint32_t ti = (uint32_t)(~cur);
-        for (;;)
-        {
-            const float4* tp = wtris + (size_t)ti * 3;
-            float4 q0 = ld_bvh<(SMEM == 1)>(tp), q1 = ld_bvh<(SMEM == 1)>(tp + 1), q2 = ld_bvh<(SMEM == 1)>(tp + 2);
-            f3 p1 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q0.w, q1.x, q1.y), e2 = mk3(q1.z, q1.w, q2.x);
-            bool last = __float_as_uint(q2.y) != 0u;
-#ifdef RT_FMA_TRAVERSAL
-#define RT_CROSS(a, b) mk3(__fmaf_rn((a).y, (b).z, -((a).z * (b).y)), __fmaf_rn((a).z, (b).x, -((a).x * (b).z)), __fmaf_rn((a).x, (b).y, -((a).y * (b).x)))
-#define RT_DOT(a, b) __fmaf_rn((a).x, (b).x, __fmaf_rn((a).y, (b).y, (a).z * (b).z))
-#else
-#define RT_CROSS(a, b) cross(a, b)
-#define RT_DOT(a, b) dot(a, b)
-#endif
-            f3 pvec = RT_CROSS(d, e2);
-            float det = RT_DOT(e1, pvec);
-            if (PIN) asm volatile("" : "+f"(det));
-            if (!(det < 1e-8f || -det > 1e-8f))
-            {
-                float inv_det = 1.0f / det;
-                f3 tvec = o - p1;
-                float u = RT_DOT(tvec, pvec) * inv_det;
-                if (!(u < 0.0f || u > 1.0f))
-                {
-                    f3 qvec = RT_CROSS(tvec, e1);
-                    float v = RT_DOT(d, qvec) * inv_det;
-                    if (!(v < 0.0f || u + v > 1.0f))
-                    {
-                        float t = RT_DOT(e2, qvec) * inv_det;
-                        if (!(t < t_min || t > t_max))
-                        {
-                            bu = u; bv = v; bt = t; prim = ti; t_max = t;
-                            if (ANY) return 0u;
-                        }
-                    }
-                }
-            }
-            if (last) break;
-            ++ti;
-        }
-        bool found = false;
-        while (sp > 0)
-                {
-                    --sp;
-                    if (SSTK) { int2 e = sstk[sp * 256]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
-                    else if (SMEM == 1) { int2 e = stack[sp]; if (t_max >= __int_as_float(e.y)) { cur = e.x; found = true; break; } }
-                    else if (t_max >= stack_t[sp]) { cur = stack_ref[sp]; found = true; break; }
-                }
-        if (!found) return prim;
-    }
-}
-
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ uint32_t trace(const DevScene& sc, int mode, f3 o, f3 d, float t_min, float t_max,
-                                          float& bu, float& bv, float& bt, uint32_t& nv, uint32_t& nt)
-{
-    if (mode == 0) return trace_literal<ANY, COUNT>(sc, o, d, t_min, t_max, bu, bv, bt, nv, nt);
-    return trace_fast<ANY, COUNT, 0>(sc, sc.wnodes, sc.wtris, o, d, t_min, t_max, bu, bv, bt, nv, nt);
-}
+#include "rt_kernel_types.cuh"
+#include "rt_traverse.cuh"
 
 // ------------------------------------------------------------------------------------ shading
 struct ShadeOut
@@ -936,279 +524,8 @@ __global__ void __launch_bounds__(256, RT_MINB_SHADE) k_shade_queues(FrameParams
     }
 }
 
-// ---- whole-frame kernel (RT_OPT_FRAME_KERNEL, default) ---------------------------------------------------------
-// ONE launch per frame.  Every CTA is an independent wavefront path tracer over its own subset of the partition's pixels
-// (groups of 32 consecutive local pixels, dealt round-robin to the resident CTAs), with its own region of every queue:
-// a path never leaves the CTA that generated its primary ray.  The per-bounce schedule is the one of rt_extend_shade /
-// rt_shadow_accumulate (integrator.cpp:27-59 fused the same way):
-//     T(b): closest-hit traversal of bounce b  +  shadow pass of bounce b-1   -> hit queue / miss queue
-//     S(b): shading of the hit queue, then of the miss queue                   -> shadow queue, ray queue of bounce b+1
-// but the queue cursors and counters live in SHARED memory and the phases are separated by __syncthreads(): no global
-// atomics on the ray path, no grid-wide synchronisation, no launch boundary between phases (the ~10-15 us floor that 22
-// dependent launches per frame cost a small multi-GPU partition), and the 4 CTAs of an SM are in different phases at any
-// time, so a CTA waiting for its slowest warp at a barrier leaves the issue slots to its neighbours.  Primary rays are
-// generated inside T(0) (no separate pass over the queue).  Results are bit-identical: every per-pixel quantity is a
-// function of (pixel, sample index, bounce) only, and the order of the additions into a pixel's radiance is unchanged.
-struct CtaFrame
-{
-    uint32_t cur_trace, cur_shade;           // work cursors of the current T / S phase
-    uint32_t ext_n[2], shadow_n[2];          // rays entering bounce b (parity b & 1), shadow rays spawned by S(b) (parity b & 1)
-    unsigned long long hm[2];                // hits (low word) and misses (high word) of T(b), parity b & 1
-    unsigned long long emit[2];              // shadow rays (low word) and continuation rays (high word) spawned by S(b): slot reservation
-    uint32_t n_emissive, n_unoccluded;
-    uint32_t ended_n[2];                     // fused gather: pixels whose path ended at a hit in S(b) (no continuation), parity b & 1
-};
+#include "rt_frame_kernel.cuh"
 
-template <int SMEM>
-__global__ void __launch_bounds__(RT_FRAME_MAX_THREADS, 1) k_frame(FrameParams p, DevScene sc, int mode, Queues q, DevCounters* ctr, float4* radiance,
-                                                              AovParams aov, uint32_t max_bounces, uint32_t slots_per_cta,
-                                                              const __grid_constant__ FrameDyn dyn)
-{
-    extern __shared__ __align__(128) float4 s_bvh[];
-    __shared__ uint64_t s_mbar;
-    __shared__ CtaFrame s;
-    p.dyn = &dyn;                                  // per-frame constants (sample index, camera) arrive as a kernel parameter
-    if (SMEM == 1) tma_stage_bvh(s_bvh, sc, &s_mbar);
-    if (SMEM == 2) tma_stage_top(s_bvh, sc.wnodes, sc.top_k, &s_mbar);
-    const int lane = threadIdx.x & 31;
-    const uint32_t base = blockIdx.x * slots_per_cta;          // this CTA's region of every queue: slots [base, base + slots_per_cta)
-    // (queue pointers are re-read from the kernel parameters where they are used: nothing but `base` stays live across the
-    // traversal and shading loops)
-#define FQ(plane, i) (q.plane)[base + (i)]
-    if (threadIdx.x == 0)
-    {
-        const uint32_t n_groups = (p.n_local + 31u) / 32u;
-        const uint32_t cta = blockIdx.x, n_cta = gridDim.x;
-        const uint32_t my_groups = cta < n_groups ? (n_groups - cta + n_cta - 1u) / n_cta : 0u;
-        s.cur_trace = 0; s.cur_shade = 0; s.ext_n[0] = my_groups * 32u; s.ext_n[1] = 0; s.shadow_n[0] = s.shadow_n[1] = 0;
-        s.hm[0] = s.hm[1] = 0ull; s.emit[0] = s.emit[1] = 0ull; s.n_emissive = 0; s.n_unoccluded = 0; s.ended_n[0] = s.ended_n[1] = 0;
-        if (blockIdx.x == 0) ctr->n_primary = p.n_local;
-    }
-    __syncthreads();
-    const uint32_t sample_idx = p.dyn->sample_idx;
-    uint32_t nv = 0, nt = 0;     // (not counted here: RT_OPT_COUNT_TRAVERSAL uses the per-phase kernels)
-
-    for (uint32_t b = 0; b <= max_bounces + 1u; ++b)
-    {
-        // ---------------------------------------------------------------- T(b): extension rays of bounce b, then shadow rays of bounce b-1
-        {
-            const int in = b & 1;
-            const uint32_t n_ext = b <= max_bounces ? s.ext_n[in] : 0u;          // the last round is the shadow pass of the last bounce only
-            const uint32_t ext_span = (n_ext + 31u) & ~31u;
-            const uint32_t n_sh = b == 0 ? 0u : s.shadow_n[(b - 1u) & 1];
-            const uint32_t total = ext_span + n_sh;
-            if (threadIdx.x == 0)
-            {   // state of the NEXT phases that nobody reads during this one
-                s.cur_shade = 0; s.ext_n[(b + 1u) & 1] = 0; s.shadow_n[in] = 0; s.emit[in] = 0ull; s.ended_n[in] = 0;
-            }
-            for (;;)
-            {
-                uint32_t at = 0;
-                if (lane == 0) at = atomicAdd(&s.cur_trace, 32u);
-                at = __shfl_sync(0xffffffffu, at, 0);
-                if (at >= total) break;
-                if (at < ext_span)
-                {
-                    const uint32_t i = at + lane;
-                    bool live = i < n_ext, hit = false;
-                    float bu = 0.0f, bv = 0.0f, bt = 0.0f;
-                    uint32_t prim = RT_INVALID_ID;
-                    float4 a, bb;
-                    if (b == 0)
-                    {   // RayGeneration (raygeneration.cl:65-139) fused into the first traversal pass; slot i <-> local pixel li
-                        const uint32_t li = (blockIdx.x + (i >> 5) * gridDim.x) * 32u + (uint32_t)lane;
-                        live = li < p.n_local;
-                        if (live)
-                        {
-                            const uint32_t px = li % p.width, py = (li / p.width) * p.world + p.rank;
-                            f3 o, d;
-                            generate_primary_ray(p.dyn->raygen, py * p.width + px, px, py, sample_idx, o, d);
-                            a = make_float4(o.x, o.y, o.z, __uint_as_float(pack_pixel(px, py)));
-                            bb = make_float4(d.x, d.y, d.z, RT_MAX_RENDER_DIST);
-                            FQ(A[0], i) = a; FQ(B[0], i) = bb; FQ(C[0], i) = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-                            if (aov.enabled)
-                            {   // raygeneration.cl:129-133
-                                aov.albedo[li] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                                aov.depth[li] = RT_MAX_RENDER_DIST;
-                                aov.normal[li] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                                aov.velocity[li] = make_float2(0.0f, 0.0f);
-                            }
-                        }
-                    }
-                    else if (live) { a = FQ(A[in], i); bb = FQ(B[in], i); }
-                    if (live)
-                    {
-                        if (SMEM == 1) prim = trace_fast<false, false, 1, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt);
-                        else if (SMEM == 2) prim = trace_fast<false, false, 2, true>(sc, s_bvh, sc.wtris, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt);
-                        else prim = trace<false, false>(sc, mode, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt);
-                        hit = prim != RT_INVALID_ID;
-                    }
-                    const unsigned hmask = __ballot_sync(0xffffffffu, hit);
-                    const unsigned mmask = __ballot_sync(0xffffffffu, live && !hit);
-                    unsigned long long slot = 0ull;
-                    if (lane == 0)
-                        slot = atomicAdd(&s.hm[in], (unsigned long long)__popc(hmask) | ((unsigned long long)__popc(mmask) << 32));
-                    slot = __shfl_sync(0xffffffffu, slot, 0);
-                    const unsigned lt_mask = (1u << lane) - 1u;
-                    if (hit) FQ(hitq, (uint32_t)slot + __popc(hmask & lt_mask)) = make_float4(bu, bv, __uint_as_float(prim), __uint_as_float(i));
-                    else if (live) FQ(missq, (uint32_t)(slot >> 32) + __popc(mmask & lt_mask)) = i;
-                }
-                else
-                {   // IntersectShadowRays + AccumulateDirectSamples of bounce b-1
-                    const uint32_t i = at - ext_span + lane;
-                    bool un = false;
-                    if (i < n_sh)
-                    {
-                        const float4 a = FQ(sA, i), bb = FQ(sB, i);
-                        float bu, bv, bt;
-                        if (SMEM == 1) un = trace_fast<true, false, 1, true>(sc, s_bvh, s_bvh + sc.wnodes_f4, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
-                        else if (SMEM == 2) un = trace_fast<true, false, 2, true>(sc, s_bvh, sc.wtris, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
-                        else un = trace<true, false>(sc, mode, mk3(a), mk3(bb), 0.0f, bb.w, bu, bv, bt, nv, nt) == RT_INVALID_ID;
-                        if (un)
-                        {
-                            const float4 c = FQ(sC, i);
-                            const uint32_t li = local_index(p, __float_as_uint(a.w));
-                            float4 r = radiance[li];
-                            r.x += c.x; r.y += c.y; r.z += c.z;
-                            radiance[li] = r;
-                        }
-                    }
-                    const unsigned umask = __ballot_sync(0xffffffffu, un);
-                    if (lane == 0 && umask) atomicAdd(&s.n_unoccluded, (uint32_t)__popc(umask));
-                }
-            }
-            __syncthreads();
-            if (p.gather && b > 0)
-            {   // fused gather: the shadow rays of bounce b-1 are accumulated, so the pixels whose path ended at a hit of S(b-1) are
-                // final; after the last round so are the paths that were still alive (their rays sit in the queue S(max) filled)
-                const int pin = (b - 1u) & 1;
-                const uint32_t n_end = s.ended_n[pin];
-                const uint32_t* list = pin ? (const uint32_t*)q.hits + base : q.shadow_flags + base;
-                for (uint32_t k = threadIdx.x; k < n_end; k += blockDim.x) { const uint32_t li = list[k]; p.gather[li] = radiance[li]; }
-                if (b > max_bounces)
-                {
-                    const uint32_t n_alive = s.ext_n[in];
-                    for (uint32_t k = threadIdx.x; k < n_alive; k += blockDim.x)
-                    {
-                        const uint32_t li = local_index(p, __float_as_uint(FQ(A[in], k).w));
-                        p.gather[li] = radiance[li];
-                    }
-                }
-            }
-            if (threadIdx.x == 0)
-            {   // per-bounce statistics (rt_read_frame_stats): one fire-and-forget global add per CTA and counter
-                const unsigned long long hm = s.hm[in];
-                if (b <= max_bounces && hm) atomicAdd((unsigned long long*)&ctr->hm[b], hm);
-                if (b > 0 && s.n_unoccluded) atomicAdd(&ctr->n_unoccluded[b - 1u], s.n_unoccluded);
-                s.n_unoccluded = 0;
-            }
-        }
-        if (b > max_bounces) break;
-        // ---------------------------------------------------------------- S(b): ShadeSurfaceHits over the hit queue, ShadeMissedRays over the miss queue
-        {
-            const int in = b & 1, out = (b + 1u) & 1;
-            const unsigned long long hm = s.hm[in];
-            const uint32_t n_hit = (uint32_t)hm, n_miss = (uint32_t)(hm >> 32);
-            const uint32_t hit_span = (n_hit + 31u) & ~31u;            // warps never mix hits and misses
-            const uint32_t total = hit_span + n_miss;
-            if (threadIdx.x == 0) { s.cur_trace = 0; s.hm[out] = 0ull; }
-            for (;;)
-            {
-                uint32_t at = 0;
-                if (lane == 0) at = atomicAdd(&s.cur_shade, 32u);
-                at = __shfl_sync(0xffffffffu, at, 0);
-                if (at >= total) break;
-                if (at < hit_span)
-                {
-                    const uint32_t k = at + lane;
-                    const bool hit = k < n_hit;
-                    uint32_t pixel = 0;
-                    ShadeOut so;
-                    so.emissive = so.spawn_next = so.spawn_shadow = false;
-                    if (hit)
-                    {
-                        const float4 h = FQ(hitq, k);
-                        const uint32_t i = __float_as_uint(h.w);
-                        const float4 a = FQ(A[in], i), bb = FQ(B[in], i), c = FQ(C[in], i);
-                        pixel = __float_as_uint(a.w);
-                        shade_hit(sc, p, aov, b, pixel, mk3(a), mk3(bb), mk3(c), __float_as_uint(h.z), h.x, h.y, so);
-                        if (so.emissive)
-                        {
-                            const uint32_t li = local_index(p, pixel);
-                            float4 r = radiance[li];
-                            r.x += so.emission_add.x; r.y += so.emission_add.y; r.z += so.emission_add.z;
-                            radiance[li] = r;
-                        }
-                    }
-                    const bool ss = hit && so.spawn_shadow, sn = hit && so.spawn_next;
-                    const unsigned smask = __ballot_sync(0xffffffffu, ss), nmask = __ballot_sync(0xffffffffu, sn);
-                    const unsigned emask = __ballot_sync(0xffffffffu, hit && so.emissive);
-                    unsigned long long slot = 0ull;
-                    if ((smask | nmask | emask) != 0u)
-                    {
-                        if (lane == 0)
-                        {
-                            slot = atomicAdd(&s.emit[in], (unsigned long long)__popc(smask) | ((unsigned long long)__popc(nmask) << 32));
-                            if (emask) atomicAdd(&s.n_emissive, (uint32_t)__popc(emask));
-                        }
-                        slot = __shfl_sync(0xffffffffu, slot, 0);
-                    }
-                    const unsigned lt_mask = (1u << lane) - 1u;
-                    if (p.gather)
-                    {   // paths that end at this hit (no continuation ray): final once their shadow ray is accumulated in T(b+1)
-                        const unsigned dmask = __ballot_sync(0xffffffffu, hit && !so.spawn_next);
-                        if (dmask)
-                        {
-                            uint32_t at0 = 0;
-                            if (lane == 0) at0 = atomicAdd(&s.ended_n[in], (uint32_t)__popc(dmask));
-                            at0 = __shfl_sync(0xffffffffu, at0, 0);
-                            if (hit && !so.spawn_next)
-                            {
-                                uint32_t* list = in ? (uint32_t*)q.hits + base : q.shadow_flags + base;
-                                list[at0 + __popc(dmask & lt_mask)] = local_index(p, pixel);
-                            }
-                        }
-                    }
-                    if (ss)
-                    {
-                        const uint32_t si = (uint32_t)slot + __popc(smask & lt_mask);
-                        FQ(sA, si) = make_float4(so.s_origin.x, so.s_origin.y, so.s_origin.z, __uint_as_float(pixel));
-                        FQ(sB, si) = make_float4(so.s_dir.x, so.s_dir.y, so.s_dir.z, so.s_tmax);
-                        FQ(sC, si) = make_float4(so.s_sample.x, so.s_sample.y, so.s_sample.z, 0.0f);
-                    }
-                    if (sn)
-                    {
-                        const uint32_t ni = (uint32_t)(slot >> 32) + __popc(nmask & lt_mask);
-                        FQ(A[out], ni) = make_float4(so.n_origin.x, so.n_origin.y, so.n_origin.z, __uint_as_float(pixel));
-                        FQ(B[out], ni) = make_float4(so.n_dir.x, so.n_dir.y, so.n_dir.z, RT_MAX_RENDER_DIST);
-                        FQ(C[out], ni) = make_float4(so.n_throughput.x, so.n_throughput.y, so.n_throughput.z, 0.0f);
-                    }
-                }
-                else
-                {
-                    const uint32_t k = at - hit_span + lane;
-                    if (k < n_miss)
-                    {
-                        const uint32_t i = FQ(missq, k);
-                        const float4 a = FQ(A[in], i), bb = FQ(B[in], i), c = FQ(C[in], i);
-                        shade_miss(sc, p, radiance, __float_as_uint(a.w), mk3(bb), mk3(c));
-                    }
-                }
-            }
-            __syncthreads();
-            if (threadIdx.x == 0)
-            {
-                const unsigned long long em = s.emit[in];
-                s.shadow_n[in] = (uint32_t)em; s.ext_n[out] = (uint32_t)(em >> 32);
-                if (em) atomicAdd((unsigned long long*)&ctr->emit[b], em);
-                if (s.n_emissive) atomicAdd(&ctr->n_emissive[b], s.n_emissive);
-                s.n_emissive = 0;
-            }
-            __syncthreads();
-        }
-    }
-}
-#undef FQ
 
 // resolve_radiance.cl:31-86: shaded colour (radiance / sample_count unless the denoiser is on, then Reinhard x/(1+x))
 // or one of the AOV views
@@ -1763,6 +1080,7 @@ int rt_set_partition(rt_ctx* c, uint32_t rank, uint32_t world)
         RT_FAIL(c, RT_ERR_UNSUPPORTED, "the temporal denoiser reprojects across the whole image and is not available with a multi-GPU partition");
     RT_CUDA(c, cudaSetDevice(c->device));
     c->rank = rank; c->world = world;
+    c->gather_slab = nullptr; c->gather_flag = nullptr;       // a gather target belongs to the partition it was set for
     return alloc_frame_buffers(c);
 }
 
@@ -2377,7 +1695,7 @@ int rt_resolve(rt_ctx* c, float* dst)
     RT_CHECK_CTX(c);
     if (!c->children.empty())
     {
-        if (c->present == 1)
+        if (c->present == 1 && dst)
         {   // the frame's ONE collective: radiance slabs -> first device over NVLink, resolved and read back there
             rt_ctx* k0 = c->children[0];
             bool pushed = true;              // did the frame kernels push this frame already (fused gather)?
