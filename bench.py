@@ -10,7 +10,8 @@ A "step" is one frame: Reset + Integrate with sample_idx = 0, so every step trac
 
 One process per GPU (torchrun for N > 1): the image is partitioned by scanline (row y -> rank y % N,
 weak in nothing: total work fixed => "strong" scaling), each rank runs the whole wavefront on its rows,
-and ONE NCCL gather of the radiance slabs to rank 0 ends the frame (inside the timed region).
+and ONE gather of the radiance slabs to rank 0 belongs to every frame (inside the timed region): an NCCL gather after the frame, or —
+above 4 ranks — the fused gather, in which the frame kernels store finished pixels into rank 0's buffer over NVLink peer memory.
 
 The JSON line carries: value (HBM-resident, device-timed, max over ranks), e2e (through the public API with
 host buffers: camera upload + frame + resolve + device->host image), roofline (dominant kernel, algorithmic
@@ -517,7 +518,7 @@ def main():
 
     def e2e_frame(parallel=False):
         ctx.set_camera(cam_host)                       # per-frame input (render.cpp:188): 64 B host -> device (kernel parameter)
-        frame()                                        # N > 1: ends with the NCCL gather of the radiance slabs to rank 0
+        frame()                                        # N > 1: includes the gather of the radiance slabs to rank 0 (NCCL or fused)
         if world == 1:
             ctx.resolve(host_np)                       # resolve + device->host of the image; blocks
         elif parallel:
@@ -665,11 +666,11 @@ def main():
                     "repetitions_ms_per_step": [round(x, 4) for x in e2e_reps], "h2d_bytes_per_step": 64,
                     "d2h_bytes_per_step": w * h * 16,          # the whole image reaches the host every step (N > 1: split over the ranks' links)
                     "api": ("rt_set_camera + rt_reset + rt_integrate + rt_resolve(host image), blocking per frame like ResolveRadiance/Finish(); best of 2 repetitions" if world == 1 else
-                            ("every rank: rt_set_camera + rt_reset + rt_integrate + NCCL gather to rank 0 + rt_resolve of its rows into ONE shared page-locked host "
+                            (f"every rank: rt_set_camera + rt_reset + rt_integrate + gather to rank 0 [{'fused' if R.fused is not None else 'NCCL'}] + rt_resolve of its rows into ONE shared page-locked host "
                              "image (N PCIe links) + barrier; blocking per frame" if shared is not None else
-                             "every rank: rt_set_camera + rt_reset + rt_integrate + NCCL gather to rank 0; rank 0: rt_resolve_gathered(whole host image), blocking per frame")),
+                             f"every rank: rt_set_camera + rt_reset + rt_integrate + gather to rank 0 [{'fused' if R.fused is not None else 'NCCL'}]; rank 0: rt_resolve_gathered(whole host image), blocking per frame")),
                     "gathered_value": (rays_per_frame / (e2e_gathered_ms * 1e-3) / 1e6) if e2e_gathered_ms else None,
-                    "gathered_api": "rank 0: rt_resolve_gathered(whole host image) after the NCCL gather (one PCIe link)" if e2e_gathered_ms else None,
+                    "gathered_api": "rank 0: rt_resolve_gathered(whole host image) after the gather (one PCIe link)" if e2e_gathered_ms else None,
                     "host_image_page_locked": (shared.pinned if shared is not None else True),
                     "pipelined_value": e2e_pipe_value, "pipelined_ms_per_step": float(e2e_pipe_ms[0]),
                     "pipelined_api": "same, with rt_resolve_async: image D2H of frame i overlaps frame i+1",
