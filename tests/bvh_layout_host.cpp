@@ -15,3 +15,13 @@ extern "C" int bvh_layout_build(const RtLinearBVHNode* nodes, uint64_t n_nodes, 
     *root_ref = wl.root_ref; *max_depth = wl.max_depth; *top_n = wl.top_n; *n_records = wl.nodes.size() / 4;
     return 0;
 }
+
+extern "C" void shade_records_build(const RtTriangle* tris, uint64_t n_tris, const RtPackedMaterial* mats, uint64_t n_mats,
+                                    const RtLight* lights, uint64_t n_lights, float* tri_out /* 28 per triangle */,
+                                    float* mat_out /* 16 per material */, float* light_out /* 8 per light */)
+{
+    std::vector<rtbvh::F4> rec;
+    rtbvh::build_tri_shade(tris, n_tris, rec); memcpy(tri_out, rec.data(), rec.size() * 16);
+    rtbvh::build_mat_rec(mats, n_mats, rec); memcpy(mat_out, rec.data(), rec.size() * 16);
+    rtbvh::build_light_rec(lights, n_lights, rec); memcpy(light_out, rec.data(), rec.size() * 16);
+}
