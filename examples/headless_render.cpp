@@ -5,25 +5,37 @@
  *
  *   g++ -std=c++17 -O2 -Iinclude -Iraytracing_b200/host examples/headless_render.cpp \
  *       -Lraytracing_b200 -lrt_host -lrt_b200 -Wl,-rpath,'$ORIGIN/../raytracing_b200' -o examples/headless_render
- *   examples/headless_render assets/CornellBox.obj assets/ibl/CGSkies_0036_free.hdr 1920 1080 64 out.pfm
+ *   examples/headless_render assets/CornellBox.obj assets/ibl/CGSkies_0036_free.hdr 1920 1080 64 out.pfm [all|d0,d1,...]
+ *
+ * The optional last argument spreads the frame over several GPUs of the node behind the same Render / Integrator objects
+ * ("all" = every CUDA device; the image is partitioned by scanline inside the library, rt_create_multi).
  *
  * Needs a B200 (there is no CPU fallback: Render's constructor throws without a CUDA device).
  */
 #include <cstdio>
 #include <cstdlib>
 #include <exception>
+#include <memory>
+#include <string>
+#include <vector>
 
 #include "render.hpp"
 
 int main(int argc, char** argv)
 {
-    if (argc < 7) { std::fprintf(stderr, "usage: %s scene.obj env.hdr width height samples out.pfm\n", argv[0]); return 2; }
+    if (argc < 7) { std::fprintf(stderr, "usage: %s scene.obj env.hdr width height samples out.pfm [all|d0,d1,...]\n", argv[0]); return 2; }
     const unsigned width = (unsigned)std::atoi(argv[3]), height = (unsigned)std::atoi(argv[4]), samples = (unsigned)std::atoi(argv[5]);
     try
     {
         rt_host::Scene scene(argv[1], 1.0f, false);
         scene.AddDirectionalLight({ -0.6f, -1.5f, 3.5f }, { 15.0f, 10.0f, 5.0f });                 // main.cpp:58
-        rt_host::Render render(width, height, rt_host::Render::RenderBackend::kCUDA, scene, argv[2]);
+        std::vector<int> devices;                                                                   // empty = every CUDA device of the node
+        bool multi = argc > 7;
+        if (multi && std::string(argv[7]) != "all")
+            for (const char* p = argv[7]; *p;) { devices.push_back(std::atoi(p)); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+        std::unique_ptr<rt_host::Render> owner(multi ? new rt_host::Render(width, height, rt_host::Render::RenderBackend::kCUDA, scene, argv[2], devices)
+                                                     : new rt_host::Render(width, height, rt_host::Render::RenderBackend::kCUDA, scene, argv[2]));
+        rt_host::Render& render = *owner;
         render.SetMaxBounces(8);
         for (unsigned s = 0; s < samples; ++s) render.RenderFrame();                               // one sample per frame, accumulated
         std::FILE* f = std::fopen(argv[6], "wb");
