@@ -231,10 +231,9 @@ def test_full_size_properties(name, w, h, mb, row_first, row_step):
         c.destroy()
 
 
-@pytest.mark.slow
 def test_full_size_synthetic_10m_triangles():
-    """BASELINE C5 at full size: 183 copies of ShaderBalls + ground = 10 026 572 triangles, 1920x1080, 8 bounces (scene build and
-    host BVH build take a minute: RT_TEST_SLOW=1).  Per-phase kernels == one-kernel frame on the whole frame, a band of 31 rows
+    """BASELINE C5 at full size: 183 copies of ShaderBalls + ground = 10 026 572 triangles, 1920x1080, 8 bounces (scene and host BVH
+    build included: ~30 s on the GPU box, profiles/r02_full_size_parity.txt).  Per-phase kernels == one-kernel frame on the whole frame, a band of 31 rows
     equals the oracle, and more than 90 % of the primary rays hit geometry."""
     from raytracing_b200 import scene_io, synthetic
     w, h, mb = 1920, 1080, 8
