@@ -6,8 +6,8 @@
  * yields (y, a, 0, 0)), rows top to bottom.
  *
  * Decoders written here (no third-party code): PNG (zlib inflate from the system library; colour types 0/2/3/4/6, bit depths
- * 1-16, tRNS, non-interlaced — Adam7 files are refused) and TGA (types 1/2/3/9/10/11: colour-mapped, true-colour 15/16/24/32 bit,
- * grey; RLE; either row order).  JPEG needs a Huffman/IDCT decoder and is refused loudly.
+ * 1-16, tRNS, Adam7 interlacing), TGA (types 1/2/3/9/10/11: colour-mapped, true-colour 15/16/24/32 bit, grey; RLE; either row
+ * order) and JPEG (jpeg_decoder.cpp).  The format is recognised by content, like the reference's loader does.
  */
 #include "reference_api.hpp"
 
@@ -86,44 +86,32 @@ bool load_png(const std::vector<unsigned char>& file, TextureImage& out, std::st
         pos += 12 + (size_t)len;
     }
     if (ctype < 0 || w == 0 || h == 0 || w > 32768 || h > 32768) { err = "bad PNG header"; return false; }
-    if (interlace) { err = "interlaced (Adam7) PNG files are not supported"; return false; }
+    if (interlace > 1) { err = "unknown PNG interlace method"; return false; }
     int src_channels;
     switch (ctype) { case 0: src_channels = 1; break; case 2: src_channels = 3; break; case 3: src_channels = 1; break;
                      case 4: src_channels = 2; break; case 6: src_channels = 4; break; default: err = "bad PNG colour type"; return false; }
     if (!(depth == 8 || depth == 16 || ((ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4)))) { err = "bad PNG bit depth"; return false; }
     if (ctype == 3 && (depth == 16 || palette.size() < 3)) { err = "bad PNG palette"; return false; }
-    const size_t bits_pp = (size_t)src_channels * depth;
-    const size_t stride = (w * bits_pp + 7) / 8, bpp = (bits_pp + 7) / 8;
-    std::vector<unsigned char> raw((stride + 1) * h);
+    const size_t bits_pp = (size_t)src_channels * depth, bpp = (bits_pp + 7) / 8;
+    // the image is stored as one pass, or as the seven Adam7 passes (each a complete filtered sub-image of the pixels
+    // x0 + i * dx, y0 + j * dy)
+    struct Pass { std::uint32_t x0, y0, dx, dy; };
+    static const Pass adam7[7] = { { 0, 0, 8, 8 }, { 4, 0, 8, 8 }, { 0, 4, 4, 8 }, { 2, 0, 4, 4 }, { 0, 2, 2, 4 }, { 1, 0, 2, 2 }, { 0, 1, 1, 2 } };
+    static const Pass whole = { 0, 0, 1, 1 };
+    const Pass* passes = interlace ? adam7 : &whole;
+    const int n_passes = interlace ? 7 : 1;
+    auto pass_w = [&](const Pass& ps) { return w > ps.x0 ? (w - ps.x0 + ps.dx - 1) / ps.dx : 0u; };
+    auto pass_h = [&](const Pass& ps) { return h > ps.y0 ? (h - ps.y0 + ps.dy - 1) / ps.dy : 0u; };
+    size_t raw_size = 0;
+    for (int i = 0; i < n_passes; ++i)
+        if (pass_w(passes[i]) && pass_h(passes[i])) raw_size += ((pass_w(passes[i]) * bits_pp + 7) / 8 + 1) * pass_h(passes[i]);
+    std::vector<unsigned char> raw(raw_size);
     {
         uLongf dst_len = (uLongf)raw.size();
         int rc = uncompress(raw.data(), &dst_len, idat.data(), (uLong)idat.size());
         if (rc != Z_OK || dst_len != raw.size()) { err = "PNG image data does not inflate to the image size"; return false; }
     }
-    // un-filter in place (each row: filter byte + stride bytes)
-    std::vector<unsigned char> lines(stride * h);
-    for (std::uint32_t y = 0; y < h; ++y)
-    {
-        const unsigned char* in = &raw[(stride + 1) * y];
-        unsigned char* cur = &lines[stride * y];
-        const unsigned char* up = y ? &lines[stride * (y - 1)] : nullptr;
-        int filter = in[0];
-        for (size_t x = 0; x < stride; ++x)
-        {
-            int a = x >= bpp ? cur[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= bpp) ? up[x - bpp] : 0, v = in[1 + x];
-            switch (filter)
-            {
-            case 0: break;
-            case 1: v += a; break;
-            case 2: v += b; break;
-            case 3: v += (a + b) >> 1; break;
-            case 4: v += paeth(a, b, c); break;
-            default: err = "bad PNG filter type"; return false;
-            }
-            cur[x] = (unsigned char)v;
-        }
-    }
-    // to 8-bit samples (16-bit: the high byte; 1/2/4-bit grey: scaled to 0..255; palette indices: kept), then expand
+    // to 8-bit samples (16-bit: the high byte; 1/2/4-bit grey: scaled to 0..255; palette indices: looked up)
     const bool has_trns = !trns.empty();
     int out_channels = ctype == 3 ? (has_trns ? 4 : 3) : src_channels + ((has_trns && (ctype == 0 || ctype == 2)) ? 1 : 0);
     std::vector<unsigned char> px((size_t)w * h * out_channels);
@@ -136,34 +124,67 @@ bool load_png(const std::vector<unsigned char>& file, TextureImage& out, std::st
     };
     auto sample16 = [&](const unsigned char* row, size_t index) -> unsigned { return depth == 16 ? (row[index * 2] << 8 | row[index * 2 + 1]) : sample(row, index); };
     const unsigned grey_scale = depth < 8 ? 255u / ((1u << depth) - 1u) : 1u;
-    for (std::uint32_t y = 0; y < h; ++y)
+    std::vector<unsigned char> lines;
+    size_t raw_pos = 0;
+    for (int pi = 0; pi < n_passes; ++pi)
     {
-        const unsigned char* row = &lines[stride * y];
-        unsigned char* o = &px[(size_t)y * w * out_channels];
-        for (std::uint32_t x = 0; x < w; ++x, o += out_channels)
+        const Pass& ps = passes[pi];
+        const std::uint32_t pw = pass_w(ps), ph = pass_h(ps);
+        if (!pw || !ph) continue;
+        const size_t stride = (pw * bits_pp + 7) / 8;
+        // un-filter (each row: filter byte + stride bytes)
+        lines.assign(stride * ph, 0);
+        for (std::uint32_t y = 0; y < ph; ++y)
         {
-            if (ctype == 3)
+            const unsigned char* in = &raw[raw_pos + (stride + 1) * y];
+            unsigned char* cur = &lines[stride * y];
+            const unsigned char* up = y ? &lines[stride * (y - 1)] : nullptr;
+            int filter = in[0];
+            for (size_t x = 0; x < stride; ++x)
             {
-                unsigned idx = sample(row, x);
-                if ((size_t)idx * 3 + 2 >= palette.size()) { err = "PNG palette index out of range"; return false; }
-                o[0] = palette[idx * 3]; o[1] = palette[idx * 3 + 1]; o[2] = palette[idx * 3 + 2];
-                if (has_trns) o[3] = idx < trns.size() ? trns[idx] : 255;
-            }
-            else
-            {
-                for (int c = 0; c < src_channels; ++c)
+                int a = x >= bpp ? cur[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= bpp) ? up[x - bpp] : 0, v = in[1 + x];
+                switch (filter)
                 {
-                    unsigned v = sample(row, (size_t)x * src_channels + c);
-                    o[c] = (unsigned char)(ctype == 0 && depth < 8 ? v * grey_scale : v);
+                case 0: break;
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) >> 1; break;
+                case 4: v += paeth(a, b, c); break;
+                default: err = "bad PNG filter type"; return false;
                 }
-                if (has_trns && ctype == 0 && trns.size() >= 2)
-                    o[1] = sample16(row, x) == (unsigned)((trns[0] << 8 | trns[1]) & (depth == 16 ? 0xFFFF : (1u << depth) - 1u)) ? 0 : 255;
-                if (has_trns && ctype == 2 && trns.size() >= 6)
+                cur[x] = (unsigned char)v;
+            }
+        }
+        raw_pos += (stride + 1) * ph;
+        for (std::uint32_t y = 0; y < ph; ++y)
+        {
+            const unsigned char* row = &lines[stride * y];
+            for (std::uint32_t x = 0; x < pw; ++x)
+            {
+                unsigned char* o = &px[((size_t)(ps.y0 + y * ps.dy) * w + (ps.x0 + x * ps.dx)) * out_channels];
+                if (ctype == 3)
                 {
-                    bool key = true;
-                    for (int c = 0; c < 3; ++c)
-                        key = key && sample16(row, (size_t)x * 3 + c) == (unsigned)((trns[c * 2] << 8 | trns[c * 2 + 1]) & (depth == 16 ? 0xFFFF : 0xFF));
-                    o[3] = key ? 0 : 255;
+                    unsigned idx = sample(row, x);
+                    if ((size_t)idx * 3 + 2 >= palette.size()) { err = "PNG palette index out of range"; return false; }
+                    o[0] = palette[idx * 3]; o[1] = palette[idx * 3 + 1]; o[2] = palette[idx * 3 + 2];
+                    if (has_trns) o[3] = idx < trns.size() ? trns[idx] : 255;
+                }
+                else
+                {
+                    for (int c = 0; c < src_channels; ++c)
+                    {
+                        unsigned v = sample(row, (size_t)x * src_channels + c);
+                        o[c] = (unsigned char)(ctype == 0 && depth < 8 ? v * grey_scale : v);
+                    }
+                    if (has_trns && ctype == 0 && trns.size() >= 2)
+                        o[1] = sample16(row, x) == (unsigned)((trns[0] << 8 | trns[1]) & (depth == 16 ? 0xFFFF : (1u << depth) - 1u)) ? 0 : 255;
+                    if (has_trns && ctype == 2 && trns.size() >= 6)
+                    {
+                        bool key = true;
+                        for (int c = 0; c < 3; ++c)
+                            key = key && sample16(row, (size_t)x * 3 + c) == (unsigned)((trns[c * 2] << 8 | trns[c * 2 + 1]) & (depth == 16 ? 0xFFFF : 0xFF));
+                        o[3] = key ? 0 : 255;
+                    }
                 }
             }
         }
@@ -274,12 +295,23 @@ bool LoadTextureImage(const char* filename, TextureImage& result, std::string& e
     std::string e(ext);
     for (char& c : e) c = (char)tolower((unsigned char)c);
     std::vector<unsigned char> file;
-    if (e == ".png" || e == ".tga")
+    if (e == ".png" || e == ".tga" || e == ".jpg")
     {
+        // the reference hands all three extensions to one loader that recognises the format by content (scene.cpp:302,
+        // image_loader.cpp:35): PNG signature, JPEG start-of-image, TGA otherwise
         if (!read_file(filename, file)) { error = "cannot read the file"; return false; }
-        return e == ".png" ? load_png(file, result, error) : load_tga(file, result, error);
+        static const unsigned char png_sig[4] = { 137, 80, 78, 71 };
+        if (file.size() >= 4 && memcmp(file.data(), png_sig, 4) == 0) return load_png(file, result, error);
+        if (file.size() >= 2 && file[0] == 0xFF && file[1] == 0xD8)
+        {
+            int w = 0, h = 0, nc = 0;
+            std::vector<unsigned char> px;
+            if (!DecodeJpeg(file.data(), file.size(), w, h, nc, px, error)) return false;
+            pack(px, w, h, nc, result);
+            return true;
+        }
+        return load_tga(file, result, error);
     }
-    if (e == ".jpg" || e == ".jpeg") { error = "JPEG textures need a JPEG decoder, which this loader does not have: convert the texture to PNG or TGA"; return false; }
     error = "unsupported texture file type (the reference accepts .jpg, .tga and .png, scene.cpp:302)";
     return false;
 }

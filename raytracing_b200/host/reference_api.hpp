@@ -107,6 +107,9 @@ struct TextureImage
     std::vector<std::uint32_t> data;
 };
 bool LoadTextureImage(const char* filename, TextureImage& result, std::string& error);
+// JPEG file in memory -> interleaved 8-bit pixels, `channels` = 3 (colour) or 1 (greyscale), in the arithmetic of the reference's
+// decoder (jpeg_decoder.cpp)
+bool DecodeJpeg(const unsigned char* file, size_t size, int& w, int& h, int& channels, std::vector<unsigned char>& pixels, std::string& error);
 
 // Radiance .hdr reader with the reference's conversion (loaders/hdr_loader.cpp:29-120):
 // rows in file order, value = (mantissa / 256) * 2^(e - 128), alpha left 0.

@@ -145,7 +145,7 @@ def test_image_textures_png_tga(tmp_path):
     """map_* textures: PNG (grey 1/8/16 bit, grey+alpha, RGB, RGBA, palette with and without tRNS, every row
     filter) and TGA (24/32 bit, grey, RLE, both row orders) decoded by host/image_loader.cpp into the reference's texel words,
     checked against PIL's decode packed like LoadSTB; texture indices in the order scene.cpp:155-186 loads them; same file -> one
-    texture; JPEG fails loudly."""
+    texture; an arithmetic-coded JPEG fails loudly."""
     from PIL import Image
     rng = np.random.default_rng(5)
     imgs = {}
@@ -203,9 +203,123 @@ def test_image_textures_png_tga(tmp_path):
     assert (m["ior_emission_idx_transparency"][5] >> 24) == tex_of[files[5]]         # material 5: map_d
     assert (m["diffuse_albedo"][1] >> 24) == 0xFF                                    # no diffuse texture there
     s.close()
-    Image.fromarray(rnd((4, 4, 3)), "RGB").save(str(tmp_path / "x.jpg"))
+    with open(tmp_path / "x.jpg", "wb") as f:                        # start-of-image, then nothing a decoder can use
+        f.write(b"\xff\xd8\xff\xc9\x00\x04\x00\x00\xff\xd9")
     with pytest.raises(hostapi.HostError, match="JPEG"):
         hostapi.HostScene(_textured_obj(tmp_path, ["x.jpg"]))
+
+
+TEXTURE_DIR = os.path.join(REPO, "tests", "golden", "textures")
+
+
+def _load_texture_files(directory, names, tmp_path):
+    """{name: (width, height, texels)} through the C++ Scene loader: one material per file, files looked up next to the OBJ."""
+    for n in names:
+        if not os.path.exists(tmp_path / n):
+            os.symlink(os.path.join(directory, n), tmp_path / n)
+    with open(tmp_path / "t.mtl", "w") as f:
+        for k, n in enumerate(names):
+            f.write(f"newmtl m{k}\nKd 0.5 0.5 0.5\nmap_Kd {n}\n")
+    with open(tmp_path / "t.obj", "w") as f:
+        f.write("mtllib t.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nvt 0 0\n")
+        for k in range(len(names)):
+            f.write(f"usemtl m{k}\nf 1/1/1 2/1/1 3/1/1\n")
+    s = hostapi.HostScene(str(tmp_path / "t.obj"))
+    s.add_directional_light((0, 0, 1), (1, 1, 1))
+    s.finalize(env=np.zeros(4, dtype=np.float32), env_width=1, env_height=1)
+    a = s.arrays()
+    assert len(a["textures"]) == len(names)
+    out = {}
+    for k, n in enumerate(names):
+        t = a["textures"][k]
+        count = int(t["width"]) * int(t["height"])
+        out[n] = (int(t["width"]), int(t["height"]), a["texels"][int(t["data_start"]): int(t["data_start"]) + count].copy())
+    s.close()
+    return out
+
+
+def test_texture_files_decode_like_the_reference(tmp_path):
+    """JPEG (baseline / progressive, every chroma layout Pillow writes, greyscale, CMYK, restart intervals) and Adam7 PNG files
+    through host/jpeg_decoder.cpp + host/image_loader.cpp against the texel words the reference's own loader (stb_image via
+    LoadSTB) produced for the same files (tests/golden/make_texture_fixtures.py).  A JPEG stream does not pin the inverse DCT,
+    the chroma filter or the colour conversion — these fixtures do."""
+    expected = np.load(os.path.join(TEXTURE_DIR, "expected.npz"))
+    names = sorted(k[:-len(":size")] for k in expected.files if k.endswith(":size"))
+    assert len(names) >= 50 and all(os.path.exists(os.path.join(TEXTURE_DIR, n)) for n in names)
+    got = _load_texture_files(TEXTURE_DIR, names, tmp_path)
+    for n in names:
+        w, h, texels = got[n]
+        assert (w, h) == tuple(expected[n + ":size"]), n
+        assert np.array_equal(texels, expected[n + ":texels"]), n
+    # the interlaced-PNG writer of the fixture script, against Pillow on the file it can read back
+    from PIL import Image
+    for n in ("plain_rgb8.png", "a7_rgb8.png", "a7_rgba8.png", "a7_ga8.png", "a7_pal4.png"):
+        im = Image.open(os.path.join(TEXTURE_DIR, n))
+        assert np.array_equal(_pack_like_stb(im.convert("RGB") if im.mode == "P" else im), expected[n + ":texels"]), n
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_ASSETS), reason="the reference's own loader only exists in the build container")
+def test_image_textures_match_the_reference_loader(tmp_path):
+    """The same textured OBJ through the reference's own Scene (tinyobj + LoadSTB, compiled into oracle/_ref) and through
+    host/image_loader.cpp: Texture[] records, texel words and packed material words identical (scene.cpp:155-186,276-300)."""
+    from PIL import Image
+    from oracle import refbind
+    if not refbind.available():
+        pytest.skip("oracle/_ref/libref.so not built")
+    rng = np.random.default_rng(21)
+
+    def rnd(shape, dtype=np.uint8, hi=256):
+        return rng.integers(0, hi, size=shape).astype(dtype)
+    imgs = {
+        "rgb.png": Image.fromarray(rnd((21, 34, 3)), "RGB"),
+        "rgba.png": Image.fromarray(rnd((16, 16, 4)), "RGBA"),
+        "grey.png": Image.fromarray(rnd((9, 13)), "L"),
+        "la.png": Image.fromarray(rnd((8, 8, 2)), "LA"),
+        "rgb.tga": Image.fromarray(rnd((12, 10, 3)), "RGB"),
+        "rgba_rle.tga": Image.fromarray(np.repeat(rnd((6, 5, 4)), 4, axis=1), "RGBA"),
+        "grey.tga": Image.fromarray(rnd((4, 7)), "L"),
+    }
+    pal = Image.fromarray(rnd((10, 12), hi=16), "P"); pal.putpalette(list(rnd(48)))
+    imgs["pal.png"] = pal
+    palt = Image.fromarray(rnd((6, 9), hi=4), "P"); palt.putpalette(list(rnd(12)))
+    imgs["pal_trns.png"] = palt
+    imgs["grey16.png"] = Image.fromarray(rnd((5, 9), np.uint16, 65536))
+    imgs["bits1.png"] = Image.fromarray(rnd((11, 19), hi=2) * 255, "L").convert("1")
+    for name, im in imgs.items():
+        if name == "rgba_rle.tga":
+            im.save(str(tmp_path / name), compression="tga_rle")
+        elif name == "pal_trns.png":
+            im.save(str(tmp_path / name), transparency=bytes([0, 128, 255, 7]))
+        else:
+            im.save(str(tmp_path / name))
+    obj = _textured_obj(tmp_path, list(imgs))
+    g = refbind.RefRenderer().open_obj("/root/reference", obj).scene()        # absolute OBJ path; the CWD only serves Finalize()
+    s = hostapi.HostScene(obj)
+    s.add_directional_light((-0.6, -1.5, 3.5), (15, 10, 5))
+    s.build_bvh()
+    s.finalize(env_path=os.path.join(REF_ASSETS, "ibl", "CGSkies_0036_free.hdr"))
+    a = s.arrays()
+    assert len(g["textures"]) == len(imgs)
+    for f in ("width", "height", "data_start"):                   # the record's padding word is uninitialised in the reference
+        assert np.array_equal(a["textures"][f], g["textures"][f]), f
+    assert np.array_equal(a["texels"], g["texels"])
+    assert a["materials"].tobytes() == g["materials"].tobytes()
+    assert np.array_equal(a["triangles"]["mtlIndex"], g["triangles"]["mtlIndex"])
+    for v in ("v1", "v2", "v3"):
+        assert np.array_equal(bits(a["triangles"][v]["texcoord"][:, :2]), bits(g["triangles"][v]["texcoord"][:, :2]))
+    s.close()
+    # freshly generated JPEG / Adam7 files (another seed than the committed fixtures) and the JPEG the reference ships
+    import shutil
+    from tests.golden import make_texture_fixtures as mk
+    fresh = tmp_path / "fresh"
+    names = mk.make_files(str(fresh), np.random.default_rng(77))
+    shutil.copy(os.path.join(REF_ASSETS, "checker3.jpg"), fresh / "checker3.jpg")
+    names.append("checker3.jpg")
+    ref = mk.reference_texels(str(fresh), names)
+    work = tmp_path / "work"; work.mkdir()
+    got = _load_texture_files(str(fresh), names, work)
+    for n in names:
+        assert got[n][:2] == ref[n][:2] and np.array_equal(got[n][2], ref[n][2]), n
 
 
 @pytest.mark.gpu
