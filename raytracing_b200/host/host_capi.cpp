@@ -3,6 +3,7 @@
  * them (ctypes): scene loading, BVH build, and the headless Render with RenderBackend::kCUDA.  Not part of
  * the reference-facing boundary (that is include/rt_b200.h + the C++ classes); test/bench plumbing only.
  */
+#include "obj_reader.hpp"
 #include <cstring>
 #include <memory>
 #include <string>
@@ -104,6 +105,12 @@ int rth_bvh_build(RtTriangle* triangles, size_t n, RtLinearBVHNode* nodes_out, s
         return 0;
     }
     catch (std::exception& e) { g_error = e.what(); return -1; }
+}
+
+// One number token in the OBJ reader's arithmetic (obj_reader.cpp ParseDouble): 1 = parsed, 0 = not a number
+int rth_obj_parse_number(const char* text, double* out)
+{
+    return obj::ParseDouble(text, text + strlen(text), out) ? 1 : 0;
 }
 
 int rth_default_camera(std::uint32_t width, std::uint32_t height, RtCamera* out)

@@ -4,6 +4,7 @@
  *   Integrator (the per-frame wavefront schedule and the base-class setters)
  */
 #include "reference_api.hpp"
+#include "obj_reader.hpp"
 
 #include <cmath>
 #include <cstdio>
@@ -64,98 +65,10 @@ std::uint32_t PackIorEmissionIdxTransparency(float ior, std::uint32_t ei, float 
     return ((std::uint32_t)(ior * 25.5f)) | (ei << 8) | ((std::uint32_t)(transparency * 255.0f) << 16) | (ti << 24);
 }
 
-struct MtlRecord
-{   // tinyobjloader defaults, tiny_obj_loader.h:1331-1340
-    float diffuse[3] = { 0, 0, 0 }, specular[3] = { 0, 0, 0 }, transmittance[3] = { 0, 0, 0 }, emission[3] = { 0, 0, 0 };
-    float ior = 1.0f, roughness = 0.0f, metallic = 0.0f;
-    // tinyobjloader's texture names (tiny_obj_loader.h: map_Kd, map_Ks, map_Pr, map_Pm, map_Ke, map_d)
-    std::string diffuse_tex, specular_tex, roughness_tex, metallic_tex, emissive_tex, alpha_tex;
-};
-
-// "map_Xx [-options ...] file name": the texture name is what follows the options (tinyobjloader parses -blendu, -o, -s, ... and
-// keeps the rest of the line); options with their numeric arguments are skipped here
-std::string texture_name(const char* p)
-{
-    std::string rest(p);
-    while (!rest.empty() && (rest.back() == '\r' || rest.back() == ' ' || rest.back() == '\t')) rest.pop_back();
-    size_t i = 0;
-    for (;;)
-    {
-        while (i < rest.size() && (rest[i] == ' ' || rest[i] == '\t')) ++i;
-        if (i < rest.size() && rest[i] == '-' && i + 1 < rest.size() && isalpha((unsigned char)rest[i + 1]))
-        {   // option: skip its name and the numeric / on / off arguments that follow
-            while (i < rest.size() && rest[i] != ' ' && rest[i] != '\t') ++i;
-            for (;;)
-            {
-                size_t j = i;
-                while (j < rest.size() && (rest[j] == ' ' || rest[j] == '\t')) ++j;
-                size_t k = j;
-                while (k < rest.size() && rest[k] != ' ' && rest[k] != '\t') ++k;
-                std::string tok = rest.substr(j, k - j);
-                char* end = nullptr;
-                bool numeric = !tok.empty() && (std::strtod(tok.c_str(), &end), end && *end == 0);
-                if (numeric || tok == "on" || tok == "off") i = k; else break;
-            }
-            continue;
-        }
-        break;
-    }
-    return rest.substr(i);
-}
-
 std::string dirname_of(const std::string& p)
 {
     size_t s = p.find_last_of("/\\");
     return s == std::string::npos ? std::string() : p.substr(0, s);
-}
-
-float parse_real(const char*& p)
-{
-    char* end = nullptr;
-    double v = std::strtod(p, &end);
-    p = end;
-    return (float)v;
-}
-
-void parse_mtl(const std::string& path, std::vector<MtlRecord>& mats, std::map<std::string, int>& index)
-{
-    std::ifstream f(path);
-    if (!f) return;      // tinyobjloader only warns when the .mtl is missing
-    std::string line;
-    MtlRecord* cur = nullptr;
-    while (std::getline(f, line))
-    {
-        const char* p = line.c_str();
-        while (*p == ' ' || *p == '\t') ++p;
-        if (*p == '#' || *p == 0) continue;
-        auto key = [&](const char* k) { size_t n = strlen(k); return strncmp(p, k, n) == 0 && (p[n] == ' ' || p[n] == '\t'); };
-        if (key("newmtl"))
-        {
-            std::string name(p + 7);
-            while (!name.empty() && (name.back() == '\r' || name.back() == ' ' || name.back() == '\t')) name.pop_back();
-            size_t b = name.find_first_not_of(" \t");
-            name = b == std::string::npos ? std::string() : name.substr(b);
-            index[name] = (int)mats.size();
-            mats.push_back(MtlRecord());
-            cur = &mats.back();
-            continue;
-        }
-        if (!cur) continue;
-        auto read3 = [&](const char* q, float* out) { out[0] = parse_real(q); out[1] = parse_real(q); out[2] = parse_real(q); };
-        if (key("Kd")) read3(p + 2, cur->diffuse);
-        else if (key("Ks")) read3(p + 2, cur->specular);
-        else if (key("Ke")) read3(p + 2, cur->emission);
-        else if (key("Kt") || key("Tf")) read3(p + 2, cur->transmittance);
-        else if (key("Ni")) { const char* q = p + 2; cur->ior = parse_real(q); }
-        else if (key("Pr")) { const char* q = p + 2; cur->roughness = parse_real(q); }
-        else if (key("Pm")) { const char* q = p + 2; cur->metallic = parse_real(q); }
-        else if (key("map_Kd")) cur->diffuse_tex = texture_name(p + 6);
-        else if (key("map_Ks")) cur->specular_tex = texture_name(p + 6);
-        else if (key("map_Pr")) cur->roughness_tex = texture_name(p + 6);
-        else if (key("map_Pm")) cur->metallic_tex = texture_name(p + 6);
-        else if (key("map_Ke")) cur->emissive_tex = texture_name(p + 6);
-        else if (key("map_d")) cur->alpha_tex = texture_name(p + 5);
-    }
 }
 
 } // namespace
@@ -172,75 +85,20 @@ Scene::Scene(std::vector<Triangle> triangles, std::vector<PackedMaterial> materi
         if (t.mtlIndex >= materials_.size()) throw std::runtime_error("Scene: triangle references a missing material");
 }
 
-// scene.cpp:127-274
+// scene.cpp:127-274: the OBJ reader's output (obj_reader.cpp stands in for tinyobjloader) -> packed materials + triangles
 void Scene::Load(const char* filename, float scale, bool flip_yz)
 {
-    std::ifstream f(filename);
-    if (!f) throw std::runtime_error("Failed to load the scene!");
-    std::string folder = dirname_of(filename);
-
-    std::vector<float> positions, normals, texcoords;
-    std::vector<MtlRecord> mtls;
-    std::map<std::string, int> mtl_index;
-    struct Corner { int v, vt, vn; };
-    struct Face { Corner c[3]; int material; };
-    std::vector<Face> faces;
-    int current_material = -1;
-
-    std::string line;
-    while (std::getline(f, line))
-    {
-        const char* p = line.c_str();
-        while (*p == ' ' || *p == '\t') ++p;
-        if (p[0] == 'v' && (p[1] == ' ' || p[1] == '\t')) { const char* q = p + 1; for (int i = 0; i < 3; ++i) positions.push_back(parse_real(q)); }
-        else if (p[0] == 'v' && p[1] == 'n' && (p[2] == ' ' || p[2] == '\t')) { const char* q = p + 2; for (int i = 0; i < 3; ++i) normals.push_back(parse_real(q)); }
-        else if (p[0] == 'v' && p[1] == 't' && (p[2] == ' ' || p[2] == '\t')) { const char* q = p + 2; for (int i = 0; i < 2; ++i) texcoords.push_back(parse_real(q)); }
-        else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t'))
-        {
-            const char* q = p + 1;
-            std::vector<Corner> corners;
-            for (;;)
-            {
-                while (*q == ' ' || *q == '\t') ++q;
-                if (*q == 0 || *q == '\r' || *q == '\n') break;
-                Corner c = { 0, 0, 0 };
-                char* end;
-                c.v = (int)strtol(q, &end, 10); q = end;
-                if (*q == '/') { ++q; if (*q != '/') { c.vt = (int)strtol(q, &end, 10); q = end; } if (*q == '/') { ++q; c.vn = (int)strtol(q, &end, 10); q = end; } }
-                // OBJ indices are 1-based; negative = relative to the end
-                auto fix = [](int idx, size_t n) { return idx > 0 ? idx - 1 : (idx < 0 ? (int)n + idx : -1); };
-                c.v = fix(c.v, positions.size() / 3); c.vt = fix(c.vt, texcoords.size() / 2); c.vn = fix(c.vn, normals.size() / 3);
-                corners.push_back(c);
-            }
-            // fan triangulation of polygons (the shipped assets are already triangulated)
-            for (size_t k = 2; k < corners.size(); ++k)
-                faces.push_back(Face{ { corners[0], corners[k - 1], corners[k] }, current_material });
-        }
-        else if (strncmp(p, "usemtl", 6) == 0 && (p[6] == ' ' || p[6] == '\t'))
-        {
-            std::string name(p + 7);
-            while (!name.empty() && (name.back() == '\r' || name.back() == ' ' || name.back() == '\t')) name.pop_back();
-            size_t b = name.find_first_not_of(" \t");
-            name = b == std::string::npos ? std::string() : name.substr(b);
-            auto it = mtl_index.find(name);
-            current_material = it == mtl_index.end() ? -1 : it->second;
-        }
-        else if (strncmp(p, "mtllib", 6) == 0 && (p[6] == ' ' || p[6] == '\t'))
-        {
-            std::string name(p + 7);
-            while (!name.empty() && (name.back() == '\r' || name.back() == ' ' || name.back() == '\t')) name.pop_back();
-            size_t b = name.find_first_not_of(" \t");
-            name = b == std::string::npos ? std::string() : name.substr(b);
-            parse_mtl(folder.empty() ? name : folder + "/" + name, mtls, mtl_index);
-        }
-    }
+    const std::string folder = dirname_of(filename);
+    obj::Mesh mesh;
+    std::string why;
+    if (!obj::Read(filename, folder, mesh, why)) throw std::runtime_error("Failed to load the scene! " + why);
 
     const float kGamma = 2.2f;
     const std::uint32_t kInvalidTextureIndex = 0xFF;
-    materials_.resize(mtls.size());
-    for (size_t i = 0; i < mtls.size(); ++i)
+    materials_.resize(mesh.materials.size());
+    for (size_t i = 0; i < mesh.materials.size(); ++i)
     {
-        const MtlRecord& m = mtls[i];
+        const obj::Material& m = mesh.materials[i];
         // scene.cpp:155-186: textures are loaded in this order (diffuse, specular, roughness, metallic, emissive, alpha), which fixes
         // their indices
         auto tex = [&](const std::string& name) -> std::uint32_t {
@@ -257,15 +115,21 @@ void Scene::Load(const char* filename, float scale, bool flip_yz)
     }
 
     auto flip = [flip_yz](float3& v) { if (flip_yz) { float t = v.y; v.y = v.z; v.z = t; v.y = -v.y; } };
-    triangles_.reserve(faces.size());
-    for (const Face& face : faces)
+    const std::vector<float>& positions = mesh.positions;
+    const std::vector<float>& normals = mesh.normals;
+    const std::vector<float>& texcoords = mesh.texcoords;
+    const size_t n_faces = mesh.indices.size() / 3;
+    triangles_.reserve(n_faces);
+    for (size_t face = 0; face < n_faces; ++face)
     {
         Triangle t;
         memset(&t, 0, sizeof(t));
         Vertex* vs[3] = { &t.v1, &t.v2, &t.v3 };
         for (int k = 0; k < 3; ++k)
         {
-            const Corner& c = face.c[k];
+            const obj::Index& c = mesh.indices[face * 3 + k];
+            // (the reference indexes its arrays unchecked here, scene.cpp:203-241: a missing vertex or normal is undefined behaviour
+            // there and an error here)
             if (c.v < 0 || (size_t)c.v * 3 + 2 >= positions.size()) throw std::runtime_error("OBJ face references a missing vertex");
             if (c.vn < 0 || (size_t)c.vn * 3 + 2 >= normals.size()) throw std::runtime_error("OBJ face has no normal (normals are required, scene.cpp:222-224)");
             if (c.vt >= 0 && (size_t)c.vt * 2 + 1 >= texcoords.size()) throw std::runtime_error("OBJ face references a missing texture coordinate");
@@ -275,7 +139,8 @@ void Scene::Load(const char* filename, float scale, bool flip_yz)
             v.texcoord = make_float3(c.vt < 0 ? 0.0f : texcoords[c.vt * 2 + 0], c.vt < 0 ? 0.0f : texcoords[c.vt * 2 + 1], 0.0f);
             flip(v.position); flip(v.normal);
         }
-        t.mtlIndex = (face.material >= 0 && (size_t)face.material < materials_.size()) ? (std::uint32_t)face.material : 0u;
+        const int material = mesh.material_ids[face];
+        t.mtlIndex = (material >= 0 && (size_t)material < materials_.size()) ? (std::uint32_t)material : 0u;
         triangles_.push_back(t);
     }
 }

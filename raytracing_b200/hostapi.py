@@ -37,6 +37,7 @@ def load_library():
     L.rth_scene_query.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.rth_bvh_build.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
     L.rth_default_camera.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+    L.rth_obj_parse_number.argtypes = [C.c_char_p, C.POINTER(C.c_double)]
     L.rth_render_create.restype = C.c_void_p
     L.rth_render_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_int, C.c_int]
     L.rth_render_free.argtypes = [C.c_void_p]
@@ -67,6 +68,12 @@ def default_camera(width, height):
     cam = np.zeros((), dtype=CAMERA_DT)
     load_library().rth_default_camera(width, height, cam.ctypes.data)
     return cam
+
+
+def obj_parse_number(text: str):
+    """A number token as the OBJ reader reads it (the reference loader's digit accumulation, not strtod); None = not a number."""
+    v = C.c_double()
+    return v.value if load_library().rth_obj_parse_number(text.encode(), C.byref(v)) else None
 
 
 def build_bvh(triangles):

@@ -1,0 +1,48 @@
+#!/usr/bin/env python3
+"""
+tests/golden/make_obj_fixtures.py — what the REFERENCE's own scene loader (tinyobjloader + Scene::Load + Bvh::BuildCPU,
+compiled into oracle/_ref) makes of the OBJ / MTL inputs of tests/obj_cases.py.
+
+    python tests/golden/make_obj_fixtures.py          (where /root/reference and oracle/_ref/libref.so exist)
+
+Writes tests/golden/obj/expected.npz: per case the triangle array (leaf order of the reference's BVH), the packed materials
+and the texture table.  tests/test_host.py::test_obj_reader_cases_load_like_the_reference loads the same inputs (re-created
+from tests/obj_cases.py, nothing but the expectations is stored) through host/obj_reader.cpp and compares.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, REPO)
+from tests import obj_cases  # noqa: E402
+
+OUT = os.path.join(REPO, "tests", "golden", "obj")
+
+
+def all_cases():
+    for name, files in obj_cases.QUIRK_CASES.items():
+        yield name, files
+    for seed, features in obj_cases.RANDOM_CASES:
+        yield "random_%d_%s" % (seed, "_".join(features) or "plain"), obj_cases.random_scene(seed, features)
+
+
+def main():
+    from oracle.refbind import RefRenderer
+    os.makedirs(OUT, exist_ok=True)
+    arrays = {}
+    for name, files in all_cases():
+        with tempfile.TemporaryDirectory() as tmp:
+            obj = obj_cases.write_case(tmp, files)
+            sc = RefRenderer().open_obj("/root/reference", obj).scene()
+        arrays[name + ":triangles"] = sc["triangles"]
+        arrays[name + ":materials"] = sc["materials"]
+        arrays[name + ":textures"] = sc["textures"]
+        print(f"{name:60s} {len(sc['triangles']):4d} triangles {len(sc['materials'])} materials {len(sc['textures'])} textures")
+    np.savez_compressed(os.path.join(OUT, "expected.npz"), **arrays)
+
+
+if __name__ == "__main__":
+    main()

@@ -209,6 +209,84 @@ def test_image_textures_png_tga(tmp_path):
         hostapi.HostScene(_textured_obj(tmp_path, ["x.jpg"]))
 
 
+def _scene_arrays_from_obj(obj_path):
+    s = hostapi.HostScene(obj_path)
+    s.add_directional_light((-0.6, -1.5, 3.5), (15, 10, 5))
+    s.build_bvh()
+    s.finalize(env=np.zeros(4, dtype=np.float32), env_width=1, env_height=1)
+    a = s.arrays()
+    s.close()
+    return a
+
+
+def _same_scene_arrays(a, g):
+    """None, or what differs between the loader's arrays `a` and the reference's `g` (triangles, materials, texture table)."""
+    if len(a["triangles"]) != len(g["triangles"]):
+        return "triangle count %d, expected %d" % (len(a["triangles"]), len(g["triangles"]))
+    for v in ("v1", "v2", "v3"):
+        for f in ("position", "texcoord", "normal"):
+            if not np.array_equal(bits(a["triangles"][v][f][:, :3]), bits(g["triangles"][v][f][:, :3])):
+                return v + "." + f
+    if not np.array_equal(a["triangles"]["mtlIndex"], g["triangles"]["mtlIndex"]):
+        return "mtlIndex"
+    if a["materials"].tobytes() != g["materials"].tobytes():
+        return "materials"
+    for f in ("width", "height", "data_start"):
+        if not np.array_equal(a["textures"][f], g["textures"][f]):
+            return "textures." + f
+    return None
+
+
+def test_obj_reader_cases_load_like_the_reference(tmp_path):
+    """host/obj_reader.cpp on the inputs of tests/obj_cases.py — number syntax and rounding, material-name tokenising, texture
+    options, dropped faces, quad diagonals, ear clipping of concave polygons, line ends ... and 30 generated scenes — against what
+    the reference's own loader (tinyobjloader + Scene::Load + Bvh::BuildCPU) made of the same files
+    (tests/golden/make_obj_fixtures.py)."""
+    from tests import obj_cases
+    from tests.golden.make_obj_fixtures import all_cases
+    expected = np.load(os.path.join(REPO, "tests", "golden", "obj", "expected.npz"))
+    n = 0
+    for name, files in all_cases():
+        a = _scene_arrays_from_obj(obj_cases.write_case(str(tmp_path / name), files))
+        g = {k: expected[name + ":" + k] for k in ("triangles", "materials", "textures")}
+        assert _same_scene_arrays(a, g) is None, (name, _same_scene_arrays(a, g))
+        n += 1
+    assert n >= 60
+    # the number reader on its own: digit accumulation, not strtod
+    assert hostapi.obj_parse_number("1.9662156701087952") == 1.9662156701087954 != float("1.9662156701087952")
+    assert hostapi.obj_parse_number("1.5x") == 1.5 and hostapi.obj_parse_number("-.25") == -0.25 and hostapi.obj_parse_number("5.") == 5.0
+    assert hostapi.obj_parse_number("1e") is None and hostapi.obj_parse_number("abc") is None and hostapi.obj_parse_number("-") is None
+    assert hostapi.obj_parse_number("1.5e+1") == 15.0 and hostapi.obj_parse_number("1E-2") == 0.01
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_ASSETS), reason="the reference's own loader only exists in the build container")
+def test_obj_reader_matches_the_reference_loader_live(tmp_path):
+    """Fresh generated scenes (other seeds than the committed expectations) and 120 000 numbers in ten notations through the
+    reference's own loader (oracle/_ref) and through host/obj_reader.cpp."""
+    from oracle import refbind
+    from tests import obj_cases
+    if not refbind.available():
+        pytest.skip("oracle/_ref/libref.so not built")
+
+    def reference_arrays(obj):
+        return refbind.RefRenderer().open_obj("/root/reference", obj).scene()
+    k = 0
+    for seed in range(100, 112):
+        for features in (("quads", "polys"), ("quads", "polys", "neg", "groups", "tabs", "crlf", "vcolor", "badmtl", "smooth")):
+            obj = obj_cases.write_case(str(tmp_path / ("r%d" % k)), obj_cases.random_scene(seed, features))
+            assert _same_scene_arrays(_scene_arrays_from_obj(obj), reference_arrays(obj)) is None, (seed, features)
+            k += 1
+    rng = np.random.default_rng(9)
+    vals = np.concatenate([rng.uniform(-3, 3, 60000), rng.normal(0, 100, 30000), 10.0 ** rng.uniform(-6, 4, 30000)])
+    rng.shuffle(vals)
+    notations = ["%.6f", "%.9f", "%.4e", "%.3f", "%.12g", "%.17g", "%.8f", "%.10e", "%.7f", "%.15f"]
+    toks = [notations[i % len(notations)] % v for i, v in enumerate(vals)]
+    lines = ["mtllib s.mtl", "vn 0 0 1", "usemtl a"] + ["v %s %s %s" % tuple(toks[3 * i: 3 * i + 3]) for i in range(len(toks) // 3)]
+    lines += ["f %d//1 %d//1 %d//1" % (i + 1, i + 2, i + 3) for i in range(0, len(toks) // 3 - 2, 3)]
+    obj = obj_cases.write_case(str(tmp_path / "numbers"), {"s.obj": "\n".join(lines) + "\n", "s.mtl": "newmtl a\nKd 0.5 0.5 0.5\n"})
+    assert _same_scene_arrays(_scene_arrays_from_obj(obj), reference_arrays(obj)) is None
+
+
 TEXTURE_DIR = os.path.join(REPO, "tests", "golden", "textures")
 
 
