@@ -6,7 +6,8 @@ compiled into oracle/_ref) makes of the OBJ / MTL inputs of tests/obj_cases.py.
     python tests/golden/make_obj_fixtures.py          (where /root/reference and oracle/_ref/libref.so exist)
 
 Writes tests/golden/obj/expected.npz: per case the triangle array (leaf order of the reference's BVH), the packed materials
-and the texture table.  tests/test_host.py::test_obj_reader_cases_load_like_the_reference loads the same inputs (re-created
+and the texture table; and bvh_soups.json: digests of the trees Bvh::BuildCPU built over ten generated triangle soups
+(uniform, clustered, repeated centroids, regular grid, one axis; 3 000 and 20 000 triangles).  tests/test_host.py::test_obj_reader_cases_load_like_the_reference loads the same inputs (re-created
 from tests/obj_cases.py, nothing but the expectations is stored) through host/obj_reader.cpp and compares.
 """
 import os
@@ -42,6 +43,16 @@ def main():
         arrays[name + ":textures"] = sc["textures"]
         print(f"{name:60s} {len(sc['triangles']):4d} triangles {len(sc['materials'])} materials {len(sc['textures'])} textures")
     np.savez_compressed(os.path.join(OUT, "expected.npz"), **arrays)
+    # BVH builder inputs: only a digest of the reference's tree is stored
+    import json
+    digests = {}
+    for mode, seed, n in obj_cases.SOUP_CASES:
+        with tempfile.TemporaryDirectory() as tmp:
+            obj = obj_cases.write_case(tmp, obj_cases.triangle_soup(mode, seed, n))
+            digests["%s_%d_%d" % (mode, seed, n)] = obj_cases.tree_digest(RefRenderer().open_obj("/root/reference", obj).scene())
+        print(mode, seed, n, digests["%s_%d_%d" % (mode, seed, n)][:24])
+    with open(os.path.join(OUT, "bvh_soups.json"), "w") as f:
+        json.dump(digests, f, indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":

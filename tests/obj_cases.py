@@ -143,3 +143,42 @@ def write_case(directory, files, rng=None):
         Image.fromarray(rng.integers(0, 256, (4, 4, 3)).astype(np.uint8)).save(os.path.join(directory, "b c.png"))
         Image.fromarray(rng.integers(0, 256, (4, 4, 4)).astype(np.uint8)).save(os.path.join(directory, "d.tga"))
     return os.path.join(directory, "s.obj")
+
+
+SOUP_CASES = [(mode, seed, n) for mode in ("uniform", "clusters", "duplicates", "grid", "line") for seed, n in ((1, 3000), (2, 20000))]
+
+
+def triangle_soup(mode, seed, n):
+    """OBJ text of n separate triangles whose centroids are spread uniformly / in tight clusters / on few repeated points (leaves
+    of many identical centroids) / on a regular grid (ties in every SAH bucket) / along one axis: inputs for the BVH builder."""
+    rng = np.random.default_rng(seed)
+    if mode == "uniform":
+        c = rng.uniform(-5, 5, (n, 3)); e = rng.normal(0, 0.2, (n, 3, 3))
+    elif mode == "clusters":
+        cc = rng.uniform(-5, 5, (20, 3)); c = cc[rng.integers(0, 20, n)] + rng.normal(0, 0.05, (n, 3)); e = rng.normal(0, 0.02, (n, 3, 3))
+    elif mode == "duplicates":
+        base = rng.uniform(-5, 5, (n // 50 + 1, 3)); c = base[rng.integers(0, len(base), n)]; e = np.tile(rng.normal(0, 0.2, (1, 3, 3)), (n, 1, 1))
+    elif mode == "grid":
+        g = int(np.ceil(n ** (1 / 3)))
+        c = np.stack(np.unravel_index(np.arange(n), (g, g, g)), -1).astype(float)
+        e = np.tile(np.array([[0, 0, 0], [0.5, 0, 0], [0, 0.5, 0]])[None], (n, 1, 1)) - 0.2
+    else:
+        c = np.stack([np.linspace(0, 100, n), np.zeros(n), np.zeros(n)], -1); e = rng.normal(0, 0.2, (n, 3, 3))
+    p = (c[:, None, :] + e).reshape(-1, 3)
+    lines = ["mtllib s.mtl", "vn 0 0 1", "usemtl a"] + ["v %.6f %.6f %.6f" % tuple(v) for v in p]
+    lines += ["f %d//1 %d//1 %d//1" % (3 * i + 1, 3 * i + 2, 3 * i + 3) for i in range(n)]
+    return {"s.obj": "\n".join(lines) + "\n", "s.mtl": "newmtl a\nKd 0.5 0.5 0.5\n"}
+
+
+def tree_digest(scene):
+    """sha256 over the node array (bounds bits, offset, primitive count / axis) and the leaf-ordered vertex positions."""
+    import hashlib
+    h = hashlib.sha256()
+    nodes, tris = scene["nodes"], scene["triangles"]
+    for k in ("bounds_min", "bounds_max"):
+        h.update(np.ascontiguousarray(nodes[k][:, :3]).view(np.uint32).tobytes())
+    for k in ("offset", "num_primitives_axis"):
+        h.update(np.ascontiguousarray(nodes[k]).tobytes())
+    for v in ("v1", "v2", "v3"):
+        h.update(np.ascontiguousarray(tris[v]["position"][:, :3]).view(np.uint32).tobytes())
+    return "%d:%s" % (len(nodes), h.hexdigest())

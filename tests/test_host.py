@@ -259,6 +259,20 @@ def test_obj_reader_cases_load_like_the_reference(tmp_path):
     assert hostapi.obj_parse_number("1.5e+1") == 15.0 and hostapi.obj_parse_number("1E-2") == 0.01
 
 
+def test_bvh_builder_on_generated_soups(tmp_path):
+    """host/bvh.cpp (SAH buckets, leaf rule, child order, OpenMP tasks above 8192 primitives) on ten generated triangle soups —
+    uniform, clustered, many identical centroids, a regular grid (ties in every bucket), one axis — against digests of the trees
+    the reference's Bvh::BuildCPU built from the same OBJ text (tests/golden/make_obj_fixtures.py)."""
+    import json
+    from tests import obj_cases
+    with open(os.path.join(REPO, "tests", "golden", "obj", "bvh_soups.json")) as f:
+        expected = json.load(f)
+    for mode, seed, n in obj_cases.SOUP_CASES:
+        key = "%s_%d_%d" % (mode, seed, n)
+        obj = obj_cases.write_case(str(tmp_path / key), obj_cases.triangle_soup(mode, seed, n))
+        assert obj_cases.tree_digest(_scene_arrays_from_obj(obj)) == expected[key], key
+
+
 @pytest.mark.skipif(not os.path.isdir(REF_ASSETS), reason="the reference's own loader only exists in the build container")
 def test_obj_reader_matches_the_reference_loader_live(tmp_path):
     """Fresh generated scenes (other seeds than the committed expectations) and 120 000 numbers in ten notations through the
