@@ -217,7 +217,9 @@ bool read_flat(std::vector<Rgbe>& line, size_t from, FILE* f)
         if (r == 1 && g == 1 && b == 1)
         {
             if (i == 0) return false;             // a run marker needs a previous pixel to repeat
-            for (int n = e << rshift; n > 0 && i < line.size(); --n) { line[i] = line[i - 1]; ++i; }
+            // the reference keeps the repeat count in an unsigned char (hdr_loader.cpp:192): a second marker in a row, whose count
+            // the format shifts left by 8, repeats nothing there — and so nothing here
+            for (int n = (unsigned char)(e << rshift); n > 0 && i < line.size(); --n) { line[i] = line[i - 1]; ++i; }
             rshift += 8;
         }
         else { line[i].c[0] = (unsigned char)r; line[i].c[1] = (unsigned char)g; line[i].c[2] = (unsigned char)b; line[i].c[3] = (unsigned char)e; ++i; rshift = 0; }

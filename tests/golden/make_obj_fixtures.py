@@ -7,7 +7,8 @@ compiled into oracle/_ref) makes of the OBJ / MTL inputs of tests/obj_cases.py.
 
 Writes tests/golden/obj/expected.npz: per case the triangle array (leaf order of the reference's BVH), the packed materials
 and the texture table; and bvh_soups.json: digests of the trees Bvh::BuildCPU built over ten generated triangle soups
-(uniform, clustered, repeated centroids, regular grid, one axis; 3 000 and 20 000 triangles).  tests/test_host.py::test_obj_reader_cases_load_like_the_reference loads the same inputs (re-created
+(uniform, clustered, repeated centroids, regular grid, one axis; 3 000 and 20 000 triangles); and hdr_files.json: digests of
+the environment images LoadHDR read from the files of tests/hdr_cases.py.  tests/test_host.py::test_obj_reader_cases_load_like_the_reference loads the same inputs (re-created
 from tests/obj_cases.py, nothing but the expectations is stored) through host/obj_reader.cpp and compares.
 """
 import os
@@ -28,6 +29,18 @@ def all_cases():
         yield name, files
     for seed, features in obj_cases.RANDOM_CASES:
         yield "random_%d_%s" % (seed, "_".join(features) or "plain"), obj_cases.random_scene(seed, features)
+
+
+def reference_env(tmp, hdr_bytes):
+    """(env, width, height) as the reference reads `hdr_bytes`: Scene::Finalize opens assets/ibl/CGSkies_0036_free.hdr relative to the
+    working directory (scene.cpp:360), so the file is placed under that name in a scratch root."""
+    from oracle.refbind import RefRenderer
+    os.makedirs(os.path.join(tmp, "assets", "ibl"))
+    with open(os.path.join(tmp, "assets", "ibl", "CGSkies_0036_free.hdr"), "wb") as f:
+        f.write(hdr_bytes)
+    obj = obj_cases.write_case(tmp, obj_cases.QUIRK_CASES["plain"])
+    sc = RefRenderer().open_obj(tmp, obj).scene()
+    return sc["env"], int(sc["env_width"]), int(sc["env_height"])
 
 
 def main():
@@ -52,6 +65,15 @@ def main():
             digests["%s_%d_%d" % (mode, seed, n)] = obj_cases.tree_digest(RefRenderer().open_obj("/root/reference", obj).scene())
         print(mode, seed, n, digests["%s_%d_%d" % (mode, seed, n)][:24])
     with open(os.path.join(OUT, "bvh_soups.json"), "w") as f:
+        json.dump(digests, f, indent=1, sort_keys=True)
+    # environment maps: digests of what the reference's LoadHDR (through Scene::Finalize) read
+    from tests import hdr_cases
+    digests = {}
+    for name, data in hdr_cases.cases().items():
+        with tempfile.TemporaryDirectory() as tmp:
+            digests[name] = hdr_cases.digest(*reference_env(tmp, data))
+        print(name, digests[name][:28])
+    with open(os.path.join(OUT, "hdr_files.json"), "w") as f:
         json.dump(digests, f, indent=1, sort_keys=True)
 
 

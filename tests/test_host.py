@@ -259,6 +259,31 @@ def test_obj_reader_cases_load_like_the_reference(tmp_path):
     assert hostapi.obj_parse_number("1.5e+1") == 15.0 and hostapi.obj_parse_number("1E-2") == 0.01
 
 
+def _load_env(path):
+    s = hostapi.HostScene(PROC_OBJ)
+    s.add_directional_light((0, 0, 1), (1, 1, 1))
+    s.finalize(env_path=path)
+    a = s.arrays()
+    s.close()
+    return a["env"], int(a["env_width"]), int(a["env_height"])
+
+
+def test_hdr_reader_cases_load_like_the_reference(tmp_path):
+    """LoadHDR on the files of tests/hdr_cases.py (flat / new / old run-length coding, window edges of the new coding, two repeat
+    markers in a row — where the reference keeps the count in 8 bits —, look-alike scanline starts, a file cut short) against
+    digests of what the reference's LoadHDR read (tests/golden/make_obj_fixtures.py)."""
+    import json
+    from tests import hdr_cases
+    with open(os.path.join(REPO, "tests", "golden", "obj", "hdr_files.json")) as f:
+        expected = json.load(f)
+    files = hdr_cases.cases()
+    assert set(files) == set(expected) and len(files) >= 20
+    for name, data in files.items():
+        with open(tmp_path / "e.hdr", "wb") as f:
+            f.write(data)
+        assert hdr_cases.digest(*_load_env(str(tmp_path / "e.hdr"))) == expected[name], name
+
+
 def test_bvh_builder_on_generated_soups(tmp_path):
     """host/bvh.cpp (SAH buckets, leaf rule, child order, OpenMP tasks above 8192 primitives) on ten generated triangle soups —
     uniform, clustered, many identical centroids, a regular grid (ties in every bucket), one axis — against digests of the trees
@@ -299,6 +324,14 @@ def test_obj_reader_matches_the_reference_loader_live(tmp_path):
     lines += ["f %d//1 %d//1 %d//1" % (i + 1, i + 2, i + 3) for i in range(0, len(toks) // 3 - 2, 3)]
     obj = obj_cases.write_case(str(tmp_path / "numbers"), {"s.obj": "\n".join(lines) + "\n", "s.mtl": "newmtl a\nKd 0.5 0.5 0.5\n"})
     assert _same_scene_arrays(_scene_arrays_from_obj(obj), reference_arrays(obj)) is None
+    # environment maps, another seed than the committed digests
+    from tests import hdr_cases
+    from tests.golden.make_obj_fixtures import reference_env
+    for i, (name, data) in enumerate(hdr_cases.cases(seed=31).items()):
+        with open(tmp_path / "e.hdr", "wb") as f:
+            f.write(data)
+        root = tmp_path / ("env%d" % i); root.mkdir()
+        assert hdr_cases.digest(*_load_env(str(tmp_path / "e.hdr"))) == hdr_cases.digest(*reference_env(str(root), data)), name
 
 
 TEXTURE_DIR = os.path.join(REPO, "tests", "golden", "textures")
