@@ -95,10 +95,9 @@ int rth_bvh_build(RtTriangle* triangles, size_t n, RtLinearBVHNode* nodes_out, s
 {
     try
     {
-        std::vector<Triangle> t(triangles, triangles + n);
+        static_assert(sizeof(Triangle) == sizeof(RtTriangle), "layout");
         Bvh bvh;
-        bvh.BuildCPU(t);
-        memcpy(triangles, t.data(), n * sizeof(Triangle));
+        bvh.Build(reinterpret_cast<Triangle*>(triangles), n);
         memcpy(nodes_out, bvh.GetNodes().data(), bvh.GetNodes().size() * sizeof(LinearBVHNode));
         *n_nodes = bvh.GetNodes().size();
         if (max_depth) *max_depth = bvh.MaxDepth();

@@ -79,12 +79,14 @@ def obj_parse_number(text: str):
 def build_bvh(triangles):
     """Host SAH build over a triangle array -> (triangles in leaf order, LinearBVHNode[], max depth)."""
     L = load_library()
-    t = np.ascontiguousarray(triangles, dtype=TRIANGLE_DT).copy()
-    nodes = np.zeros(2 * t.shape[0], dtype=NODE_DT)
+    src = np.ascontiguousarray(triangles, dtype=TRIANGLE_DT)
+    t = np.empty(src.shape, dtype=TRIANGLE_DT)
+    t.view(np.uint8)[:] = src.view(np.uint8)                   # byte copy: numpy copies structured records field by field otherwise
+    nodes = np.empty(2 * t.shape[0], dtype=NODE_DT)          # a binary tree over n leaves has at most 2n - 1 nodes
     n, depth = C.c_size_t(), C.c_uint32()
     if L.rth_bvh_build(t.ctypes.data, t.shape[0], nodes.ctypes.data, C.byref(n), C.byref(depth)) != 0:
         raise _err(L)
-    return t, nodes[: n.value].copy(), depth.value
+    return t, nodes[: n.value], depth.value
 
 
 class HostScene:

@@ -36,7 +36,7 @@ def replicate(base_triangles: np.ndarray, copies: int = 183, grid: int = 14, see
         p = (pos - centre * [1, 1, 0]) @ rot.T + cell
         n = nrm @ rot.T
         blk = out[k * len(t):(k + 1) * len(t)]
-        blk[:] = t
+        blk.view(np.uint8)[:] = t.view(np.uint8)               # (a record-wise copy of a structured array is ~20x slower)
         for j, v in enumerate(("v1", "v2", "v3")):
             blk[v]["position"][:, :3] = p[:, j].astype(np.float32)
             blk[v]["normal"][:, :3] = n[:, j].astype(np.float32)

@@ -145,12 +145,13 @@ def write_case(directory, files, rng=None):
     return os.path.join(directory, "s.obj")
 
 
-SOUP_CASES = [(mode, seed, n) for mode in ("uniform", "clusters", "duplicates", "grid", "line") for seed, n in ((1, 3000), (2, 20000))]
+SOUP_CASES = [(mode, seed, n) for mode in ("uniform", "clusters", "duplicates", "grid", "line", "signed_zeros") for seed, n in ((1, 3000), (2, 20000))]
 
 
 def triangle_soup(mode, seed, n):
     """OBJ text of n separate triangles whose centroids are spread uniformly / in tight clusters / on few repeated points (leaves
-    of many identical centroids) / on a regular grid (ties in every SAH bucket) / along one axis: inputs for the BVH builder."""
+    of many identical centroids) / on a regular grid (ties in every SAH bucket) / along one axis / on a few values including
+    both zeros: inputs for the BVH builder."""
     rng = np.random.default_rng(seed)
     if mode == "uniform":
         c = rng.uniform(-5, 5, (n, 3)); e = rng.normal(0, 0.2, (n, 3, 3))
@@ -162,8 +163,11 @@ def triangle_soup(mode, seed, n):
         g = int(np.ceil(n ** (1 / 3)))
         c = np.stack(np.unravel_index(np.arange(n), (g, g, g)), -1).astype(float)
         e = np.tile(np.array([[0, 0, 0], [0.5, 0, 0], [0, 0.5, 0]])[None], (n, 1, 1)) - 0.2
-    else:
+    elif mode == "line":
         c = np.stack([np.linspace(0, 100, n), np.zeros(n), np.zeros(n)], -1); e = rng.normal(0, 0.2, (n, 3, 3))
+    else:       # coordinates from a small set that holds both zeros: the sign of a zero bound depends on the order of the unions
+        values = np.array([-0.0, 0.0, -0.0, 0.0, 1.0, -1.0, 2.0, -2.0, 0.5])
+        c = np.zeros((n, 3)); e = values[rng.integers(0, len(values), (n, 3, 3))]
     p = (c[:, None, :] + e).reshape(-1, 3)
     lines = ["mtllib s.mtl", "vn 0 0 1", "usemtl a"] + ["v %.6f %.6f %.6f" % tuple(v) for v in p]
     lines += ["f %d//1 %d//1 %d//1" % (3 * i + 1, 3 * i + 2, 3 * i + 3) for i in range(n)]

@@ -285,8 +285,9 @@ def test_hdr_reader_cases_load_like_the_reference(tmp_path):
 
 
 def test_bvh_builder_on_generated_soups(tmp_path):
-    """host/bvh.cpp (SAH buckets, leaf rule, child order, OpenMP tasks above 8192 primitives) on ten generated triangle soups —
-    uniform, clustered, many identical centroids, a regular grid (ties in every bucket), one axis — against digests of the trees
+    """host/bvh.cpp (SAH buckets, leaf rule, child order; child tasks, chunked passes at the top of the tree) on twelve generated
+    triangle soups — uniform, clustered, many identical centroids, a regular grid (ties in every bucket), one axis, coordinates
+    with both zeros — against digests of the trees
     the reference's Bvh::BuildCPU built from the same OBJ text (tests/golden/make_obj_fixtures.py)."""
     import json
     from tests import obj_cases
@@ -296,6 +297,20 @@ def test_bvh_builder_on_generated_soups(tmp_path):
         key = "%s_%d_%d" % (mode, seed, n)
         obj = obj_cases.write_case(str(tmp_path / key), obj_cases.triangle_soup(mode, seed, n))
         assert obj_cases.tree_digest(_scene_arrays_from_obj(obj)) == expected[key], key
+    # the tree does not depend on how the build is spread over threads: (threads, nodes above this size run their passes in
+    # chunks, children of nodes above this size become tasks)
+    saved = {k: os.environ.get(k) for k in ("RT_BVH_THREADS", "RT_BVH_PARALLEL_NODE", "RT_BVH_TASK_NODE")}
+    try:
+        for threads, par_node, task_node in ((1, 1000, 200), (3, 500, 100), (8, 1000, 200), (5, 64, 16), (8, 1 << 30, 1 << 30)):
+            os.environ.update(RT_BVH_THREADS=str(threads), RT_BVH_PARALLEL_NODE=str(par_node), RT_BVH_TASK_NODE=str(task_node))
+            for mode, seed, n in obj_cases.SOUP_CASES:
+                if n > 3000 and threads not in (3, 8):
+                    continue
+                key = "%s_%d_%d" % (mode, seed, n)
+                assert obj_cases.tree_digest(_scene_arrays_from_obj(str(tmp_path / key / "s.obj"))) == expected[key], (key, threads, par_node, task_node)
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_ASSETS), reason="the reference's own loader only exists in the build container")
