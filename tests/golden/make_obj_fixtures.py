@@ -24,11 +24,18 @@ from tests import obj_cases  # noqa: E402
 OUT = os.path.join(REPO, "tests", "golden", "obj")
 
 
+# cases loaded with the reference's --scale / --flip_yz options (main.cpp:45-47; the Bistro command line uses 0.01 and 1)
+LOAD_OPTIONS = {"scaled_flipped_quads_polys": (0.01, True), "scaled_groups": (3.5, False), "flipped_plain": (1.0, True)}
+
+
 def all_cases():
     for name, files in obj_cases.QUIRK_CASES.items():
         yield name, files
     for seed, features in obj_cases.RANDOM_CASES:
         yield "random_%d_%s" % (seed, "_".join(features) or "plain"), obj_cases.random_scene(seed, features)
+    yield "scaled_flipped_quads_polys", obj_cases.random_scene(50, ("quads", "polys", "neg"))
+    yield "scaled_groups", obj_cases.random_scene(51, ("groups", "tabs", "quads"))
+    yield "flipped_plain", obj_cases.random_scene(52, ())
 
 
 def reference_env(tmp, hdr_bytes):
@@ -50,7 +57,8 @@ def main():
     for name, files in all_cases():
         with tempfile.TemporaryDirectory() as tmp:
             obj = obj_cases.write_case(tmp, files)
-            sc = RefRenderer().open_obj("/root/reference", obj).scene()
+            scale, flip = LOAD_OPTIONS.get(name, (1.0, False))
+            sc = RefRenderer().open_obj("/root/reference", obj, scale=scale, flip_yz=flip).scene()
         arrays[name + ":triangles"] = sc["triangles"]
         arrays[name + ":materials"] = sc["materials"]
         arrays[name + ":textures"] = sc["textures"]

@@ -209,8 +209,8 @@ def test_image_textures_png_tga(tmp_path):
         hostapi.HostScene(_textured_obj(tmp_path, ["x.jpg"]))
 
 
-def _scene_arrays_from_obj(obj_path):
-    s = hostapi.HostScene(obj_path)
+def _scene_arrays_from_obj(obj_path, scale=1.0, flip_yz=False):
+    s = hostapi.HostScene(obj_path, scale=scale, flip_yz=flip_yz)
     s.add_directional_light((-0.6, -1.5, 3.5), (15, 10, 5))
     s.build_bvh()
     s.finalize(env=np.zeros(4, dtype=np.float32), env_width=1, env_height=1)
@@ -239,15 +239,16 @@ def _same_scene_arrays(a, g):
 
 def test_obj_reader_cases_load_like_the_reference(tmp_path):
     """host/obj_reader.cpp on the inputs of tests/obj_cases.py — number syntax and rounding, material-name tokenising, texture
-    options, dropped faces, quad diagonals, ear clipping of concave polygons, line ends ... and 30 generated scenes — against what
+    options, dropped faces, quad diagonals, ear clipping of concave polygons, line ends ..., 30 generated scenes, the --scale and
+    --flip_yz load options — against what
     the reference's own loader (tinyobjloader + Scene::Load + Bvh::BuildCPU) made of the same files
     (tests/golden/make_obj_fixtures.py)."""
     from tests import obj_cases
-    from tests.golden.make_obj_fixtures import all_cases
+    from tests.golden.make_obj_fixtures import all_cases, LOAD_OPTIONS
     expected = np.load(os.path.join(REPO, "tests", "golden", "obj", "expected.npz"))
     n = 0
     for name, files in all_cases():
-        a = _scene_arrays_from_obj(obj_cases.write_case(str(tmp_path / name), files))
+        a = _scene_arrays_from_obj(obj_cases.write_case(str(tmp_path / name), files), *LOAD_OPTIONS.get(name, (1.0, False)))
         g = {k: expected[name + ":" + k] for k in ("triangles", "materials", "textures")}
         assert _same_scene_arrays(a, g) is None, (name, _same_scene_arrays(a, g))
         n += 1
