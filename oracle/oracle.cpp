@@ -160,6 +160,33 @@ inline Ray RayGeneration(uint32_t pixel_idx, uint32_t width, uint32_t height, co
 // ------------------------------------------------------------------ traversal
 struct TraceCounters { uint64_t nodes_visited, tris_tested; };
 
+#ifdef ORACLE_FMA_TRAVERSAL
+// Build variant liboracle_fma.so (make fma): a CPU MODEL of the CUDA kernels' -DRT_FMA_TRAVERSAL experiment build
+// (raytracing_b200/csrc/rt_traverse.cuh: slab planes as fma(plane, inv, -(o * inv)), cross and dot products of the triangle test
+// contracted the same way).  It is not part of any parity test and nothing ships with it: tools/fma_sensitivity.py uses it to
+// report how far a contracted traversal moves the image (profiles/r02_fma_sensitivity.txt).
+inline float fdot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+inline V3 fcross(V3 a, V3 b) { return v3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x))); }
+inline bool RayTriangleFma(const Ray& ray, V3 p1, V3 p2, V3 p3, float* u_out, float* v_out, float* t_out)
+{
+    V3 e1 = p2 - p1, e2 = p3 - p1;
+    V3 pvec = fcross(ray.d, e2);
+    float det = fdot(e1, pvec);
+    if (det < 1e-8f || -det > 1e-8f) return false;
+    float inv_det = 1.0f / det;
+    V3 tvec = ray.o - p1;
+    float u = fdot(tvec, pvec) * inv_det;
+    if (u < 0.0f || u > 1.0f) return false;
+    V3 qvec = fcross(tvec, e1);
+    float v = fdot(ray.d, qvec) * inv_det;
+    if (v < 0.0f || u + v > 1.0f) return false;
+    float t = fdot(e2, qvec) * inv_det;
+    if (t < ray.tmin || t > ray.tmax) return false;
+    *u_out = u; *v_out = v; *t_out = t;
+    return true;
+}
+#endif
+
 // kernels/cl/trace_bvh.cl:28-73 — back-face culling (det < 1e-8 rejects), inclusive edges
 inline bool RayTriangle(const Ray& ray, V3 p1, V3 p2, V3 p3, float* u_out, float* v_out, float* t_out)
 {
@@ -192,6 +219,18 @@ inline bool RayBounds(const RtLinearBVHNode& n, V3 o, V3 inv_dir, float t_min, f
     return tmax >= tmin;
 }
 
+#ifdef ORACLE_FMA_TRAVERSAL
+inline bool RayBoundsFma(const RtLinearBVHNode& n, V3 o, V3 inv_dir, float t_min, float t_max)
+{
+    V3 noi = v3(-(o.x * inv_dir.x), -(o.y * inv_dir.y), -(o.z * inv_dir.z));
+    V3 t0 = v3(fmaf(n.bounds_min.x, inv_dir.x, noi.x), fmaf(n.bounds_min.y, inv_dir.y, noi.y), fmaf(n.bounds_min.z, inv_dir.z, noi.z));
+    V3 t1 = v3(fmaf(n.bounds_max.x, inv_dir.x, noi.x), fmaf(n.bounds_max.y, inv_dir.y, noi.y), fmaf(n.bounds_max.z, inv_dir.z, noi.z));
+    float lo = rt_fmaxf(rt_fmaxf(rt_fminf(t0.x, t1.x), rt_fminf(t0.y, t1.y)), rt_fminf(t0.z, t1.z));
+    float hi = rt_fminf(rt_fminf(rt_fmaxf(t0.x, t1.x), rt_fmaxf(t0.y, t1.y)), rt_fmaxf(t0.z, t1.z));
+    return rt_fminf(hi, t_max) >= rt_fmaxf(lo, t_min);
+}
+#endif
+
 // kernels/cl/trace_bvh.cl:99-211.  any_hit == the -D SHADOW_RAYS variant.
 // Returns primitive id (closest) or 0 (any hit) / RT_INVALID_ID.
 inline uint32_t TraceBvh(const Scene& sc, Ray ray, bool any_hit, RtHit* hit_out, TraceCounters* ctr)
@@ -203,11 +242,21 @@ inline uint32_t TraceBvh(const Scene& sc, Ray ray, bool any_hit, RtHit* hit_out,
     int to_visit = 0, cur = 0;
     int stack[64];
     uint64_t nv = 0, nt = 0;
+#ifdef ORACLE_FMA_TRAVERSAL
+    // as the experiment build: rays with a non-finite component and the root box keep the exact arithmetic
+    const float fin = ((ray.o.x + ray.o.y) + ray.o.z) + ((ray.d.x + ray.d.y) + ray.d.z);
+    const bool contracted = std::fabs(fin) <= 3.0e38f;
+#define ORC_BOUNDS(node, index) ((contracted && (index) != 0) ? RayBoundsFma(node, ray.o, inv_dir, ray.tmin, ray.tmax) : RayBounds(node, ray.o, inv_dir, ray.tmin, ray.tmax))
+#define ORC_TRIANGLE(...) (contracted ? RayTriangleFma(__VA_ARGS__) : RayTriangle(__VA_ARGS__))
+#else
+#define ORC_BOUNDS(node, index) RayBounds(node, ray.o, inv_dir, ray.tmin, ray.tmax)
+#define ORC_TRIANGLE(...) RayTriangle(__VA_ARGS__)
+#endif
     for (;;)
     {
         const RtLinearBVHNode& node = sc.nodes[cur];
         ++nv;
-        if (RayBounds(node, ray.o, inv_dir, ray.tmin, ray.tmax))
+        if (ORC_BOUNDS(node, cur))
         {
             int nprims = (int)(node.num_primitives_axis >> 16);
             if (nprims > 0)
@@ -216,7 +265,7 @@ inline uint32_t TraceBvh(const Scene& sc, Ray ray, bool any_hit, RtHit* hit_out,
                 {
                     const RtTriangle& t = sc.triangles[node.offset + i];
                     ++nt;
-                    if (RayTriangle(ray, v3(t.v1.position), v3(t.v2.position), v3(t.v3.position), &bu, &bv, &bt))
+                    if (ORC_TRIANGLE(ray, v3(t.v1.position), v3(t.v2.position), v3(t.v3.position), &bu, &bv, &bt))
                     {
                         prim = node.offset + i;
                         ray.tmax = bt;                                         // :157-162, later equal-t hit overwrites

@@ -37,10 +37,11 @@ def build():
 
 
 class Oracle:
-    def __init__(self, scene: dict):
-        if not os.path.exists(LIB):
+    def __init__(self, scene: dict, lib: str = None):
+        """lib: another build of oracle.cpp (tools/fma_sensitivity.py loads the contracted-traversal model liboracle_fma.so)."""
+        if lib is None and not os.path.exists(LIB):
             build()
-        L = self.lib = C.CDLL(LIB)
+        L = self.lib = C.CDLL(lib or LIB)
         L.orc_wang_hash.restype = C.c_uint32
         L.orc_wang_hash.argtypes = [C.c_uint32]
         L.orc_set_sampler_tables.argtypes = [C.c_void_p] * 3
