@@ -18,7 +18,7 @@ def _fmt(rng, v):
 
 
 def random_scene(seed, features=()):
-    """-> {"s.obj": text, "s.mtl": text}.  features: quads, polys, neg, groups, smooth, tabs, crlf, vcolor, badmtl."""
+    """-> {"s.obj": text, "s.mtl": text}.  features: quads, polys, neg, groups, smooth, tabs, crlf, vcolor, badmtl, tex."""
     rng = np.random.default_rng(seed)
     nv, nn, nt = int(rng.integers(8, 40)), int(rng.integers(3, 10)), int(rng.integers(3, 10))
     V = rng.uniform(-2, 2, (nv, 3)); N = rng.normal(size=(nn, 3)); N /= np.linalg.norm(N, axis=1)[:, None]; T = rng.uniform(0, 1, (nt, 2))
@@ -34,6 +34,9 @@ def random_scene(seed, features=()):
         if rng.random() < 0.5: mtl.append("Pm " + _fmt(rng, rng.uniform(0, 1)))
         if rng.random() < 0.3: mtl.append("Tf " + " ".join(_fmt(rng, x) for x in rng.uniform(0, 1, 3)))
         if rng.random() < 0.3: mtl += ["Ns 10", "d 0.5", "illum 2"]
+        if "tex" in features:          # image textures on random slots (write_case provides the three files)
+            for key in ("map_Kd", "map_Ks", "map_Pr", "map_Pm", "map_Ke", "map_d"):
+                if rng.random() < 0.35: mtl.append("%s %s" % (key, ("a.png", "b c.png", "d.tga")[int(rng.integers(0, 3))]))
     lines = ["mtllib s.mtl"]
     for v in V:
         l = "v " + " ".join(_fmt(rng, x) for x in v)
@@ -140,7 +143,7 @@ def write_case(directory, files, rng=None):
             f.write(text)
     if any(("a.png" in t or "b c.png" in t or "d.tga" in t) for t in files.values()):
         Image.fromarray(rng.integers(0, 256, (4, 4, 3)).astype(np.uint8)).save(os.path.join(directory, "a.png"))
-        Image.fromarray(rng.integers(0, 256, (4, 4, 3)).astype(np.uint8)).save(os.path.join(directory, "b c.png"))
+        Image.fromarray(rng.integers(0, 256, (5, 3, 3)).astype(np.uint8)).save(os.path.join(directory, "b c.png"))
         Image.fromarray(rng.integers(0, 256, (4, 4, 4)).astype(np.uint8)).save(os.path.join(directory, "d.tga"))
     return os.path.join(directory, "s.obj")
 

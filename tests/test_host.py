@@ -285,6 +285,34 @@ def test_hdr_reader_cases_load_like_the_reference(tmp_path):
         assert hdr_cases.digest(*_load_env(str(tmp_path / "e.hdr"))) == expected[name], name
 
 
+@pytest.mark.skipif(not os.path.isdir(REF_ASSETS), reason="the reference's own pipeline only exists in the build container")
+@pytest.mark.parametrize("seed", range(8))
+def test_generated_obj_renders_like_the_reference_pipeline(tmp_path, seed):
+    """A generated textured OBJ (quads, polygons, random materials, PNG / TGA maps) through BOTH whole pipelines on the CPU: the
+    reference's Scene + Bvh + kernels (oracle/_ref) against host loader + host BVH + oracle — primary hits and every radiance
+    bit.  (60 further seeds were run once with 0 differences.)"""
+    from oracle import refbind
+    from tests import obj_cases
+    if not refbind.available():
+        pytest.skip("oracle/_ref/libref.so not built")
+    features = ("quads", "polys", "tex", "neg", "groups") if seed % 2 else ("tex", "quads")
+    obj = obj_cases.write_case(str(tmp_path), obj_cases.random_scene(200 + seed, features))
+    w, h, mb = 96, 54, 5
+    cam = hostapi.default_camera(w, h); cam["position"][:3] = (0.2, -3.4, 0.4)
+    r = refbind.RefRenderer().open_obj("/root/reference", obj)
+    r.begin(w, h); r.set_camera(cam); r.set_max_bounces(mb); r.integrate()
+    s = hostapi.HostScene(obj)
+    s.add_directional_light((-0.6, -1.5, 3.5), (15, 10, 5)); s.build_bvh()
+    s.finalize(env_path=os.path.join(REF_ASSETS, "ibl", "CGSkies_0036_free.hdr"))
+    a = s.arrays(); s.close()
+    acc, hits, st = Oracle(a).render(cam, w, h, mb)
+    assert (hits["primitive_id"] != 0xFFFFFFFF).sum() > 100
+    assert np.array_equal(hits["primitive_id"], r.primary_hits()["primitive_id"])
+    assert np.array_equal(st["n_ext"][: mb + 1], r.stats()["n_ext"][: mb + 1])
+    assert np.array_equal(bits(acc[..., :3]), bits(r.radiance()[..., :3]))
+    r.close()
+
+
 def test_bvh_builder_on_generated_soups(tmp_path):
     """host/bvh.cpp (SAH buckets, leaf rule, child order; child tasks, chunked passes at the top of the tree) on twelve generated
     triangle soups — uniform, clustered, many identical centroids, a regular grid (ties in every bucket), one axis, coordinates
