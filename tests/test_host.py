@@ -290,7 +290,7 @@ def test_hdr_reader_cases_load_like_the_reference(tmp_path):
 def test_generated_obj_renders_like_the_reference_pipeline(tmp_path, seed):
     """A generated textured OBJ (quads, polygons, random materials, PNG / TGA maps) through BOTH whole pipelines on the CPU: the
     reference's Scene + Bvh + kernels (oracle/_ref) against host loader + host BVH + oracle — primary hits and every radiance
-    bit.  (60 further seeds were run once with 0 differences.)"""
+    bit.  (560 further seeds were run once with 0 differences.)"""
     from oracle import refbind
     from tests import obj_cases
     if not refbind.available():
