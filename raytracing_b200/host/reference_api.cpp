@@ -99,8 +99,10 @@ void Scene::Load(const char* filename, float scale, bool flip_yz)
     for (size_t i = 0; i < mesh.materials.size(); ++i)
     {
         const obj::Material& m = mesh.materials[i];
-        // scene.cpp:155-186: textures are loaded in this order (diffuse, specular, roughness, metallic, emissive, alpha), which fixes
-        // their indices
+        // scene.cpp:155-186: the order in which the textures are loaded fixes their indices.  Diffuse and specular are separate
+        // statements; the roughness / metallic pair and the emissive / alpha pair are each two arguments of ONE call
+        // (scene.cpp:172-184), and both g++ and MSVC evaluate the later argument first: metallic before roughness, alpha before
+        // emissive
         auto tex = [&](const std::string& name) -> std::uint32_t {
             return name.empty() ? kInvalidTextureIndex : (std::uint32_t)LoadTexture(folder + "/" + name);
         };
@@ -108,9 +110,9 @@ void Scene::Load(const char* filename, float scale, bool flip_yz)
         o.diffuse_albedo = PackAlbedo(std::pow(m.diffuse[0], kGamma), std::pow(m.diffuse[1], kGamma), std::pow(m.diffuse[2], kGamma), tex(m.diffuse_tex));
         o.specular_albedo = PackAlbedo(std::pow(m.specular[0], kGamma), std::pow(m.specular[1], kGamma), std::pow(m.specular[2], kGamma), tex(m.specular_tex));
         o.emission = PackRGBE(m.emission[0], m.emission[1], m.emission[2]);
-        const std::uint32_t rt = tex(m.roughness_tex), mt = tex(m.metallic_tex);
+        const std::uint32_t mt = tex(m.metallic_tex), rt = tex(m.roughness_tex);
         o.roughness_metalness = PackRoughnessMetalness(m.roughness, rt, m.metallic, mt);
-        const std::uint32_t et = tex(m.emissive_tex), at = tex(m.alpha_tex);
+        const std::uint32_t at = tex(m.alpha_tex), et = tex(m.emissive_tex);
         o.ior_emission_idx_transparency = PackIorEmissionIdxTransparency(m.ior, et, m.transmittance[0], at);
     }
 

@@ -108,6 +108,9 @@ QUIRK_CASES = {
     "texture_options": {"s.obj": "mtllib s.mtl\n" + _V + "usemtl a\n" + _T + "usemtl b\n" + _T + "usemtl c\n" + _T,
                         "s.mtl": "newmtl a\nKd 1 1 1\nmap_Kd -s 1 1 1 -o 0 0 0 -blendu on -mm 0 1 a.png\nmap_Ks -clamp on -bm 2 b c.png\nnewmtl b\n"
                                  "map_Ke -texres 512 -imfchan r -type sphere -colorspace sRGB d.tga\nmap_Pr -boost 1 -t 0 0 0 a.png\nnewmtl c\nmap_d -blendv off a.png\nmap_Pm b c.png\n"},
+    # two maps that are arguments of one call in the reference (scene.cpp:172-184): the later argument's file is loaded first
+    "texture_load_order": {"s.obj": "mtllib s.mtl\n" + _V + "usemtl a\n" + _T + "usemtl b\n" + _T,
+                           "s.mtl": "newmtl a\nKd 1 1 1\nmap_Pr a.png\nmap_Pm d.tga\nnewmtl b\nKd 1 1 1\nmap_Ke b c.png\nmap_d a.png\nmap_Kd d.tga\n"},
     "texture_name_with_blanks": {"s.obj": "mtllib s.mtl\n" + _V + "usemtl a\n" + _T, "s.mtl": "newmtl a\nmap_Kd b c.png   \n"},
     "two_mtllib_lines": {"s.obj": "mtllib s.mtl\nmtllib t.mtl\n" + _V + "usemtl a\n" + _T + "usemtl z\n" + _T, "s.mtl": _M, "t.mtl": "newmtl z\nKd 0.5 0.5 0\nnewmtl a\nKd 0 0 0.5\n"},
     "mtllib_several_names": {"s.obj": "mtllib missing.mtl t.mtl s.mtl\n" + _V + "usemtl a\n" + _T + "usemtl z\n" + _T, "s.mtl": _M, "t.mtl": "newmtl z\nKd 0.5 0.5 0\n"},
